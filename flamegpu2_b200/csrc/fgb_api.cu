@@ -1,0 +1,458 @@
+// fgb_api.cu -- C ABI entry points (include/flamegpu2_b200.h) of the sm_100a hot-path library.
+// Host launchers only: every entry point enqueues kernels on the caller's stream and returns.
+// There is no CPU fallback; without a CUDA device every call fails with FGB_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "fgb_binsort.cuh"
+#include "fgb_common.cuh"
+#include "fgb_compact.cuh"
+#include "fgb_scan.cuh"
+
+using namespace fgb;
+
+namespace {
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline bool vars_in_aligned(const fgb_var *vars, unsigned int nvars) {
+  for (unsigned int v = 0; v < nvars; ++v)
+    if (!aligned16(vars[v].in)) return false;
+  return true;
+}
+inline bool vars_out_aligned(const fgb_var *vars, unsigned int nvars) {
+  for (unsigned int v = 0; v < nvars; ++v)
+    if (!aligned16(vars[v].out)) return false;
+  return true;
+}
+
+int reserve_zeroed(DevBuf &b, size_t need) {
+  if (need <= b.bytes) return 0;
+  int r = b.reserve(need);
+  if (r) return r;
+  return static_cast<int>(cudaMemset(b.p, 0, b.bytes));
+}
+
+// approxExactlyDivisible<float> (include/flamegpu/detail/numeric.h:25-32)
+bool approx_exactly_divisible(float x, float y) {
+  const float scaled_eps = std::max(std::fabs(x), std::fabs(y)) * 1.1920928955078125e-07f;
+  const float v = std::fmod(x, y);
+  return v <= scaled_eps || v > y - scaled_eps;
+}
+
+inline int launch_ok() { return static_cast<int>(cudaPeekAtLastError()); }
+
+// worklist entries needed for n items: bins with more than kFixSmall items
+inline size_t worklist_bytes(unsigned int n) { return (static_cast<size_t>(n) / (kFixSmall + 1) + 1) * sizeof(uint32_t); }
+
+// The stable tail shared by fgb_build_index(STABLE) and fgb_sort_by_key:
+// per-bin index fix-up, then the gather that applies the permutation.
+int stable_tail(fgb_ctx *ctx, const uint32_t *pbm, unsigned int bins, uint32_t *perm, uint32_t *worklist,
+                uint32_t *ctrl, unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars,
+                cudaStream_t st) {
+  k_fix_small<<<(bins + 255) / 256, 256, 0, st>>>(pbm, bins, perm, worklist, ctrl);
+  k_fix_big<<<kNumSMs, 1024, 0, st>>>(pbm, perm, worklist, ctrl);
+  ctx->launches += 2;
+  if (nvars) {
+    VarTable vt;
+    int r = make_var_table(vars, nvars, &vt);
+    if (r) return r;
+    const bool vec = aligned16(perm) && vars_out_aligned(vars, nvars);
+    if (vec)
+      k_gather<true><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    else
+      k_gather<false><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    ctx->launches += 1;
+  }
+  return launch_ok();
+}
+
+template <int DIMS>
+int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                     const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, cudaStream_t st) {
+  fgb_ctx *ctx = sp->ctx;
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  KeySrc<DIMS> src{};
+  src.x = x;
+  src.y = y;
+  src.z = z;
+  src.keys = nullptr;
+  src.mask = 0;
+  src.g = Geo{sp->md.min[0], sp->md.min[1], sp->md.min[2], sp->md.radius, static_cast<int>(sp->md.grid_dim[0]),
+              static_cast<int>(sp->md.grid_dim[1]), static_cast<int>(sp->md.grid_dim[2])};
+  const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z)) && vars_in_aligned(vars, nvars);
+  const unsigned int grid = bin_grid(n);
+  const unsigned int B = sp->bin_count;
+  const bool stable = (flags & FGB_BUILD_STABLE) != 0;
+  if (stable) {
+    r = sp->perm.reserve(static_cast<size_t>(n) * 4);
+    if (r) return r;
+    r = sp->worklist.reserve(worklist_bytes(n));
+    if (r) return r;
+  }
+  if (vec)
+    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+  else
+    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
+  ctx->launches += 2;
+  uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
+  if (!stable) {
+    if (vec)
+      k_bin_scatter<DIMS, true, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr);
+    else
+      k_bin_scatter<DIMS, false, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr);
+    ctx->launches += 1;
+    return launch_ok();
+  }
+  if (vec)
+    k_bin_scatter<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm);
+  else
+    k_bin_scatter<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm);
+  ctx->launches += 1;
+  return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars,
+                     st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fgb_version(void) { return FGB_VERSION; }
+
+const char *fgb_error_string(fgb_status s) {
+  if (s > 0) return cudaGetErrorString(static_cast<cudaError_t>(s));
+  switch (s) {
+    case FGB_OK: return "ok";
+    case FGB_ERR_INVALID_ARG: return "invalid argument";
+    case FGB_ERR_TOO_MANY_VARS: return "too many variables (FGB_MAX_VARS)";
+    case FGB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case FGB_ERR_ALLOC: return "allocation failed";
+    case FGB_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown";
+  }
+}
+
+fgb_status fgb_ctx_create(int device, fgb_ctx **out) {
+  if (!out) return FGB_ERR_INVALID_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return FGB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return FGB_ERR_INVALID_ARG;
+  FGB_CHECK(cudaSetDevice(device));
+  fgb_ctx *c = new (std::nothrow) fgb_ctx();
+  if (!c) return FGB_ERR_ALLOC;
+  c->device = device;
+  *out = c;
+  return FGB_OK;
+}
+
+fgb_status fgb_ctx_destroy(fgb_ctx *ctx) {
+  if (!ctx) return FGB_OK;
+  for (auto &s : ctx->slot) {
+    s.tile_state.release();
+    s.sort_hist.release();
+    s.sort_cursor.release();
+    s.perm.release();
+    s.worklist.release();
+    s.ctrl.release();
+  }
+  delete ctx;
+  return FGB_OK;
+}
+
+unsigned long long fgb_launch_count(const fgb_ctx *ctx) { return ctx ? ctx->launches : 0ull; }
+
+fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
+                              fgb_spatial **out) {
+  if (!ctx || !out || !env_min || !env_max || (dims != 2 && dims != 3) || !(radius > 0.f)) return FGB_ERR_INVALID_ARG;
+  fgb_spatial *sp = new (std::nothrow) fgb_spatial();
+  if (!sp) return FGB_ERR_ALLOC;
+  sp->ctx = ctx;
+  sp->dims = dims;
+  fgb_spatial_metadata &md = sp->md;
+  std::memset(&md, 0, sizeof(md));
+  md.radius = radius;
+  md.wrap_compatible = true;
+  unsigned long long bins = 1;
+  for (int a = 0; a < 3; ++a) md.grid_dim[a] = 1;
+  for (int a = 0; a < dims; ++a) {
+    md.min[a] = env_min[a];
+    md.max[a] = env_max[a];
+    md.environment_width[a] = md.max[a] - md.min[a];
+    // static_cast<unsigned int>(ceil(environmentWidth / radius)), MessageSpatial3D.cu:47
+    md.grid_dim[a] = static_cast<unsigned int>(std::ceil(md.environment_width[a] / md.radius));
+    bins *= md.grid_dim[a];
+    md.wrap_compatible = md.wrap_compatible && approx_exactly_divisible(md.environment_width[a], md.radius);
+  }
+  if (bins == 0 || bins >= 0x7FFFFFFFull) {
+    delete sp;
+    return FGB_ERR_INVALID_ARG;
+  }
+  sp->bin_count = static_cast<unsigned int>(bins);
+  const size_t words = static_cast<size_t>(sp->bin_count) + 1;
+  sp->n_state = scan_num_tiles(sp->bin_count);
+  cudaError_t e = cudaMalloc(&sp->d_hist, words * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&md.PBM, words * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_state, static_cast<size_t>(sp->n_state) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_md, sizeof(fgb_spatial_metadata));
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_ctrl, 16);
+  if (e == cudaSuccess) e = cudaMemset(sp->d_hist, 0, words * 4);
+  if (e == cudaSuccess) e = cudaMemset(md.PBM, 0, words * 4);  // MessageSpatial3D.cu:77
+  if (e == cudaSuccess) e = cudaMemset(sp->d_state, 0, static_cast<size_t>(sp->n_state) * 8);
+  if (e == cudaSuccess) e = cudaMemset(sp->d_ctrl, 0, 16);
+  if (e == cudaSuccess) e = cudaMemcpy(sp->d_md, &md, sizeof(md), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    fgb_spatial_destroy(sp);
+    return static_cast<int>(e);
+  }
+  *out = sp;
+  return FGB_OK;
+}
+
+fgb_status fgb_spatial_destroy(fgb_spatial *sp) {
+  if (!sp) return FGB_OK;
+  if (sp->d_hist) cudaFree(sp->d_hist);
+  if (sp->md.PBM) cudaFree(sp->md.PBM);
+  if (sp->d_state) cudaFree(sp->d_state);
+  if (sp->d_md) cudaFree(sp->d_md);
+  if (sp->d_ctrl) cudaFree(sp->d_ctrl);
+  sp->perm.release();
+  sp->worklist.release();
+  delete sp;
+  return FGB_OK;
+}
+
+fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata *host_out, unsigned int *bin_count) {
+  if (!sp) return FGB_ERR_INVALID_ARG;
+  if (host_out) *host_out = sp->md;
+  if (bin_count) *bin_count = sp->bin_count;
+  return FGB_OK;
+}
+
+const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp) { return sp ? sp->d_md : nullptr; }
+
+fgb_status fgb_spatial_read_pbm(const fgb_spatial *sp, unsigned int *host_out, void *stream) {
+  if (!sp || !host_out) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FGB_CHECK(cudaMemcpyAsync(host_out, sp->md.PBM, (static_cast<size_t>(sp->bin_count) + 1) * 4, cudaMemcpyDeviceToHost,
+                            st));
+  FGB_CHECK(cudaStreamSynchronize(st));
+  return FGB_OK;
+}
+
+fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max) {
+  if (!sp) return FGB_ERR_INVALID_ARG;
+  int r = sp->perm.reserve(static_cast<size_t>(n_max) * 4);
+  if (r) return r;
+  return sp->worklist.reserve(worklist_bytes(n_max));
+}
+
+fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                           const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, void *stream) {
+  if (!sp) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {  // MessageSpatial3D.cu:116-120
+    FGB_CHECK(cudaMemsetAsync(sp->md.PBM, 0, (static_cast<size_t>(sp->bin_count) + 1) * 4, st));
+    return FGB_OK;
+  }
+  if (!x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;
+  if (sp->dims == 3) return build_index_impl<3>(sp, n, d_n, x, y, z, vars, nvars, flags, st);
+  return build_index_impl<2>(sp, n, d_n, x, y, nullptr, vars, nvars, flags, st);
+}
+
+fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_max, int max_bit) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || max_bit < 0 || max_bit > 30) return FGB_ERR_INVALID_ARG;
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  int r = reserve_zeroed(s.ctrl, 64);
+  if (r) return r;
+  const size_t tiles = std::max<size_t>(compact_num_tiles(n_max), 1);
+  size_t state_words = tiles;
+  if (max_bit > 0) {
+    const size_t H = static_cast<size_t>(1) << max_bit;
+    state_words = std::max(state_words, static_cast<size_t>(scan_num_tiles(static_cast<unsigned int>(H))));
+    r = reserve_zeroed(s.sort_hist, (H + 1) * 4);
+    if (r) return r;
+    r = s.sort_cursor.reserve((H + 1) * 4);
+    if (r) return r;
+    r = s.worklist.reserve(worklist_bytes(n_max));
+    if (r) return r;
+    r = s.perm.reserve(static_cast<size_t>(std::max(n_max, 1u)) * 4);
+    if (r) return r;
+  }
+  return reserve_zeroed(s.tile_state, state_words * 8);
+}
+
+fgb_status fgb_exclusive_scan_u32(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *in, unsigned int *out,
+                                  unsigned int n, void *stream) {
+  if (!ctx || !out || (n && !in) || stream_id >= FGB_MAX_STREAMS) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    FGB_CHECK(cudaMemsetAsync(out, 0, 4, st));
+    return FGB_OK;
+  }
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const unsigned int tiles = scan_num_tiles(n);
+  int r = reserve_zeroed(s.tile_state, static_cast<size_t>(tiles) * 8);
+  if (r) return r;
+  unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
+  FGB_CHECK(cudaMemsetAsync(state, 0, static_cast<size_t>(tiles) * 8, st));
+  uint32_t *inp = const_cast<uint32_t *>(in);
+  if (aligned16(in) && aligned16(out))
+    k_exclusive_scan<true><<<tiles, kScanThreads, 0, st>>>(inp, out, n, state, 0, 0);
+  else
+    k_exclusive_scan<false><<<tiles, kScanThreads, 0, st>>>(inp, out, n, state, 0, 0);
+  // the compaction kernels expect clean look-back words
+  FGB_CHECK(cudaMemsetAsync(state, 0, static_cast<size_t>(tiles) * 8, st));
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_compact(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *flags, int invert, unsigned int n,
+                       const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset,
+                       const unsigned int *d_out_offset, const fgb_var *vars, unsigned int nvars,
+                       unsigned int *d_out_count, unsigned int *d_out_total, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || (n > keep_front && !flags)) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  if (n == 0) {
+    if (d_out_count) FGB_CHECK(cudaMemsetAsync(d_out_count, 0, 4, st));
+    if (d_out_total) {
+      if (d_out_offset) FGB_CHECK(cudaMemcpyAsync(d_out_total, d_out_offset, 4, cudaMemcpyDeviceToDevice, st));
+      else FGB_CHECK(cudaMemcpyAsync(d_out_total, &out_offset, 4, cudaMemcpyHostToDevice, st));
+    }
+    return FGB_OK;
+  }
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const unsigned int tiles = compact_num_tiles(n);
+  r = reserve_zeroed(s.tile_state, static_cast<size_t>(tiles) * 8);
+  if (r) return r;
+  r = reserve_zeroed(s.ctrl, 64);
+  if (r) return r;
+  unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
+  uint32_t *done = static_cast<uint32_t *>(s.ctrl.p) + 1;
+  const bool vec = aligned16(flags) && vars_in_aligned(vars, nvars);
+  if (vec)
+    k_compact<true><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, vt, state,
+                                                   done, d_out_count, d_out_total);
+  else
+    k_compact<false><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, vt,
+                                                    state, done, d_out_count, d_out_total);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_scatter_all(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,
+                           const unsigned int *d_n, unsigned int out_offset, const unsigned int *d_out_offset,
+                           void *stream) {
+  if (!ctx) return FGB_ERR_INVALID_ARG;
+  if (n == 0 || nvars == 0) return FGB_OK;  // CUDAScatter.cu:225-226
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  const unsigned int grid = (n + 1023) / 1024;
+  if (vars_in_aligned(vars, nvars) && vars_out_aligned(vars, nvars))
+    k_scatter_all<true><<<grid, 256, 0, st>>>(n, d_n, out_offset, d_out_offset, vt);
+  else
+    k_scatter_all<false><<<grid, 256, 0, st>>>(n, d_n, out_offset, d_out_offset, vt);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_gather(fgb_ctx *ctx, const unsigned int *position, const fgb_var *vars, unsigned int nvars,
+                      unsigned int n, const unsigned int *d_n, void *stream) {
+  if (!ctx || (n && !position)) return FGB_ERR_INVALID_ARG;
+  if (n == 0 || nvars == 0) return FGB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  if (aligned16(position) && vars_out_aligned(vars, nvars))
+    k_gather<true><<<bin_grid(n), kBinThreads, 0, st>>>(position, n, d_n, vt);
+  else
+    k_gather<false><<<bin_grid(n), kBinThreads, 0, st>>>(position, n, d_n, vt);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_broadcast_init(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,
+                              unsigned int out_offset, void *stream) {
+  if (!ctx) return FGB_ERR_INVALID_ARG;
+  if (n == 0 || nvars == 0) return FGB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  k_broadcast_init<<<(n + 255) / 256, 256, 0, st>>>(n, out_offset, vt);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_sort_keys(fgb_ctx *ctx, const float *x, const float *y, const float *z, const float *env_min,
+                         const float *env_width, const unsigned int *grid_dim, unsigned int n,
+                         const unsigned int *d_n, unsigned int *keys_out, void *stream) {
+  if (!ctx || !x || !y || !env_min || !env_width || !grid_dim || !keys_out) return FGB_ERR_INVALID_ARG;
+  if (n == 0) return FGB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SortGeo g{};
+  g.min0 = env_min[0]; g.min1 = env_min[1]; g.min2 = z ? env_min[2] : 0.f;
+  g.w0 = env_width[0]; g.w1 = env_width[1]; g.w2 = z ? env_width[2] : 1.f;
+  g.g0 = grid_dim[0]; g.g1 = grid_dim[1]; g.g2 = z ? grid_dim[2] : 1u;
+  if (z)
+    k_sort_keys<3><<<(n + 255) / 256, 256, 0, st>>>(x, y, z, g, n, d_n, keys_out);
+  else
+    k_sort_keys<2><<<(n + 255) / 256, 256, 0, st>>>(x, y, nullptr, g, n, d_n, keys_out);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_sort_by_key(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *keys, int max_bit,
+                           unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars,
+                           unsigned int *position_out, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || max_bit < 1 || max_bit > 30 || (n && !keys)) return FGB_ERR_INVALID_ARG;
+  if (n == 0) return FGB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int r = fgb_ctx_reserve(ctx, stream_id, n, max_bit);
+  if (r) return r;
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const unsigned int H = 1u << max_bit;
+  uint32_t *hist = static_cast<uint32_t *>(s.sort_hist.p);
+  uint32_t *cursor = static_cast<uint32_t *>(s.sort_cursor.p);
+  unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
+  uint32_t *ctrl = static_cast<uint32_t *>(s.ctrl.p);
+  uint32_t *perm = position_out ? position_out : static_cast<uint32_t *>(s.perm.p);
+  uint32_t *worklist = static_cast<uint32_t *>(s.worklist.p);
+  KeySrc<0> src{};
+  src.keys = keys;
+  src.mask = H - 1u;
+  VarTable none{};
+  none.n = 0;
+  const unsigned int grid = bin_grid(n);
+  const unsigned int n_state = scan_num_tiles(H);
+  if (aligned16(keys)) {
+    k_bin_hist<0, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, hist, state, n_state, ctrl);
+    k_exclusive_scan<true><<<n_state, kScanThreads, 0, st>>>(hist, cursor, H, state, 1, 1);
+    k_bin_scatter<0, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, cursor, none, perm);
+  } else {
+    k_bin_hist<0, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, hist, state, n_state, ctrl);
+    k_exclusive_scan<true><<<n_state, kScanThreads, 0, st>>>(hist, cursor, H, state, 1, 1);
+    k_bin_scatter<0, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, cursor, none, perm);
+  }
+  ctx->launches += 3;
+  r = stable_tail(ctx, cursor, H, perm, worklist, ctrl, n, d_n, vars, nvars, st);
+  if (r) return r;
+  // leave the look-back words clean for the compaction kernels sharing this slot
+  FGB_CHECK(cudaMemsetAsync(state, 0, static_cast<size_t>(n_state) * 8, st));
+  return FGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// fgb_binsort.cuh -- device kernels shared by the PBM build (fgb_build_index) and the automatic
+// agent sort (fgb_sort_by_key): key histogram, cursor scatter, per-bin order fix-up, gather.
+//
+// Pipeline (every arrow is one kernel launch; nothing returns to the host):
+//   keys -> k_*_hist (RLE-aggregated RED atomics into a clean histogram)
+//        -> k_exclusive_scan (shift=1: cursor[k+1] = start of bin k; histogram re-zeroed)
+//        -> k_*_scatter (dst = atomicAdd(&cursor[k+1], run) ; afterwards cursor[] IS the prefix
+//                        array, i.e. the PBM -- no separate cursor array, no second memset)
+//   default order : the scatter moves the payload directly (arrival order inside a bin)
+//   stable order  : the scatter writes source indices, k_fix_* sorts each bin's indices
+//                   ascending (== source order), k_gather applies the permutation.
+#pragma once
+#include "fgb_common.cuh"
+
+namespace fgb {
+
+struct Geo {
+  float min0, min1, min2, radius;
+  int g0, g1, g2;
+};
+
+#ifdef __CUDACC__
+
+// getGridPosition3D + getHash3D (MessageSpatial3DDevice.cuh:646-672): IEEE divide, floorf, clamp.
+template <int DIMS>
+__device__ __forceinline__ uint32_t bin_key(const Geo &g, float x, float y, float z) {
+  int cx = static_cast<int>(floorf(__fdiv_rn(x - g.min0, g.radius)));
+  int cy = static_cast<int>(floorf(__fdiv_rn(y - g.min1, g.radius)));
+  cx = cx < 0 ? 0 : (cx >= g.g0 ? g.g0 - 1 : cx);
+  cy = cy < 0 ? 0 : (cy >= g.g1 ? g.g1 - 1 : cy);
+  if (DIMS == 3) {
+    int cz = static_cast<int>(floorf(__fdiv_rn(z - g.min2, g.radius)));
+    cz = cz < 0 ? 0 : (cz >= g.g2 ? g.g2 - 1 : cz);
+    return (static_cast<uint32_t>(cz) * g.g1 + cy) * g.g0 + cx;
+  }
+  return static_cast<uint32_t>(cy) * g.g0 + cx;
+}
+
+constexpr int kBinThreads = 256;
+constexpr int kBinItems = 4;
+
+// Key source: either positions (PBM build) or a ready key array masked to max_bit bits (agent sort).
+template <int DIMS>  // DIMS 2/3: positions; DIMS 0: key array
+struct KeySrc {
+  const float *x, *y, *z;
+  const uint32_t *keys;
+  uint32_t mask;
+  Geo g;
+  template <bool VEC>
+  __device__ __forceinline__ void load4(uint32_t i0, uint32_t n, uint32_t k[4]) const {
+    if (VEC && i0 + 4 <= n) {
+      if (DIMS == 0) {
+        uint4 q = ld_stream_u4(keys + i0);
+        k[0] = q.x & mask; k[1] = q.y & mask; k[2] = q.z & mask; k[3] = q.w & mask;
+      } else {
+        const float4 X = __ldg(reinterpret_cast<const float4 *>(x + i0));
+        const float4 Y = __ldg(reinterpret_cast<const float4 *>(y + i0));
+        float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DIMS == 3) Z = __ldg(reinterpret_cast<const float4 *>(z + i0));
+        k[0] = bin_key<DIMS == 0 ? 3 : DIMS>(g, X.x, Y.x, Z.x);
+        k[1] = bin_key<DIMS == 0 ? 3 : DIMS>(g, X.y, Y.y, Z.y);
+        k[2] = bin_key<DIMS == 0 ? 3 : DIMS>(g, X.z, Y.z, Z.z);
+        k[3] = bin_key<DIMS == 0 ? 3 : DIMS>(g, X.w, Y.w, Z.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t i = i0 + j;
+        if (i < n) {
+          if (DIMS == 0) k[j] = __ldg(keys + i) & mask;
+          else k[j] = bin_key<DIMS == 0 ? 3 : DIMS>(g, __ldg(x + i), __ldg(y + i), DIMS == 3 ? __ldg(z + i) : 0.f);
+        } else {
+          k[j] = 0xFFFFFFFFu;
+        }
+      }
+    }
+  }
+};
+
+// Runs of equal keys among a thread's (up to) four consecutive items.
+struct Runs {
+  bool head1, head2, head3;  // item j starts a new run (item 0 always does)
+  uint32_t len0, len1, len2; // run length if the run starts at item 0/1/2 (a run at 3 has length 1)
+};
+__device__ __forceinline__ Runs make_runs(const uint32_t k[4], int cnt) {
+  const bool v1 = cnt > 1, v2 = cnt > 2, v3 = cnt > 3;
+  const bool s1 = v1 && k[1] == k[0], s2 = v2 && k[2] == k[1], s3 = v3 && k[3] == k[2];
+  Runs r;
+  r.head1 = v1 && !s1;
+  r.head2 = v2 && !s2;
+  r.head3 = v3 && !s3;
+  const uint32_t t3 = s3 ? 1u : 0u;
+  r.len2 = 1u + t3;
+  const uint32_t t2 = s2 ? r.len2 : 0u;
+  r.len1 = 1u + t2;
+  const uint32_t t1 = s1 ? r.len1 : 0u;
+  r.len0 = 1u + t1;
+  return r;
+}
+
+// ---- phase 1: histogram ------------------------------------------------------------------
+// Also zeroes the look-back words of the scan that follows and the big-bin counter.
+// hist[] must be all-zero on entry; the scan re-zeroes it.
+template <int DIMS, bool VEC>
+__global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                          uint32_t *hist, unsigned long long *state,
+                                                          uint32_t n_state, uint32_t *ctrl) {
+  const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
+  const uint32_t total = gridDim.x * kBinThreads;
+  for (uint32_t s = gtid; s < n_state; s += total) state[s] = 0ull;
+  if (gtid == 0 && ctrl) ctrl[0] = 0u;
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i0 = gtid * kBinItems;
+  if (i0 >= n) return;
+  uint32_t k[4];
+  src.template load4<VEC>(i0, n, k);
+  // run-length aggregate the thread's consecutive items: lists arrive nearly bin-sorted (agents
+  // are bin-sorted every step), so most threads issue one RED instead of four.
+  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
+  const Runs r = make_runs(k, cnt);
+  atomicAdd(hist + k[0], r.len0);
+  if (r.head1) atomicAdd(hist + k[1], r.len1);
+  if (r.head2) atomicAdd(hist + k[2], r.len2);
+  if (r.head3) atomicAdd(hist + k[3], 1u);
+}
+
+// ---- phase 3: scatter --------------------------------------------------------------------
+// cursor[k+1] holds the next free slot of bin k.  IDX_ONLY: perm[dst] = source index.
+template <int DIMS, bool VEC, bool IDX_ONLY>
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                             uint32_t *cursor, const __grid_constant__ VarTable vt,
+                                                             uint32_t *perm) {
+  const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i0 = gtid * kBinItems;
+  if (i0 >= n) return;
+  uint32_t k[4], dst[4];
+  src.template load4<VEC>(i0, n, k);
+  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
+  // claim one contiguous slot range per run of equal keys (independent atomics, all in flight)
+  const Runs r = make_runs(k, cnt);
+  const uint32_t b0 = atomicAdd(cursor + k[0] + 1, r.len0);
+  const uint32_t b1 = r.head1 ? atomicAdd(cursor + k[1] + 1, r.len1) : 0u;
+  const uint32_t b2 = r.head2 ? atomicAdd(cursor + k[2] + 1, r.len2) : 0u;
+  const uint32_t b3 = r.head3 ? atomicAdd(cursor + k[3] + 1, 1u) : 0u;
+  dst[0] = b0;
+  dst[1] = r.head1 ? b1 : dst[0] + 1;
+  dst[2] = r.head2 ? b2 : dst[1] + 1;
+  dst[3] = r.head3 ? b3 : dst[2] + 1;
+  if constexpr (IDX_ONLY) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < cnt) perm[dst[t]] = i0 + t;
+  } else {
+  for (uint32_t v = 0; v < vt.n; ++v) {
+    const uint32_t len = vt.len[v];
+    if (VEC && len == 4 && cnt == 4) {
+      const uint4 q = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+      uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+      o[dst[0]] = q.x;
+      o[dst[1]] = q.y;
+      o[dst[2]] = q.z;
+      o[dst[3]] = q.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+    }
+  }
+  }
+}
+
+// ---- stable order: per-bin fix-up --------------------------------------------------------
+constexpr int kFixSmall = 32;
+
+// One thread per bin: bins of <= kFixSmall items are insertion-sorted in place, larger bins are
+// queued for k_fix_big.  pbm[] is the final prefix array (bin b = [pbm[b], pbm[b+1])).
+__global__ void __launch_bounds__(256) k_fix_small(const uint32_t *__restrict__ pbm, uint32_t bins, uint32_t *perm,
+                                                   uint32_t *worklist, uint32_t *ctrl) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= bins) return;
+  const uint32_t s = pbm[b], e = pbm[b + 1];
+  const uint32_t n = e - s;
+  if (n <= 1) return;
+  if (n > kFixSmall) {
+    worklist[atomicAdd(ctrl, 1u)] = b;
+    return;
+  }
+  uint32_t a[kFixSmall];
+  for (uint32_t i = 0; i < n; ++i) a[i] = perm[s + i];
+  bool sorted = true;
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint32_t key = a[i];
+    uint32_t p = i;
+    while (p > 0 && a[p - 1] > key) {
+      a[p] = a[p - 1];
+      --p;
+      sorted = false;
+    }
+    a[p] = key;
+  }
+  if (!sorted)
+    for (uint32_t i = 0; i < n; ++i) perm[s + i] = a[i];
+}
+
+// Arbitrary-n bitonic network in the all-ascending form (partner i^(k-1) for the first step of a
+// merge, i^j afterwards); items at virtual indices >= n act as +inf and never move.
+__device__ __forceinline__ void block_bitonic(uint32_t *a, uint32_t n) {
+  for (uint32_t k = 2; (k >> 1) < n; k <<= 1) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t l = i ^ (k - 1);
+      if (l > i && l < n) {
+        const uint32_t ai = a[i], al = a[l];
+        if (ai > al) { a[i] = al; a[l] = ai; }
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t l = i ^ j;
+        if (l > i && l < n) {
+          const uint32_t ai = a[i], al = a[l];
+          if (ai > al) { a[i] = al; a[l] = ai; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr int kFixBigSmem = 8192;
+// Persistent blocks walk the big-bin worklist; a bin that fits shared memory is sorted there,
+// a larger one in place in global memory (correct for any size, slow only for degenerate inputs).
+__global__ void __launch_bounds__(1024) k_fix_big(const uint32_t *__restrict__ pbm, uint32_t *perm,
+                                                  const uint32_t *worklist, const uint32_t *ctrl) {
+  __shared__ uint32_t buf[kFixBigSmem];
+  const uint32_t count = *ctrl;
+  for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
+    const uint32_t b = worklist[w];
+    const uint32_t s = pbm[b], n = pbm[b + 1] - s;
+    if (n <= kFixBigSmem) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) buf[i] = perm[s + i];
+      __syncthreads();
+      block_bitonic(buf, n);
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) perm[s + i] = buf[i];
+      __syncthreads();
+    } else {
+      block_bitonic(perm + s, n);
+    }
+  }
+}
+
+// ---- gather: out[j] = in[perm[j]] (scatter_position_generic, CUDAScatter.cu:89-104) ------
+template <bool VEC>
+__global__ void __launch_bounds__(kBinThreads) k_gather(const uint32_t *__restrict__ perm, uint32_t n_max,
+                                                        const unsigned int *d_n, const __grid_constant__ VarTable vt) {
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t j0 = (blockIdx.x * kBinThreads + threadIdx.x) * 4;
+  if (j0 >= n) return;
+  uint32_t src[4];
+  const int cnt = (n - j0) < 4u ? static_cast<int>(n - j0) : 4;
+  if (VEC && cnt == 4) {
+    const uint4 q = ld_stream_u4(perm + j0);
+    src[0] = q.x; src[1] = q.y; src[2] = q.z; src[3] = q.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) src[t] = t < cnt ? perm[j0 + t] : 0u;
+  }
+  for (uint32_t v = 0; v < vt.n; ++v) {
+    const uint32_t len = vt.len[v];
+    if (VEC && len == 4 && cnt == 4) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]);
+      uint4 q;
+      q.x = __ldg(in + src[0]);
+      q.y = __ldg(in + src[1]);
+      q.z = __ldg(in + src[2]);
+      q.w = __ldg(in + src[3]);
+      *reinterpret_cast<uint4 *>(vt.out[v] + static_cast<size_t>(j0) * 4) = q;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < cnt) copy_item(vt, v, src[t], j0 + t);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+inline unsigned int bin_grid(unsigned int n) {
+  const unsigned int per_block = kBinThreads * kBinItems;
+  return (n + per_block - 1) / per_block;
+}
+
+}  // namespace fgb

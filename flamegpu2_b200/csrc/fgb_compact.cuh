@@ -1,0 +1,180 @@
+// fgb_compact.cuh -- single-pass stable flag compaction over all SoA variables, plus the plain
+// data-movement kernels (append copy, default broadcast, sort-key computation).
+//
+// The reference compacts in three steps with two host round trips: cub ExclusiveSum over the
+// scan flags (CUDAFatAgent.cu:118-132), scatter_generic (CUDAScatter.cu:67-88), then a D2H copy
+// of position[n] and a stream sync (CUDAScatter.cu:175-178).  Here one kernel reads the flags,
+// resolves the global rank of every kept item with a decoupled look-back over tile aggregates and
+// moves every variable; the survivor count stays on the device.
+#pragma once
+#include "fgb_common.cuh"
+
+namespace fgb {
+
+constexpr int kCmpThreads = 256;
+constexpr int kCmpItems = 8;
+constexpr int kCmpTile = kCmpThreads * kCmpItems;
+
+inline unsigned int compact_num_tiles(unsigned int n) { return (n + kCmpTile - 1) / kCmpTile; }
+
+#ifdef __CUDACC__
+
+// state[]: one look-back word per tile, all-zero on entry; done: zero on entry.  The last block
+// to finish its look-back re-zeroes both, so consecutive launches (and CUDA-graph replays) need
+// no memset in between.
+template <bool VEC>
+__global__ void __launch_bounds__(kCmpThreads)
+k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const unsigned int *d_n, uint32_t keep_front,
+          uint32_t out_offset, const unsigned int *d_out_offset, const __grid_constant__ VarTable vt,
+          unsigned long long *state, uint32_t *done, uint32_t *d_out_count, uint32_t *d_out_total) {
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t s_excl;
+  __shared__ uint32_t s_last;
+  const uint32_t n = load_count(d_n, n_max);
+  const int tile = blockIdx.x;
+  const bool last_tile = tile == static_cast<int>(gridDim.x) - 1;
+  const uint32_t i0 = static_cast<uint32_t>(tile) * kCmpTile + threadIdx.x * kCmpItems;
+  if (d_out_offset) out_offset = __ldg(d_out_offset);
+
+  // ---- keep mask of this thread's 8 consecutive items
+  uint32_t keep = 0;
+  if (i0 < n) {
+    if (VEC && keep_front == 0 && i0 + kCmpItems <= n) {
+      const uint4 a = ld_stream_u4(flags + i0), b = ld_stream_u4(flags + i0 + 4);
+      const uint32_t f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) keep |= (((f[j] == 1u) != (invert != 0)) ? 1u : 0u) << j;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t i = i0 + j;
+        if (i < n) {
+          bool k = i < keep_front;
+          if (!k) k = (ld_stream_u32(flags + (i - keep_front)) == 1u) != (invert != 0);
+          keep |= (k ? 1u : 0u) << j;
+        }
+      }
+    }
+  }
+  const uint32_t tcount = __popc(keep);
+  uint32_t agg;
+  const uint32_t texcl = block_exclusive_scan(tcount, warp_sums, &agg);
+
+  // ---- publish the tile aggregate, resolve the exclusive prefix
+  if (threadIdx.x == 0) {
+    st_state(state + tile, (tile == 0 ? kStInclusive : kStAggregate) | agg);
+    if (tile == 0) s_excl = 0;
+  }
+  const bool need_prefix = agg != 0 || last_tile;  // empty tiles only publish
+  if (tile > 0 && need_prefix && threadIdx.x < 32) {
+    const uint32_t e = lookback_exclusive(state, tile);
+    if (threadIdx.x == 0) {
+      st_state(state + tile, kStInclusive | static_cast<unsigned long long>(e + agg));
+      s_excl = e;
+    }
+  }
+  __syncthreads();
+  const uint32_t tile_excl = s_excl;
+  if (last_tile && threadIdx.x == 0) {
+    if (d_out_count) *d_out_count = tile_excl + agg;
+    if (d_out_total) *d_out_total = out_offset + tile_excl + agg;
+  }
+
+  // ---- move the kept items of every variable; a thread's kept items are contiguous in the output
+  if (keep) {
+    const size_t pos0 = static_cast<size_t>(out_offset) + tile_excl + texcl;
+    for (uint32_t v = 0; v < vt.n; ++v) {
+      const uint32_t len = vt.len[v];
+      if (VEC && len == 4 && i0 + kCmpItems <= n) {
+        const uint4 a = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+        const uint4 b = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]) + pos0;
+        if (keep == 0xFFu && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+          reinterpret_cast<uint4 *>(o)[0] = a;
+          reinterpret_cast<uint4 *>(o)[1] = b;
+        } else {
+          uint32_t p = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (keep & (1u << j)) o[p++] = w[j];
+        }
+      } else {
+        uint32_t p = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (keep & (1u << j)) copy_item(vt, v, i0 + j, pos0 + p++);
+      }
+    }
+  }
+
+  // ---- self-clean the look-back words once every block is past its look-back
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    for (uint32_t t = threadIdx.x; t < gridDim.x; t += blockDim.x) state[t] = 0ull;
+    if (threadIdx.x == 0) *done = 0u;
+  }
+}
+
+// scatter_all_generic (CUDAScatter.cu:105-117): out[off + i] = in[i]
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_scatter_all(uint32_t n_max, const unsigned int *d_n, uint32_t out_offset,
+                                                     const unsigned int *d_out_offset,
+                                                     const __grid_constant__ VarTable vt) {
+  const uint32_t n = load_count(d_n, n_max);
+  if (d_out_offset) out_offset = __ldg(d_out_offset);
+  const uint32_t i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
+  for (uint32_t v = 0; v < vt.n; ++v) {
+    if (VEC && vt.len[v] == 4 && cnt == 4 && (out_offset & 3u) == 0) {
+      const uint4 q = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+      *reinterpret_cast<uint4 *>(vt.out[v] + (static_cast<size_t>(out_offset) + i0) * 4) = q;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t < cnt) copy_item(vt, v, i0 + t, static_cast<size_t>(out_offset) + i0 + t);
+    }
+  }
+}
+
+// broadcastInitKernel (CUDAScatter.cu:404-422): every item gets the default value at vt.in[v]
+__global__ void __launch_bounds__(256) k_broadcast_init(uint32_t n, uint32_t out_offset,
+                                                        const __grid_constant__ VarTable vt) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  for (uint32_t v = 0; v < vt.n; ++v) copy_item(vt, v, 0, static_cast<size_t>(out_offset) + i);
+}
+
+struct SortGeo {
+  float min0, min1, min2;
+  float w0, w1, w2;
+  uint32_t g0, g1, g2;
+};
+
+// calculateSpatialHash (CUDASimulation.cu:376-408): floorf(((p-min)/width)*gridDim), no clamp.
+template <int DIMS>
+__device__ __forceinline__ uint32_t sort_key(const SortGeo &g, float x, float y, float z) {
+  const int gx = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(x - g.min0, g.w0), static_cast<float>(g.g0))));
+  const int gy = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(y - g.min1, g.w1), static_cast<float>(g.g1))));
+  if (DIMS == 3) {
+    const int gz = static_cast<int>(floorf(__fmul_rn(__fdiv_rn(z - g.min2, g.w2), static_cast<float>(g.g2))));
+    return static_cast<uint32_t>(gz) * g.g0 * g.g1 + static_cast<uint32_t>(gy) * g.g0 + static_cast<uint32_t>(gx);
+  }
+  return static_cast<uint32_t>(gy) * g.g0 + static_cast<uint32_t>(gx);
+}
+
+template <int DIMS>
+__global__ void __launch_bounds__(256) k_sort_keys(const float *__restrict__ x, const float *__restrict__ y,
+                                                   const float *__restrict__ z, SortGeo g, uint32_t n_max,
+                                                   const unsigned int *d_n, uint32_t *__restrict__ keys) {
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = sort_key<DIMS>(g, __ldg(x + i), __ldg(y + i), DIMS == 3 ? __ldg(z + i) : 0.f);
+}
+
+#endif  // __CUDACC__
+}  // namespace fgb

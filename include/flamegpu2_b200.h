@@ -1,0 +1,197 @@
+/*
+ * flamegpu2_b200.h -- C ABI of the B200-native (sm_100a) implementation of FLAME GPU 2's
+ * per-step spatial hot path: spatial message binning (PBM build), stable compaction for agent
+ * death / birth / optional messages / function conditions, the automatic spatial agent sort,
+ * and the generic SoA data movement those need.
+ *
+ * The reference (FLAME GPU 2, v2.0.0-rc.5) has no C ABI: its seams are C++ virtual dispatch
+ * (MessageSpecialisationHandler) and the CUDAScatter class.  Each entry point below names the
+ * reference interface (file:line, relative to the reference root) it replaces; the C++ shim
+ * classes that a maintainer drops into the reference are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer marked "device" is a CUDA device pointer;
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - all calls are asynchronous on `stream` unless stated otherwise and never synchronise the
+ *    device (the reference synchronises after most of these, e.g. CUDAScatter.cu:177,336);
+ *  - item counts: `n` is the host-known upper bound used to size the launch; when `d_n` is
+ *    non-NULL the kernels read the actual count from that device word (<= n), so a captured
+ *    CUDA graph stays valid while the population changes;
+ *  - `stream_id` (< 128) selects the per-stream scratch slot, exactly like the reference's
+ *    streamResourceId argument; calls that may overlap in time must use different slots;
+ *  - no process-global state: all scratch belongs to an fgb_ctx (one per simulation, any number
+ *    per process, as CUDAEnsemble runs many simulations concurrently, CUDAEnsemble.cu:214-260);
+ *  - return value: 0 on success, a positive cudaError_t, or a negative fgb_error.
+ *  - there is NO CPU fallback: every entry point fails with FGB_ERR_NO_DEVICE without a GPU.
+ */
+#ifndef FLAMEGPU2_B200_H_
+#define FLAMEGPU2_B200_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGB_VERSION 100
+
+typedef int fgb_status;
+enum fgb_error {
+  FGB_OK = 0,
+  FGB_ERR_INVALID_ARG = -1,
+  FGB_ERR_TOO_MANY_VARS = -2,
+  FGB_ERR_NO_DEVICE = -3,
+  FGB_ERR_ALLOC = -4,
+  FGB_ERR_UNSUPPORTED = -5
+};
+
+#define FGB_MAX_VARS 32
+
+/* One SoA variable of a list being moved: same layout and meaning as
+ * CUDAScatter::ScatterData {size_t typeLen; char *in; char *out;}
+ * (include/flamegpu/simulation/detail/CUDAScatter.cuh:58-62).  type_len = type_size * elements. */
+typedef struct fgb_var {
+  size_t type_len;
+  const void *in; /* device */
+  void *out;      /* device */
+} fgb_var;
+
+/* Device-visible message-list metadata.  Field-for-field the layout of
+ * MessageSpatial3D::MetaData (include/flamegpu/runtime/messaging/MessageSpatial3D.h:38-68); a
+ * 2D list uses the first two entries of each array, grid_dim[2] == 1. */
+typedef struct fgb_spatial_metadata {
+  float min[3];
+  float max[3];
+  float radius;
+  unsigned int *PBM; /* device, bin_count + 1 entries */
+  unsigned int grid_dim[3];
+  float environment_width[3];
+  bool wrap_compatible;
+} fgb_spatial_metadata;
+
+typedef struct fgb_ctx fgb_ctx;         /* per-simulation scratch owner */
+typedef struct fgb_spatial fgb_spatial; /* per message list: histogram, PBM, metadata */
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Replaces the Singletons{scatter, ...} bundle a CUDASimulation owns (CUDASimulation.h:567-591).
+ * Synchronous. */
+fgb_status fgb_ctx_create(int device, fgb_ctx **out);
+/* Frees all scratch.  Like CUDAScatter::purge (CUDAScatter.cu:46-54) it must be called before
+ * device reset, not from a static destructor.  Synchronous. */
+fgb_status fgb_ctx_destroy(fgb_ctx *ctx);
+const char *fgb_error_string(fgb_status s);
+int fgb_version(void);
+
+/* ---- spatial message list handler ----------------------------------------------------------- */
+/* MessageSpatial3D::CUDAModelHandler ctor + init + allocateMetaDataDevicePtr
+ * (src/flamegpu/runtime/messaging/MessageSpatial3D.cu:31-52,74-90); dims==2 gives the
+ * MessageSpatial2D twin (MessageSpatial2D.cu:35-52,74-90).  Computes grid_dim/bin_count/
+ * wrap_compatible exactly as the reference, allocates PBM (zeroed), histogram and the device
+ * MetaData.  Synchronous. */
+fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
+                              fgb_spatial **out);
+/* CUDAModelHandler::freeMetaDataDevicePtr (MessageSpatial3D.cu:92-111).  Synchronous. */
+fgb_status fgb_spatial_destroy(fgb_spatial *sp);
+/* Host copy of the metadata (PBM is the device pointer) and the bin count. */
+fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata *host_out, unsigned int *bin_count);
+/* MessageSpecialisationHandler::getMetaDataDevicePtr
+ * (include/flamegpu/runtime/messaging/MessageSpecialisationHandler.h:44) */
+const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp);
+
+/* Inspection helper (no reference counterpart: "The PBM is never stored on the host",
+ * MessageSpatial3D.h:55-58): copies the bin_count+1 PBM entries to host memory after
+ * synchronising `stream`.  Used by tests and by the parity harness. */
+fgb_status fgb_spatial_read_pbm(const fgb_spatial *sp, unsigned int *host_out, void *stream);
+
+enum fgb_build_flags {
+  FGB_BUILD_DEFAULT = 0,
+  /* within-bin order = source order (deterministic).  Default order is arrival order of the
+   * scatter, like the reference's atomicInc sub-index (MessageSpatial3D.cu:70). */
+  FGB_BUILD_STABLE = 1
+};
+
+/* MessageSpatial3D::CUDAModelHandler::buildIndex (MessageSpatial3D.cu:113-146) and
+ * MessageSpatial2D::CUDAModelHandler::buildIndex (MessageSpatial2D.cu:113-146), including the
+ * CUDAScatter::pbm_reorder they call (CUDAScatter.cu:276-337):
+ *   bins every message by its location (x,y[,z] device float arrays, z ignored for 2D),
+ *   writes the PBM (exclusive scan of the bin counts, bin_count+1 entries, PBM[bin_count] = n),
+ *   and copies every variable vars[v].in -> vars[v].out grouped by bin.
+ * x/y/z are the `in` arrays of the location variables and must also be listed in vars.
+ * The caller swaps its read/write lists afterwards (CUDAMessage::swap, MessageSpatial3D.cu:139).
+ * n == 0 (and d_n == NULL) zeroes the PBM like MessageSpatial3D.cu:116-120. */
+fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                           const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, void *stream);
+
+/* ---- scan / compaction / data movement ------------------------------------------------------ */
+/* cub::DeviceScan::ExclusiveSum as called at CUDAFatAgent.cu:118-132, CUDAAgentStateList.cu:195-210,
+ * CUDAMessage.cu:180-194: out[i] = sum_{j<i} in[j] for i in [0,n]  (n+1 outputs, out[n] = total),
+ * in[] has n valid entries.  Single pass, decoupled look-back. */
+fgb_status fgb_exclusive_scan_u32(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *in, unsigned int *out,
+                                  unsigned int n, void *stream);
+
+/* Scan-flag compaction in ONE pass (flags -> positions -> move), replacing the pair
+ * cub::DeviceScan::ExclusiveSum + CUDAScatter::scatter / scatter_generic
+ * (CUDAFatAgent.cu:105-137 death, CUDAFatAgent.cu:186-236 function condition,
+ *  CUDAMessage.cu:171-208 optional messages, CUDAAgentStateList.cu:189-250 birth append;
+ *  kernel CUDAScatter.cu:67-88, wrapper CUDAScatter.cu:138-179).
+ * Item i in [0,n) is kept if i < keep_front (scatter_all_count) or
+ * (flags[i - keep_front] == 1) != invert (InversionIterator, CUDAScatter.cuh:32-49);
+ * kept items keep their relative order and go to vars[v].out[out_offset + rank].
+ * The kept count (including keep_front) is written to *d_out_count (device, may be NULL);
+ * when d_out_total is non-NULL it receives out_offset + kept (the new list size after an append).
+ * out_offset may also be read from the device word d_out_offset when that is non-NULL. */
+fgb_status fgb_compact(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *flags, int invert, unsigned int n,
+                       const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset, const unsigned int *d_out_offset,
+                       const fgb_var *vars, unsigned int nvars, unsigned int *d_out_count, unsigned int *d_out_total,
+                       void *stream);
+
+/* CUDAScatter::scatterAll / scatter_all_generic (CUDAScatter.cu:105-117,219-262):
+ * out[out_offset + i] = in[i] for every variable (state transition append, message append). */
+fgb_status fgb_scatter_all(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,
+                           const unsigned int *d_n, unsigned int out_offset, const unsigned int *d_out_offset,
+                           void *stream);
+
+/* CUDAScatter::scatterPosition / scatter_position_generic (CUDAScatter.cu:89-104,180-218):
+ * out[i] = in[position[i]] for every variable (the gather that applies a sort). */
+fgb_status fgb_gather(fgb_ctx *ctx, const unsigned int *position, const fgb_var *vars, unsigned int nvars,
+                      unsigned int n, const unsigned int *d_n, void *stream);
+
+/* CUDAScatter::broadcastInit / broadcastInitKernel (CUDAScatter.cu:404-422,490-539):
+ * fills out[out_offset + i] of every variable with the type_len bytes at vars[v].in (a DEVICE
+ * pointer to one default value). */
+fgb_status fgb_broadcast_init(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,
+                              unsigned int out_offset, void *stream);
+
+/* ---- automatic spatial agent sort ----------------------------------------------------------- */
+/* calculateSpatialHash kernels (src/flamegpu/simulation/CUDASimulation.cu:335-408):
+ * key = floorf(((p-min)/width)*grid_dim) linearised, NOT clamped.  z == NULL for 2D.
+ * grid_dim as CUDASimulation.cu:498-505 computes it (ceilf(width/radius), 1 when width == 0). */
+fgb_status fgb_sort_keys(fgb_ctx *ctx, const float *x, const float *y, const float *z, const float *env_min,
+                         const float *env_width, const unsigned int *grid_dim, unsigned int n,
+                         const unsigned int *d_n, unsigned int *keys_out, void *stream);
+
+/* HostAgentAPI::sort_async<unsigned int> (include/flamegpu/runtime/agent/HostAgentAPI.cuh:858-914:
+ * fillTIDArray + cub::DeviceRadixSort::SortPairs on bits [0,max_bit) + scatterSort_async) fused:
+ * stable sort of the n items by (keys[i] & ((1<<max_bit)-1)), applied to every variable
+ * (vars[v].in -> vars[v].out).  If position_out is non-NULL it receives the permutation
+ * (position_out[j] = source index of sorted item j). */
+fgb_status fgb_sort_by_key(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *keys, int max_bit,
+                           unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars,
+                           unsigned int *position_out, void *stream);
+
+/* Scratch (look-back words, histograms, permutations) grows on demand with cudaMalloc, which is
+ * not allowed during CUDA stream capture: reserve for the largest n / max_bit up front (or run
+ * one warm-up call outside the capture).  stream_id < 128 selects the scratch slot, like the
+ * reference's streamResourceId (CUDAScatter.cuh:100-317). */
+fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_max, int max_bit);
+fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max);
+
+/* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
+unsigned long long fgb_launch_count(const fgb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAMEGPU2_B200_H_ */

@@ -1,0 +1,290 @@
+"""GPU parity tests of the C-ABI kernels against the CPU oracle (bit-exact integer/index work)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from flamegpu2_b200 import host
+
+    c = host.Context(0)
+    yield c
+    c.close()
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def as_u32(tensor):
+    return tensor.cpu().numpy().view(np.uint32)
+
+
+def _positions(n, lo, hi, seed, sorted_like=False, dims=3):
+    rng = np.random.default_rng(seed)
+    p = [rng.uniform(lo[a], hi[a], n).astype(np.float32) for a in range(dims)]
+    return p
+
+
+def _check_build(ctx, dims, mn, mx, radius, pos, stable, extra_len=0):
+    from flamegpu2_b200 import host
+
+    n = len(pos[0])
+    g = orc.Grid(dims, mn, mx, radius)
+    sp = host.Spatial(ctx, dims, mn, mx, radius)
+    assert sp.bin_count == g.bin_count and sp.grid_dim == g.grid_dim and sp.wrap_compatible == g.wrap_compatible
+    ids = np.arange(n, dtype=np.uint32)
+    names = ["id", "x", "y"] + (["z"] if dims == 3 else [])
+    host_vars = {"id": ids, "x": pos[0], "y": pos[1]}
+    if dims == 3:
+        host_vars["z"] = pos[2]
+    if extra_len:  # an array variable (test_spatial_3d.cu:568-616 ArrayVariable)
+        arr = np.arange(n * extra_len, dtype=np.uint32).reshape(n, extra_len) * 3
+        host_vars["v"] = arr
+        names.append("v")
+    ins = [t(host_vars[k]) for k in names]
+    outs = [torch.zeros_like(a) for a in ins]
+    zt = ins[names.index("z")] if dims == 3 else None
+    sp.build_index(ins[names.index("x")], ins[names.index("y")], zt, ins, outs, n, stable=stable)
+    torch.cuda.synchronize()
+    pbm = sp.pbm()
+    pbm_ref, perm_ref = g.build_index(pos[0], pos[1], pos[2] if dims == 3 else None)
+    assert np.array_equal(pbm, pbm_ref), "PBM must be bit-exact"
+    got_id = as_u32(outs[0])
+    if stable:
+        assert np.array_equal(got_id, perm_ref), "stable mode: source order inside every bin"
+    else:
+        # within-bin order is unspecified (reference: atomicInc arrival order): compare as multisets per bin
+        a = np.sort(got_id.reshape(-1))
+        assert np.array_equal(a, np.arange(n, dtype=np.uint32)), "every message appears exactly once"
+        keys = g.bin_keys(pos[0], pos[1], pos[2] if dims == 3 else None)
+        bins_of_sorted = np.repeat(np.arange(g.bin_count, dtype=np.uint32), np.diff(pbm.astype(np.int64)))
+        assert np.array_equal(keys[got_id], bins_of_sorted), "every message sits inside its own bin"
+    # every variable travelled with its message
+    for k, o in zip(names, outs):
+        hv = host_vars[k]
+        assert np.array_equal(o.cpu().numpy().view(hv.dtype).reshape(hv.shape), hv[got_id]), k
+    sp.close()
+
+
+@pytest.mark.parametrize("stable", [False, True])
+@pytest.mark.parametrize("n", [1, 5, 2049, 100003])
+def test_build_index_3d(ctx, n, stable):
+    pos = _positions(n, (-0.5, -0.5, -0.5), (10.5, 7.5, 5.5), seed=n)  # some points outside -> clamped
+    _check_build(ctx, 3, (0, 0, 0), (10, 7, 5), 0.5, pos, stable)
+
+
+@pytest.mark.parametrize("stable", [False, True])
+def test_build_index_3d_nonfactor_and_array_var(ctx, stable):
+    pos = _positions(30011, (0, 0, 0), (50.1, 50.1, 50.1), seed=7)
+    _check_build(ctx, 3, (0, 0, 0), (50.1, 50.1, 50.1), 10.0, pos, stable, extra_len=3)
+
+
+@pytest.mark.parametrize("stable", [False, True])
+@pytest.mark.parametrize("n", [3, 2049, 250001])
+def test_build_index_2d(ctx, n, stable):
+    pos = _positions(n, (0, 0), (11, 11), seed=n + 1, dims=2)
+    _check_build(ctx, 2, (0, 0), (11, 11), 1.0 if n < 10000 else 0.05, pos, stable)
+
+
+@pytest.mark.parametrize("stable", [False, True])
+def test_build_index_degenerate_single_bin(ctx, stable):
+    # every message in one bin (big-bin path of the stable fix-up), and a second crowded bin
+    n = 20000
+    x = np.full(n, 1.25, np.float32)
+    x[::3] = 7.75
+    pos = [x, np.full(n, 2.5, np.float32), np.full(n, 0.5, np.float32)]
+    _check_build(ctx, 3, (0, 0, 0), (10, 10, 10), 1.0, pos, stable)
+
+
+def test_build_index_golden_mandatory(ctx, golden_dir):
+    import os
+
+    pos = np.fromfile(os.path.join(golden_dir, "mandatory3d_pos.f32"), dtype=np.float32).reshape(3, -1)
+    _check_build(ctx, 3, (0, 0, 0), (5, 5, 5), 1.0, [pos[0], pos[1], pos[2]], True)
+    _check_build(ctx, 3, (0, 0, 0), (5, 5, 5), 1.0, [pos[0], pos[1], pos[2]], False)
+
+
+def test_build_index_empty_and_device_count(ctx):
+    from flamegpu2_b200 import host
+
+    sp = host.Spatial(ctx, 3, (0, 0, 0), (5, 5, 5), 1.0)
+    n = 4096
+    pos = _positions(n, (0, 0, 0), (5, 5, 5), seed=2)
+    ins = [t(p) for p in pos]
+    outs = [torch.zeros_like(a) for a in ins]
+    sp.build_index(ins[0], ins[1], ins[2], ins, outs, n)
+    assert sp.pbm()[-1] == n
+    # ReadEmpty (test_spatial_3d.cu:507-537): empty list -> PBM all zero
+    sp.build_index(ins[0], ins[1], ins[2], ins, outs, 0)
+    assert not sp.pbm().any()
+    # device-resident count smaller than the launch bound
+    d_n = torch.tensor([1000], dtype=torch.int32, device=DEV)
+    g = orc.Grid(3, (0, 0, 0), (5, 5, 5), 1.0)
+    for stable in (False, True):
+        sp.build_index(ins[0], ins[1], ins[2], ins, outs, n, d_n=d_n, stable=stable)
+        pbm_ref, _ = g.build_index(pos[0][:1000], pos[1][:1000], pos[2][:1000])
+        assert np.array_equal(sp.pbm(), pbm_ref)
+    d_n.zero_()
+    sp.build_index(ins[0], ins[1], ins[2], ins, outs, n, d_n=d_n)
+    assert not sp.pbm().any()
+    sp.close()
+
+
+def test_build_index_repeatable_many_calls(ctx):
+    # the histogram / look-back words must come back clean after every call
+    from flamegpu2_b200 import host
+
+    g = orc.Grid(3, (0, 0, 0), (20, 20, 20), 1.0)
+    sp = host.Spatial(ctx, 3, (0, 0, 0), (20, 20, 20), 1.0)
+    for it in range(6):
+        n = 50000 + 1111 * it
+        pos = _positions(n, (0, 0, 0), (20, 20, 20), seed=100 + it)
+        ins = [t(p) for p in pos]
+        outs = [torch.zeros_like(a) for a in ins]
+        sp.build_index(ins[0], ins[1], ins[2], ins, outs, n, stable=bool(it & 1))
+        pbm_ref, _ = g.build_index(*pos)
+        assert np.array_equal(sp.pbm(), pbm_ref)
+    sp.close()
+
+
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 125001, 3000000])
+def test_exclusive_scan(ctx, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 50, n).astype(np.uint32)
+    inp = t(a)
+    out = torch.zeros(n + 1, dtype=torch.int32, device=DEV)
+    ctx.exclusive_scan(inp, out, n)
+    ref = np.concatenate([[0], np.cumsum(a.astype(np.uint64))]).astype(np.uint32)
+    assert np.array_equal(as_u32(out), ref)
+
+
+@pytest.mark.parametrize("n,frac", [(1, 1.0), (7, 0.5), (2048, 0.9), (2049, 0.0), (100001, 0.9), (1000003, 0.5)])
+def test_compact_death(ctx, n, frac):
+    # AgentDeath (test_cuda_simulation.cu:406-430) + AgentDeath_array (test_device_api.cu:15-58)
+    rng = np.random.default_rng(n)
+    flags = (rng.random(n) < frac).astype(np.uint32)
+    x = rng.random(n).astype(np.float32)
+    ids = np.arange(n, dtype=np.uint32)
+    arr = rng.integers(0, 1 << 30, (n, 4)).astype(np.uint32)   # 16-byte array variable
+    arr3 = rng.integers(0, 1 << 30, (n, 3)).astype(np.uint32)  # 12-byte array variable
+    d64 = rng.random(n).astype(np.float64)
+    b8 = rng.integers(0, 255, n).astype(np.uint8)
+    ins = [t(x), t(ids), t(arr), t(arr3), t(d64), t(b8)]
+    outs = [torch.zeros_like(a) for a in ins]
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    tot = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ctx.compact(t(flags), ins, outs, n, d_out_count=cnt, d_out_total=tot)
+    perm = orc.compact(flags, n)
+    k = len(perm)
+    assert int(cnt.item()) == k and int(tot.item()) == k
+    for h, o in zip([x, ids, arr, arr3, d64, b8], outs):
+        assert np.array_equal(o.cpu().numpy()[:k], h[perm]), "survivor order must be stable and bit-exact"
+    # a second call on the same scratch (self-cleaning look-back words)
+    ctx.compact(t(flags), ins[:2], outs[:2], n, invert=True, d_out_count=cnt)
+    perm = orc.compact(flags, n, invert=True)
+    assert int(cnt.item()) == len(perm)
+    assert np.array_equal(outs[1].cpu().numpy().view(np.uint32)[: len(perm)], ids[perm])
+
+
+def test_compact_keep_front_offset_and_device_args(ctx):
+    # function-condition style: disabled agents at the front copied unconditionally (CUDAScatter.cu:82-83),
+    # birth-append style: output offset and item count read from device words
+    rng = np.random.default_rng(5)
+    n, keep_front, off = 70001, 1234, 5000
+    flags = (rng.random(n - keep_front) < 0.4).astype(np.uint32)
+    ids = np.arange(n, dtype=np.uint32)
+    out = torch.full((n + off,), -1, dtype=torch.int32, device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    tot = torch.zeros(1, dtype=torch.int32, device=DEV)
+    d_off = torch.tensor([off], dtype=torch.int32, device=DEV)
+    d_n = torch.tensor([n - 777], dtype=torch.int32, device=DEV)
+    ctx.compact(t(flags), [t(ids)], [out], n, keep_front=keep_front, d_out_offset=d_off, d_n=d_n, d_out_count=cnt,
+                d_out_total=tot)
+    perm = orc.compact(flags, n - 777, keep_front=keep_front)
+    assert int(cnt.item()) == len(perm) and int(tot.item()) == off + len(perm)
+    got = as_u32(out)
+    assert np.array_equal(got[off: off + len(perm)], ids[perm])
+    assert np.all(got[:off] == 0xFFFFFFFF) and np.all(got[off + len(perm):] == 0xFFFFFFFF)
+
+
+def test_scatter_all_gather_broadcast(ctx):
+    rng = np.random.default_rng(9)
+    n = 33333
+    a = rng.integers(0, 1 << 31, n).astype(np.uint32)
+    b = rng.random((n, 3)).astype(np.float32)
+    oa = torch.zeros(n + 10, dtype=torch.int32, device=DEV)
+    ob = torch.zeros((n + 10, 3), dtype=torch.float32, device=DEV)
+    ctx.scatter_all([t(a), t(b)], [oa, ob], n, out_offset=10)
+    assert np.array_equal(as_u32(oa)[10:], a) and np.array_equal(ob.cpu().numpy()[10:], b)
+    perm = rng.permutation(n).astype(np.uint32)
+    ga = torch.zeros(n, dtype=torch.int32, device=DEV)
+    gb = torch.zeros((n, 3), dtype=torch.float32, device=DEV)
+    ctx.gather(t(perm), [t(a), t(b)], [ga, gb], n)
+    assert np.array_equal(as_u32(ga), a[perm]) and np.array_equal(gb.cpu().numpy(), b[perm])
+    # default-value broadcast for new agents (test_device_agent_creation.cu:604 default values)
+    d1 = t(np.array([12.5], np.float32))
+    d2 = t(np.array([1, 2, 3], np.uint32))
+    o1 = torch.zeros(100, dtype=torch.float32, device=DEV)
+    o2 = torch.zeros((100, 3), dtype=torch.int32, device=DEV)
+    ctx.broadcast_init([d1, d2], [o1, o2], 60, out_offset=40)
+    assert np.all(o1.cpu().numpy()[40:] == 12.5) and np.all(o1.cpu().numpy()[:40] == 0)
+    assert np.all(o2.cpu().numpy()[40:] == [1, 2, 3])
+
+
+@pytest.mark.parametrize("n", [4, 1000, 200003])
+def test_agent_sort(ctx, n):
+    # auto-sort: key kernel bit-exact, stable order bit-exact (test_spatial_agent_sort.cu:69-111)
+    g = orc.Grid(3, (-5, -5, -5), (5, 5, 5), 0.2)
+    rng = np.random.default_rng(n)
+    if n == 4:
+        p = -np.arange(4, dtype=np.float32)
+        pos = [p, p.copy(), p.copy()]
+    else:
+        pos = [rng.uniform(-5.3, 5.3, n).astype(np.float32) for _ in range(3)]  # out-of-range keys wrap in uint
+    keys_ref = g.sort_keys(*pos)
+    keys = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ins = [t(p) for p in pos]
+    ctx.sort_keys(ins[0], ins[1], ins[2], g.min, g.env_width, g.sort_grid_dim(), n, keys)
+    assert np.array_equal(as_u32(keys), keys_ref)
+    mb = g.sort_max_bit()
+    perm_ref = orc.sort_perm(keys_ref, mb)
+    order = np.arange(n, dtype=np.uint32)
+    ins2 = ins + [t(order)]
+    outs = [torch.zeros_like(a) for a in ins2]
+    pos_out = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ctx.sort_by_key(keys, mb, ins2, outs, n, position_out=pos_out)
+    assert np.array_equal(as_u32(pos_out), perm_ref)
+    assert np.array_equal(as_u32(outs[3]), order[perm_ref])
+    assert np.array_equal(outs[0].cpu().numpy(), pos[0][perm_ref])
+    if n == 4:
+        assert list(as_u32(outs[3])) == [3, 2, 1, 0]
+    # compaction right after a sort on the same scratch slot
+    flags = (rng.random(n) < 0.5).astype(np.uint32)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    o = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ctx.compact(t(flags), [t(order)], [o], n, d_out_count=cnt)
+    assert int(cnt.item()) == int(flags.sum())
+
+
+def test_agent_sort_2d_and_many_ties(ctx):
+    g = orc.Grid(2, (0, 0), (8, 8), 1.0)
+    n = 50000
+    rng = np.random.default_rng(77)
+    pos = [rng.uniform(0, 8, n).astype(np.float32) for _ in range(2)]
+    keys_ref = g.sort_keys(pos[0], pos[1])
+    keys = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ctx.sort_keys(t(pos[0]), t(pos[1]), None, g.min, g.env_width, g.sort_grid_dim(), n, keys)
+    assert np.array_equal(as_u32(keys), keys_ref)
+    mb = g.sort_max_bit()
+    order = np.arange(n, dtype=np.uint32)
+    out = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ctx.sort_by_key(keys, mb, [t(order)], [out], n)   # ~780 agents per bin: big-bin fix-up path
+    assert np.array_equal(as_u32(out), orc.sort_perm(keys_ref, mb))

@@ -1,0 +1,113 @@
+"""Kernel-level microbenchmarks through the C ABI (CUDA-event timing, L2 flushed between reps).
+Writes one JSON object per line to stdout.  Used for profiles/, not for BENCH json."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flamegpu2_b200 import host  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, reps=20, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.add_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def circles_positions(n, L, sorted_like, seed=0):
+    g = torch.Generator(device=DEV)
+    g.manual_seed(seed)
+    pos = torch.rand((3, n), generator=g, device=DEV) * L
+    if sorted_like:
+        # steady-state message order: agents are bin-sorted every step, then move a little
+        cell = torch.floor(pos / 2.0).to(torch.int64)
+        gd = int(np.ceil(L / 2.0))
+        key = (cell[2] * gd + cell[1]) * gd + cell[0]
+        order = torch.argsort(key, stable=True)
+        pos = pos[:, order].contiguous()
+        pos = (pos + (torch.rand((3, n), generator=g, device=DEV) - 0.5) * 0.1).clamp_(0, L * 0.999999)
+    return pos.contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="1000000,16777216")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ctx = host.Context(0)
+    flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=DEV)  # 256 MB > 126 MB L2
+    for n in [int(s) for s in args.sizes.split(",")]:
+        L = float(round((n) ** (1.0 / 3.0)))
+        sp = host.Spatial(ctx, 3, (0, 0, 0), (L, L, L), 2.0)
+        sp.reserve(n)
+        for sorted_like in (True, False):
+            pos = circles_positions(n, L, sorted_like)
+            ids = torch.arange(n, dtype=torch.int32, device=DEV)
+            ins = [ids, pos[0].contiguous(), pos[1].contiguous(), pos[2].contiguous()]
+            outs = [torch.empty_like(a) for a in ins]
+            alg = n * 2 * 16 + 4 * (sp.bin_count + 1)
+            for stable in (False, True):
+                med, best = timed(lambda: sp.build_index(ins[1], ins[2], ins[3], ins, outs, n, stable=stable),
+                                  reps=args.reps, flush=flush)
+                print(json.dumps({"op": "build_index", "n": n, "bins": sp.bin_count, "stable": stable,
+                                  "input": "bin-sorted+jitter" if sorted_like else "random", "us_median": med,
+                                  "us_best": best, "alg_bytes": alg, "GBps": alg / med / 1e3,
+                                  "frac_of_measured_peak": alg / med / 1e3 / peak}), flush=True)
+        # death compaction: 24 B/agent, 10% die
+        vars_in = [torch.rand(n, device=DEV) for _ in range(4)] + [torch.arange(n, dtype=torch.int32, device=DEV)] * 2
+        vars_out = [torch.empty_like(a) for a in vars_in]
+        flags = (torch.rand(n, device=DEV) >= 0.1).to(torch.int32)
+        cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        ctx.reserve(n, 0)
+        med, best = timed(lambda: ctx.compact(flags, vars_in, vars_out, n, d_out_count=cnt), reps=args.reps, flush=flush)
+        keep = int(cnt.item())
+        alg = n * 4 + n * 24 + keep * 24
+        print(json.dumps({"op": "compact_death", "n": n, "kept": keep, "us_median": med, "us_best": best,
+                          "alg_bytes": alg, "GBps": alg / med / 1e3, "frac_of_measured_peak": alg / med / 1e3 / peak}),
+              flush=True)
+        # agent sort (key + stable sort + gather of 6 x 4-byte variables)
+        gd = int(np.ceil(L / 2.0))
+        mb = int(np.floor(np.log2(gd ** 3))) + 1
+        pos = circles_positions(n, L, True, seed=3)
+        keys = torch.empty(n, dtype=torch.int32, device=DEV)
+        ctx.reserve(n, mb)
+
+        def sort_all():
+            ctx.sort_keys(pos[0], pos[1], pos[2], (0, 0, 0), (L, L, L), (gd, gd, gd), n, keys)
+            ctx.sort_by_key(keys, mb, vars_in, vars_out, n)
+
+        med, best = timed(sort_all, reps=args.reps, flush=flush)
+        alg = n * (2 * 24 + 12)
+        print(json.dumps({"op": "agent_sort", "n": n, "max_bit": mb, "us_median": med, "us_best": best,
+                          "alg_bytes": alg, "GBps": alg / med / 1e3, "frac_of_measured_peak": alg / med / 1e3 / peak}),
+              flush=True)
+        sp.close()
+
+
+if __name__ == "__main__":
+    main()
