@@ -1,0 +1,230 @@
+// fgb_models.cu -- the example / benchmark models (examples/*.cuh), compiled against this repo's
+// C++ API layer (include/flamegpu) and exposed through a small C ABI so that the Python harness
+// (tests, bench.py, multi-GPU driver) can drive whole CUDASimulation::step() runs.
+// The same model headers are compiled against the REFERENCE library by oracle/ref_build/ref_sim.cu.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+
+#include "flamegpu/flamegpu.h"
+
+#include "../../../examples/boids_model.cuh"
+#include "../../../examples/circles_model.cuh"
+#include "../../../examples/stress_model.cuh"
+#include "../../../examples/test_models.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Sim {
+  std::unique_ptr<flamegpu::ModelDescription> model;
+  std::unique_ptr<flamegpu::CUDASimulation> sim;
+  std::map<std::string, std::unique_ptr<flamegpu::AgentVector>> staging;  // per agent, reused by the host-buffer path
+};
+
+std::map<std::string, std::string> parse_kv(const char *s) {
+  std::map<std::string, std::string> kv;
+  if (!s) return kv;
+  std::stringstream ss(s);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    const size_t eq = item.find('=');
+    if (eq == std::string::npos) continue;
+    kv[item.substr(0, eq)] = item.substr(eq + 1);
+  }
+  return kv;
+}
+float getf(const std::map<std::string, std::string> &kv, const char *k, float d) {
+  auto it = kv.find(k);
+  return it == kv.end() ? d : std::strtof(it->second.c_str(), nullptr);
+}
+unsigned int getu(const std::map<std::string, std::string> &kv, const char *k, unsigned int d) {
+  auto it = kv.find(k);
+  return it == kv.end() ? d : static_cast<unsigned int>(std::strtoul(it->second.c_str(), nullptr, 10));
+}
+
+template <typename F>
+int guarded(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return -1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fgbm_last_error(void) { return g_last_error.c_str(); }
+
+// model: "circles" | "boids3d" | "boids2d" | "stress" | "test"; params: "key=value,key=value"
+int fgbm_create(const char *model_name, const char *params, int device, void **out) {
+  return guarded([&] {
+    const std::string name = model_name ? model_name : "";
+    const auto kv = parse_kv(params);
+    auto s = std::make_unique<Sim>();
+    s->model = std::make_unique<flamegpu::ModelDescription>(name);
+    if (name == "circles") {
+      fgb_examples::CirclesParams p;
+      p.env_max = getf(kv, "env_max", p.env_max);
+      p.radius = getf(kv, "radius", p.radius);
+      p.repulse = getf(kv, "repulse", p.repulse);
+      p.sort_period = getu(kv, "sort_period", p.sort_period);
+      fgb_examples::define_circles(*s->model, p);
+    } else if (name == "boids3d" || name == "boids2d") {
+      fgb_examples::BoidsParams p;
+      p.dims = name == "boids3d" ? 3 : 2;
+      p.min_position = getf(kv, "min_position", p.min_position);
+      p.max_position = getf(kv, "max_position", p.max_position);
+      p.interaction_radius = getf(kv, "interaction_radius", p.interaction_radius);
+      p.separation_radius = getf(kv, "separation_radius", p.separation_radius);
+      fgb_examples::define_boids(*s->model, p);
+    } else if (name == "stress") {
+      fgb_examples::StressParams p;
+      p.env_max = getf(kv, "env_max", p.env_max);
+      p.radius = getf(kv, "radius", p.radius);
+      p.death_mod = getu(kv, "death_mod", p.death_mod);
+      p.birth_mod = getu(kv, "birth_mod", p.birth_mod);
+      fgb_examples::define_stress(*s->model, p);
+    } else if (name == "test") {
+      fgb_examples::TestParams p;
+      p.which = static_cast<int>(getu(kv, "which", 0));
+      p.mn[0] = getf(kv, "min_x", 0.f); p.mn[1] = getf(kv, "min_y", 0.f); p.mn[2] = getf(kv, "min_z", 0.f);
+      p.mx[0] = getf(kv, "max_x", 5.f); p.mx[1] = getf(kv, "max_y", 5.f); p.mx[2] = getf(kv, "max_z", 5.f);
+      p.radius = getf(kv, "radius", 1.f);
+      p.sort_period = getu(kv, "sort_period", 1);
+      fgb_examples::define_test_model(*s->model, p);
+    } else {
+      throw std::runtime_error("unknown model '" + name + "'");
+    }
+    s->sim = std::make_unique<flamegpu::CUDASimulation>(*s->model);
+    s->sim->CUDAConfig().device_id = device;
+    s->sim->CUDAConfig().useCUDAGraphs = getu(kv, "graphs", 1) != 0;
+    s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
+    s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
+    *out = s.release();
+  });
+}
+
+int fgbm_destroy(void *h) {
+  return guarded([&] { delete static_cast<Sim *>(h); });
+}
+
+// Upload a population: n agents, nvars SoA host arrays named names[v] (any variable not listed keeps
+// its default).  Replaces the state list.
+int fgbm_set_population(void *h, const char *agent, const char *state, unsigned int n, unsigned int nvars,
+                        const char **names, const void **host_ptrs) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    auto &stg = s->staging[agent];
+    if (!stg) stg = std::make_unique<flamegpu::AgentVector>(s->model->Agent(agent), 0);
+    stg->resize(0);
+    stg->resize(n);
+    for (unsigned int v = 0; v < nvars; ++v) {
+      std::vector<char> &col = stg->raw(names[v]);
+      std::memcpy(col.data(), host_ptrs[v], col.size());
+    }
+    s->sim->setPopulationData(*stg, state ? state : flamegpu::DEFAULT_STATE);
+  });
+}
+
+int fgbm_get_count(void *h, const char *agent, const char *state, unsigned int *n) {
+  return guarded([&] { *n = static_cast<Sim *>(h)->sim->getAgentCount(agent, state ? state : flamegpu::DEFAULT_STATE); });
+}
+
+// Copy one variable of a state list to host memory (bytes = count * type_len, checked).
+int fgbm_get_variable(void *h, const char *agent, const char *state, const char *var, void *host_out, size_t bytes) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    const char *st = state ? state : flamegpu::DEFAULT_STATE;
+    const unsigned int n = s->sim->getAgentCount(agent, st);
+    const auto &vars = s->model->Agent(agent).agent->variables;
+    auto it = vars.find(var);
+    if (it == vars.end()) throw std::runtime_error(std::string("no variable ") + var);
+    if (bytes != static_cast<size_t>(n) * it->second.bytes()) throw std::runtime_error("size mismatch in fgbm_get_variable");
+    void *d = s->sim->getAgentVariableDevicePtr(agent, st, var);
+    if (n && cudaMemcpy(host_out, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) throw std::runtime_error("cudaMemcpy failed");
+  });
+}
+
+int fgbm_step(void *h, unsigned int steps) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    for (unsigned int i = 0; i < steps; ++i) s->sim->step();
+  });
+}
+
+int fgbm_sync(void *h) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->synchronize(); });
+}
+
+void *fgbm_stream(void *h) { return static_cast<Sim *>(h)->sim->getStream(); }
+unsigned long long fgbm_launch_count(void *h) { return static_cast<Sim *>(h)->sim->getLaunchCount(); }
+unsigned int fgbm_graph_count(void *h) { return static_cast<Sim *>(h)->sim->getGraphCount(); }
+unsigned int fgbm_step_counter(void *h) { return static_cast<Sim *>(h)->sim->getStepCounter(); }
+
+// Per-step device times (seconds) recorded when the model was created with timing=1.
+int fgbm_step_times(void *h, double *out, unsigned int cap, unsigned int *n) {
+  return guarded([&] {
+    std::vector<double> t = static_cast<Sim *>(h)->sim->getElapsedTimeSteps();
+    *n = static_cast<unsigned int>(t.size());
+    for (unsigned int i = 0; i < cap && i < t.size(); ++i) out[i] = t[i];
+  });
+}
+
+// Message list inspection for the parity harness: count, PBM (bin_count+1 words) and one variable.
+int fgbm_message_count(void *h, const char *message, unsigned int *n) {
+  return guarded([&] { *n = static_cast<Sim *>(h)->sim->getMessageCount(message); });
+}
+int fgbm_message_pbm(void *h, const char *message, unsigned int *host_out, unsigned int *bin_count) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    fgb_spatial *sp = s->sim->getSpatialHandler(message);
+    if (!sp) throw std::runtime_error("not a spatial message list");
+    fgb_spatial_metadata md;
+    unsigned int bins = 0;
+    fgb_spatial_get_metadata(sp, &md, &bins);
+    if (bin_count) *bin_count = bins;
+    if (host_out) {
+      s->sim->synchronize();
+      if (fgb_spatial_read_pbm(sp, host_out, s->sim->getStream()) != 0) throw std::runtime_error("fgb_spatial_read_pbm failed");
+    }
+  });
+}
+int fgbm_message_variable(void *h, const char *message, const char *var, void *host_out, size_t bytes) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    s->sim->synchronize();
+    void *d = s->sim->getMessageVariableDevicePtr(message, var);
+    if (bytes && cudaMemcpy(host_out, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) throw std::runtime_error("cudaMemcpy failed");
+  });
+}
+
+// End-to-end Circles step with HOST buffers (bench.py "e2e"): upload x,y,z,drift of n agents from
+// (pinned) host memory, run `steps` steps, download x,y,z,drift and the ids in device order.
+int fgbm_circles_step_host(void *h, unsigned int n, const float *x, const float *y, const float *z, const float *drift,
+                           unsigned int steps, float *x_out, float *y_out, float *z_out, float *drift_out,
+                           unsigned int *id_out) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    const char *names[4] = {"x", "y", "z", "drift"};
+    const void *ptrs[4] = {x, y, z, drift};
+    if (fgbm_set_population(h, "Circle", nullptr, n, 4, names, ptrs) != 0) throw std::runtime_error(g_last_error);
+    for (unsigned int i = 0; i < steps; ++i) s->sim->step();
+    const size_t b = static_cast<size_t>(n) * 4;
+    if (fgbm_get_variable(h, "Circle", nullptr, "x", x_out, b) || fgbm_get_variable(h, "Circle", nullptr, "y", y_out, b) ||
+        fgbm_get_variable(h, "Circle", nullptr, "z", z_out, b) || fgbm_get_variable(h, "Circle", nullptr, "drift", drift_out, b) ||
+        (id_out && fgbm_get_variable(h, "Circle", nullptr, "_id", id_out, b)))
+      throw std::runtime_error(g_last_error);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""ctypes face of libfgb_models.so: whole CUDASimulation::step() runs of the example models
+(examples/*.cuh compiled against include/flamegpu, the C++ API layer of this repo).
+
+Used by tests, bench.py and the multi-GPU driver.  No CPU fallback: creating a Simulation without a
+GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfgb_models.so")
+
+_lib = None
+
+TEST_MODELS = {
+    "count3d": 0, "optional3d": 1, "wrap3d": 2, "count2d": 3, "wrap2d": 4, "death": 5,
+    "birth_mandatory": 6, "birth_optional": 7, "birth_optional_death": 8, "birth_other_agent": 9,
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        # the kernel library must be loaded first (the models library links against it by rpath)
+        from . import host
+
+        host.lib()
+        L = C.CDLL(LIB_PATH)
+        L.fgbm_last_error.restype = C.c_char_p
+        L.fgbm_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.fgbm_destroy.argtypes = [C.c_void_p]
+        L.fgbm_set_population.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_uint,
+                                          C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
+        L.fgbm_get_count.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint)]
+        L.fgbm_get_variable.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.fgbm_step.argtypes = [C.c_void_p, C.c_uint]
+        L.fgbm_sync.argtypes = [C.c_void_p]
+        L.fgbm_stream.argtypes = [C.c_void_p]
+        L.fgbm_stream.restype = C.c_void_p
+        L.fgbm_launch_count.argtypes = [C.c_void_p]
+        L.fgbm_launch_count.restype = C.c_ulonglong
+        L.fgbm_graph_count.argtypes = [C.c_void_p]
+        L.fgbm_graph_count.restype = C.c_uint
+        L.fgbm_step_counter.argtypes = [C.c_void_p]
+        L.fgbm_step_counter.restype = C.c_uint
+        L.fgbm_step_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint, C.POINTER(C.c_uint)]
+        L.fgbm_message_count.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint)]
+        L.fgbm_message_pbm.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_uint)]
+        L.fgbm_message_variable.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.fgbm_circles_step_host.argtypes = [C.c_void_p, C.c_uint] + [C.c_void_p] * 4 + [C.c_uint] + [C.c_void_p] * 5
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, where: str):
+    if rc != 0:
+        raise RuntimeError(f"{where}: {lib().fgbm_last_error().decode()}")
+
+
+class Simulation:
+    """One CUDASimulation of a named example model ("circles", "boids3d", "boids2d", "stress", "test")."""
+
+    def __init__(self, model: str, device: int = 0, **params):
+        self.model = model
+        p = ",".join(f"{k}={v}" for k, v in params.items())
+        h = C.c_void_p()
+        _check(lib().fgbm_create(model.encode(), p.encode(), device, C.byref(h)), "fgbm_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fgbm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_population(self, agent: str, variables: Dict[str, np.ndarray], state: Optional[str] = None):
+        names = list(variables)
+        arrs = [np.ascontiguousarray(variables[k]) for k in names]
+        n = len(arrs[0]) if arrs else 0
+        cn = (C.c_char_p * max(len(names), 1))(*[k.encode() for k in names])
+        cp = (C.c_void_p * max(len(names), 1))(*[a.ctypes.data for a in arrs])
+        _check(lib().fgbm_set_population(self.h, agent.encode(), state.encode() if state else None, n, len(names), cn, cp),
+               "fgbm_set_population")
+
+    def count(self, agent: str, state: Optional[str] = None) -> int:
+        n = C.c_uint()
+        _check(lib().fgbm_get_count(self.h, agent.encode(), state.encode() if state else None, C.byref(n)), "fgbm_get_count")
+        return int(n.value)
+
+    def get(self, agent: str, var: str, dtype, elements: int = 1, state: Optional[str] = None) -> np.ndarray:
+        n = self.count(agent, state)
+        shape = (n,) if elements == 1 else (n, elements)
+        out = np.empty(shape, dtype=dtype)
+        _check(lib().fgbm_get_variable(self.h, agent.encode(), state.encode() if state else None, var.encode(),
+                                       out.ctypes.data_as(C.c_void_p), out.nbytes), "fgbm_get_variable")
+        return out
+
+    def step(self, steps: int = 1):
+        _check(lib().fgbm_step(self.h, steps), "fgbm_step")
+
+    def sync(self):
+        _check(lib().fgbm_sync(self.h), "fgbm_sync")
+
+    @property
+    def stream(self) -> int:
+        return int(lib().fgbm_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().fgbm_launch_count(self.h))
+
+    @property
+    def graphs(self) -> int:
+        return int(lib().fgbm_graph_count(self.h))
+
+    @property
+    def step_counter(self) -> int:
+        return int(lib().fgbm_step_counter(self.h))
+
+    def step_times(self) -> np.ndarray:
+        cap = 1 << 16
+        buf = (C.c_double * cap)()
+        n = C.c_uint()
+        _check(lib().fgbm_step_times(self.h, buf, cap, C.byref(n)), "fgbm_step_times")
+        return np.array(buf[: min(cap, n.value)])
+
+    def message_count(self, message: str) -> int:
+        n = C.c_uint()
+        _check(lib().fgbm_message_count(self.h, message.encode(), C.byref(n)), "fgbm_message_count")
+        return int(n.value)
+
+    def message_pbm(self, message: str) -> np.ndarray:
+        bins = C.c_uint()
+        _check(lib().fgbm_message_pbm(self.h, message.encode(), None, C.byref(bins)), "fgbm_message_pbm")
+        out = np.empty(bins.value + 1, dtype=np.uint32)
+        _check(lib().fgbm_message_pbm(self.h, message.encode(), out.ctypes.data_as(C.c_void_p), C.byref(bins)), "fgbm_message_pbm")
+        return out
+
+    def message_variable(self, message: str, var: str, dtype, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=dtype)
+        _check(lib().fgbm_message_variable(self.h, message.encode(), var.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes),
+               "fgbm_message_variable")
+        return out
+
+    def circles_step_host(self, x, y, z, drift, steps, out):
+        """bench.py e2e path: host buffers in, host buffers out (copies inside the call)."""
+        n = len(x)
+        _check(lib().fgbm_circles_step_host(self.h, n, x.ctypes.data, y.ctypes.data, z.ctypes.data, drift.ctypes.data, steps,
+                                            out["x"].ctypes.data, out["y"].ctypes.data, out["z"].ctypes.data,
+                                            out["drift"].ctypes.data, out["id"].ctypes.data), "fgbm_circles_step_host")
+
+
+def smoke_check():
+    """One tiny Circles step on cuda:0 through the C++ API layer, checked against the CPU oracle."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "tests"))
+    import oracle_py as orc
+
+    n, L = 4096, 16.0
+    rng = np.random.default_rng(1)
+    pos = [rng.uniform(0, L, n).astype(np.float32) for _ in range(3)]
+    sim = Simulation("circles", env_max=L, radius=2.0)
+    sim.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+    sim.step(1)
+    ids = sim.get("Circle", "_id", np.uint32)
+    x = sim.get("Circle", "x", np.float32)
+    g = orc.Grid(3, (0, 0, 0), (L, L, L), 2.0)
+    i2, x2, y2, z2, d2, pbm = g.circles_step(np.arange(1, n + 1, dtype=np.uint32), pos[0], pos[1], pos[2],
+                                             np.zeros(n, np.float32), want_pbm=True)
+    assert np.array_equal(ids, i2), "agent order after the auto-sort must match the oracle bit-exactly"
+    assert np.array_equal(sim.message_pbm("location"), pbm), "PBM must match the oracle bit-exactly"
+    assert np.allclose(x, x2, rtol=1e-5, atol=1e-6), "agent positions differ from the oracle beyond tolerance"
+    sim.close()

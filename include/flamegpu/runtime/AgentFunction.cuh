@@ -1,0 +1,88 @@
+// flamegpu/runtime/AgentFunction.cuh -- FLAMEGPU_AGENT_FUNCTION and the kernel that runs it.
+// Same user-facing macro as the reference (runtime/AgentFunction_shim.cuh:32-40); the kernel
+// takes ONE by-value argument block and needs no shared memory (the reference's wrapper fills a
+// cuRVE table into shared memory and __syncthreads() before any agent code, AgentFunction.cuh:77-93).
+#ifndef FGB_INCLUDE_FLAMEGPU_RUNTIME_AGENTFUNCTION_CUH_
+#define FGB_INCLUDE_FLAMEGPU_RUNTIME_AGENTFUNCTION_CUH_
+
+#include <typeindex>
+
+#include "flamegpu/defines.h"
+#include "flamegpu/runtime/DeviceAPI.cuh"
+#include "flamegpu/runtime/detail/FunctionArgs.h"
+#include "flamegpu/runtime/messaging/MessageBruteForce.cuh"
+#include "flamegpu/runtime/messaging/MessageNone.h"
+#include "flamegpu/runtime/messaging/MessageSpatial2D.cuh"
+#include "flamegpu/runtime/messaging/MessageSpatial3D.cuh"
+
+namespace flamegpu {
+
+typedef void(AgentFunctionWrapper)(const detail::FunctionArgs);
+typedef void(AgentFunctionConditionWrapper)(const detail::FunctionArgs);
+
+#if defined(__CUDACC__)
+template <typename AgentFunction, typename MessageIn, typename MessageOut>
+__global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionArgs args) {
+  const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int n = args.bound;
+  if (args.d_count) {
+    const unsigned int c = __ldg(args.d_count);
+    n = c < n ? c : n;
+  }
+  if (index >= n) return;
+  DeviceAPI<MessageIn, MessageOut> api(args, index);
+  const AGENT_STATUS status = AgentFunction()(&api);
+  // one flag store per thread, no memset beforehand (reference AgentFunction.cuh:111-119 +
+  // CUDAScanCompaction::zero_async)
+  if (args.death_flag) args.death_flag[index] = static_cast<unsigned int>(status);
+  if (MessageOut::HAS_OUTPUT) {
+    if (args.msg_out_flag) args.msg_out_flag[index] = api.message_out.written() ? 1u : 0u;
+  }
+  api.agent_out.finalise();
+}
+
+// reference runtime/AgentFunctionCondition.cuh:45: the boolean goes into the AGENT_DEATH scan flags
+template <typename AgentFunctionCondition>
+__global__ void agent_function_condition_wrapper(const __grid_constant__ detail::FunctionArgs args) {
+  const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int n = args.bound;
+  if (args.d_count) {
+    const unsigned int c = __ldg(args.d_count);
+    n = c < n ? c : n;
+  }
+  if (index >= n) return;
+  ReadOnlyDeviceAPI api(args, index);
+  args.death_flag[index] = AgentFunctionCondition()(&api) ? 1u : 0u;
+}
+#endif
+
+}  // namespace flamegpu
+
+#define FLAMEGPU_AGENT_FUNCTION(funcName, message_in, message_out)                                                      \
+  struct funcName##_impl {                                                                                              \
+    __device__ __forceinline__ flamegpu::AGENT_STATUS operator()(                                                       \
+        flamegpu::DeviceAPI<message_in, message_out> *FLAMEGPU) const;                                                  \
+    static constexpr flamegpu::AgentFunctionWrapper *fnPtr() {                                                          \
+      return &flamegpu::agent_function_wrapper<funcName##_impl, message_in, message_out>;                               \
+    }                                                                                                                   \
+    static std::type_index inType() { return std::type_index(typeid(message_in)); }                                     \
+    static std::type_index outType() { return std::type_index(typeid(message_out)); }                                   \
+  };                                                                                                                    \
+  funcName##_impl funcName;                                                                                             \
+  __device__ __forceinline__ flamegpu::AGENT_STATUS funcName##_impl::operator()(                                        \
+      flamegpu::DeviceAPI<message_in, message_out> *FLAMEGPU) const
+
+#define FLAMEGPU_AGENT_FUNCTION_CONDITION(funcName)                                                                     \
+  struct funcName##_cdn_impl {                                                                                          \
+    __device__ __forceinline__ bool operator()(flamegpu::ReadOnlyDeviceAPI *FLAMEGPU) const;                            \
+    static constexpr flamegpu::AgentFunctionConditionWrapper *fnPtr() {                                                 \
+      return &flamegpu::agent_function_condition_wrapper<funcName##_cdn_impl>;                                          \
+    }                                                                                                                   \
+  };                                                                                                                    \
+  funcName##_cdn_impl funcName;                                                                                         \
+  __device__ __forceinline__ bool funcName##_cdn_impl::operator()(flamegpu::ReadOnlyDeviceAPI *FLAMEGPU) const
+
+#define FLAMEGPU_DEVICE_FUNCTION __device__ __forceinline__
+#define FLAMEGPU_HOST_DEVICE_FUNCTION __host__ __device__ __forceinline__
+
+#endif  // FGB_INCLUDE_FLAMEGPU_RUNTIME_AGENTFUNCTION_CUH_

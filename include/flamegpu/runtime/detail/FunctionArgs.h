@@ -1,0 +1,113 @@
+// flamegpu/runtime/detail/FunctionArgs.h -- what an agent-function kernel receives.
+//
+// One POD passed BY VALUE (kernel parameter space == constant bank) instead of the reference's
+// 12 separate arguments plus a 8-12 KB cuRVE hash table copied into shared memory by every block
+// (runtime/AgentFunction.cuh:40-76, runtime/detail/SharedBlock.h:15-31) and a 12 KB host-to-device
+// table upload before every launch (runtime/detail/curve/HostCurve.cu:159-163).
+#ifndef FGB_INCLUDE_FLAMEGPU_RUNTIME_DETAIL_FUNCTIONARGS_H_
+#define FGB_INCLUDE_FLAMEGPU_RUNTIME_DETAIL_FUNCTIONARGS_H_
+
+#include <cstdint>
+
+#include "flamegpu/defines.h"
+#include "flamegpu/detail/hash.h"
+
+namespace flamegpu {
+namespace detail {
+
+// name-hash -> SoA base pointer table of one list (agent state list, message list, new-agent list).
+// A per-table PERFECT hash: the host picks `salt` so that (hash * salt) >> (32 - kSlotBits) is
+// collision free for the table's names, so a lookup is one multiply-shift and one indexed
+// constant-bank load, with no loop (and is hoisted out of message loops as loop-invariant code).
+constexpr int kSlotBits = 6;
+constexpr int kSlots = 1 << kSlotBits;
+struct DevVars {
+  uint32_t n;
+  uint32_t salt;
+  uint32_t hash[kSlots];  // 0 == empty slot
+  char *ptr[kSlots];
+};
+
+// By-value copy of MessageSpatial2D/3D::MetaData (reference MessageSpatial3D.h:38-68); the
+// reference passes a pointer and re-reads it from global memory in every iterator step.
+struct SpatialMeta {
+  float min[3];
+  float max[3];
+  float radius;
+  float env_width[3];
+  int grid_dim[3];
+  int wrap_compatible;
+  const unsigned int *pbm;
+};
+
+struct DevEnv {
+  uint32_t n;
+  uint32_t salt;
+  uint32_t hash[kSlots];
+  uint32_t offset[kSlots];
+  const char *buffer;  // device copy of the packed property values
+};
+
+struct FunctionArgs {
+  const unsigned int *d_count;  // device-resident agent count (<= bound)
+  unsigned int bound;           // launch bound
+  DevVars agent;                // variables of the executing agent's state list
+  DevVars msg_in;               // input message list (bin-sorted for spatial messages)
+  DevVars msg_out;              // output message list
+  DevVars agent_out;            // new-agent scratch list (one slot per parent thread)
+  // new-agent variables in declaration order, for completing a child with its defaults
+  uint32_t agent_out_nvars;
+  uint32_t agent_out_slot[b200::kMaxVars];      // slot of variable v in agent_out
+  uint32_t agent_out_len[b200::kMaxVars];       // bytes per item
+  const char *agent_out_defaults[b200::kMaxVars];  // device pointer to the default value
+  SpatialMeta in_meta;
+  const unsigned int *d_msg_in_count;   // brute-force style inputs
+  const unsigned int *d_msg_out_offset; // append offset of the output list (NULL -> 0)
+  unsigned int *death_flag;      // scan flags, one per thread (NULL when the feature is off)
+  unsigned int *msg_out_flag;
+  unsigned int *agent_out_flag;
+  id_t *next_id;                 // per-agent-type id counter for births (atomic)
+  const unsigned int *d_step;    // device-resident step counter
+  DevEnv env;
+};
+
+// Slot of a hashed name in a table; -1 if absent.
+FGB_HD int find_slot(const DevVars &t, uint32_t h) {
+  const uint32_t i = (h * t.salt) >> (32 - kSlotBits);
+  return t.hash[i] == h ? static_cast<int>(i) : -1;
+}
+FGB_HD int find_slot(const DevEnv &t, uint32_t h) {
+  const uint32_t i = (h * t.salt) >> (32 - kSlotBits);
+  return t.hash[i] == h ? static_cast<int>(i) : -1;
+}
+
+// host: choose a salt that makes the table collision free and fill hash[]; returns false if none found
+template <typename Table>
+inline bool build_perfect_table(Table &t, const uint32_t *hashes, uint32_t n, uint32_t *slot_of) {
+  t.n = n;
+  for (uint32_t salt = 0x9E3779B1u, tries = 0; tries < (1u << 22); ++tries, salt = salt * 0x01000193u + 0x7F4A7C15u) {
+    const uint32_t s = salt | 1u;
+    uint64_t used = 0;
+    bool ok = true;
+    for (uint32_t k = 0; k < n && ok; ++k) {
+      const uint32_t i = (hashes[k] * s) >> (32 - kSlotBits);
+      if (used & (1ull << i)) ok = false;
+      used |= 1ull << i;
+    }
+    if (!ok) continue;
+    t.salt = s;
+    for (int i = 0; i < kSlots; ++i) t.hash[i] = 0u;
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t i = (hashes[k] * s) >> (32 - kSlotBits);
+      t.hash[i] = hashes[k];
+      slot_of[k] = i;
+    }
+    return true;
+  }
+  return false;
+}
+
+}  // namespace detail
+}  // namespace flamegpu
+
+#endif  // FGB_INCLUDE_FLAMEGPU_RUNTIME_DETAIL_FUNCTIONARGS_H_

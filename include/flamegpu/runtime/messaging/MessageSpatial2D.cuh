@@ -1,0 +1,249 @@
+// flamegpu/runtime/messaging/MessageSpatial2D.cuh -- device side of 2D spatially partitioned
+// messaging, API compatible with the reference's MessageSpatial2D/MessageSpatial2DDevice.cuh.
+// Same design as the 3D twin (MessageSpatial3D.cuh): 3 x-strips in dy order -1,0,1 (reference
+// :644-672), 9-bin toroidal WrapFilter with x slowest / y fastest (:253-260, :679-698).
+#ifndef FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL2D_CUH_
+#define FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL2D_CUH_
+
+#include "flamegpu/runtime/detail/FunctionArgs.h"
+#include "flamegpu/runtime/messaging/MessageBruteForce.cuh"
+
+namespace flamegpu {
+namespace detail {
+#if defined(__CUDACC__)
+// getGridPosition2D/3D (reference MessageSpatial3DDevice.cuh:646-659): IEEE divide, floorf, clamp
+__device__ __forceinline__ int grid_cell(const SpatialMeta &m, int axis, float p) {
+  const int c = static_cast<int>(floorf(__fdiv_rn(p - m.min[axis], m.radius)));
+  const int d = m.grid_dim[axis];
+  return c < 0 ? 0 : (c >= d ? d - 1 : c);
+}
+#endif
+}  // namespace detail
+
+class MessageSpatial2D {
+ public:
+  class Description;  // host side
+  static constexpr int DIMS = 2;
+  static constexpr bool SPATIAL = true;
+  static constexpr bool HAS_OUTPUT = true;
+  struct MetaData {  // reference MessageSpatial2D.h:36-66
+    float min[2];
+    float max[2];
+    float radius;
+    unsigned int *PBM;
+    unsigned int gridDim[2];
+    float environmentWidth[2];
+    bool wrapCompatible;
+  };
+  struct GridPos2D {
+    int x, y;
+  };
+
+#if defined(__CUDACC__)
+  class In {
+   public:
+    class Filter {
+     public:
+      class Message {
+        const detail::FunctionArgs &a;
+        int cx, cy;
+        int strip;  // 0..2, 3 == end
+        int idx, idx_end, nxt, nxt_end;
+        __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
+          b = 0;
+          e = 0;
+          if (s < 3) {
+            const int y = cy + s - 1;
+            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1];
+            if (y >= 0 && y < gy) {
+              const int row = y * gx;
+              const int x0 = cx > 0 ? cx - 1 : 0;
+              const int x1 = cx + 1 < gx ? cx + 1 : gx - 1;
+              b = static_cast<int>(__ldg(a.in_meta.pbm + row + x0));
+              e = static_cast<int>(__ldg(a.in_meta.pbm + row + x1 + 1));
+            }
+          }
+        }
+        __device__ __forceinline__ void next_strip() {
+          do {
+            ++strip;
+            idx = nxt;
+            idx_end = nxt_end;
+            fetch(strip + 1, nxt, nxt_end);
+          } while (idx >= idx_end && strip < 3);
+        }
+
+       public:
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, int _cx, int _cy, bool begin)
+            : a(args), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+          if (begin) {
+            strip = -1;
+            fetch(0, nxt, nxt_end);
+            next_strip();
+          }
+        }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return strip < 3; }
+        __device__ __forceinline__ bool operator==(const Message &rhs) const { return strip == rhs.strip && idx == rhs.idx; }
+        __device__ __forceinline__ Message &operator++() {
+          if (++idx >= idx_end) next_strip();
+          return *this;
+        }
+        template <typename T, unsigned int N>
+        __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
+          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          if (s < 0) return T{};
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
+        }
+        template <typename T, flamegpu::size_type N, unsigned int M>
+        __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
+          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          if (s < 0 || index >= N) return T{};
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
+        }
+        __device__ __forceinline__ unsigned int getIndex() const { return static_cast<unsigned int>(idx); }
+      };
+      class iterator {
+        Message m;
+
+       public:
+        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, int cx, int cy, bool begin)
+            : m(args, cx, cy, begin) {}
+        __device__ __forceinline__ iterator &operator++() {
+          ++m;
+          return *this;
+        }
+        __device__ __forceinline__ bool operator!=(const iterator &rhs) const { return m != rhs.m; }
+        __device__ __forceinline__ bool operator==(const iterator &rhs) const { return m == rhs.m; }
+        __device__ __forceinline__ Message &operator*() { return m; }
+        __device__ __forceinline__ Message *operator->() { return &m; }
+      };
+      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y) : a(args) {
+        cx = detail::grid_cell(args.in_meta, 0, x);
+        cy = detail::grid_cell(args.in_meta, 1, y);
+      }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, cx, cy, true); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, cx, cy, false); }
+
+     private:
+      const detail::FunctionArgs &a;
+      int cx, cy;
+    };
+
+    class WrapFilter {
+     public:
+      class Message {
+        const detail::FunctionArgs &a;
+        float lx, ly;
+        int cx, cy;
+        int cell;  // 0..8, 9 == end
+        int idx, idx_end, nxt, nxt_end;
+        __device__ __forceinline__ void fetch(int c, int &b, int &e) const {
+          b = 0;
+          e = 0;
+          if (c < 9) {
+            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1];
+            const int x = (cx + (c / 3) - 1 + gx) % gx;
+            const int y = (cy + (c % 3) - 1 + gy) % gy;
+            const int h = y * gx + x;
+            b = static_cast<int>(__ldg(a.in_meta.pbm + h));
+            e = static_cast<int>(__ldg(a.in_meta.pbm + h + 1));
+          }
+        }
+        __device__ __forceinline__ void next_cell() {
+          do {
+            ++cell;
+            idx = nxt;
+            idx_end = nxt_end;
+            fetch(cell + 1, nxt, nxt_end);
+          } while (idx >= idx_end && cell < 9);
+        }
+        __device__ __forceinline__ float virt(float p2, float p1, int axis) const {
+          const float d = p2 - p1;
+          const float w = a.in_meta.env_width[axis];
+          return fabsf(d) > w / 2.0f ? p2 - (d / fabsf(d) * w) : p2;
+        }
+
+       public:
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin)
+            : a(args), lx(x), ly(y), cx(_cx), cy(_cy), cell(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+          if (begin) {
+            cell = -1;
+            fetch(0, nxt, nxt_end);
+            next_cell();
+          }
+        }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return cell < 9; }
+        __device__ __forceinline__ bool operator==(const Message &rhs) const { return cell == rhs.cell && idx == rhs.idx; }
+        __device__ __forceinline__ Message &operator++() {
+          if (++idx >= idx_end) next_cell();
+          return *this;
+        }
+        template <typename T, unsigned int N>
+        __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
+          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          if (s < 0) return T{};
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
+        }
+        template <typename T, flamegpu::size_type N, unsigned int M>
+        __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
+          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          if (s < 0 || index >= N) return T{};
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
+        }
+        __device__ __forceinline__ float getVirtualX(float x1) const { return virt(getVariable<float>("x"), x1, 0); }
+        __device__ __forceinline__ float getVirtualY(float y1) const { return virt(getVariable<float>("y"), y1, 1); }
+        __device__ __forceinline__ float getVirtualX() const { return getVirtualX(lx); }
+        __device__ __forceinline__ float getVirtualY() const { return getVirtualY(ly); }
+      };
+      class iterator {
+        Message m;
+
+       public:
+        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, int cx, int cy, bool begin)
+            : m(args, x, y, cx, cy, begin) {}
+        __device__ __forceinline__ iterator &operator++() {
+          ++m;
+          return *this;
+        }
+        __device__ __forceinline__ bool operator!=(const iterator &rhs) const { return m != rhs.m; }
+        __device__ __forceinline__ bool operator==(const iterator &rhs) const { return m == rhs.m; }
+        __device__ __forceinline__ Message &operator*() { return m; }
+        __device__ __forceinline__ Message *operator->() { return &m; }
+      };
+      __device__ __forceinline__ WrapFilter(const detail::FunctionArgs &args, float x, float y) : a(args), lx(x), ly(y) {
+        cx = detail::grid_cell(args.in_meta, 0, x);
+        cy = detail::grid_cell(args.in_meta, 1, y);
+      }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, cx, cy, true); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, cx, cy, false); }
+
+     private:
+      const detail::FunctionArgs &a;
+      float lx, ly;
+      int cx, cy;
+    };
+
+    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args) : a(args) {}
+    __device__ __forceinline__ Filter operator()(float x, float y) const { return Filter(a, x, y); }
+    __device__ __forceinline__ WrapFilter wrap(float x, float y) const { return WrapFilter(a, x, y); }
+    __device__ __forceinline__ float radius() const { return a.in_meta.radius; }
+
+   private:
+    const detail::FunctionArgs &a;
+  };
+
+  class Out : public MessageBruteForce::Out {
+   public:
+    __device__ __forceinline__ Out(const detail::FunctionArgs &args, unsigned int index)
+        : MessageBruteForce::Out(args, index) {}
+    __device__ __forceinline__ void setLocation(float x, float y) const {
+      this->template setVariable<float>("x", x);
+      this->template setVariable<float>("y", y);
+    }
+  };
+#endif  // __CUDACC__
+};
+
+}  // namespace flamegpu
+
+#endif  // FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL2D_CUH_

@@ -1,0 +1,402 @@
+// flamegpu/simulation/CUDASimulation.h -- the per-step scheduler of the hot path.
+//
+// Replaces CUDASimulation::{step, stepLayer, spatialSortAgent_async} and the device-state managers
+// they drive (reference src/flamegpu/simulation/CUDASimulation.cu:463-1109, CUDAAgent*.cu,
+// CUDAFatAgent*.cu, CUDAMessage*.cu) for models built from agents + MessageSpatial2D/3D (and
+// brute-force) lists.  The design is B200-first rather than a translation:
+//
+//  * every count (agents per state, messages per list, next ids, step counter) lives in a small
+//    device control block; kernels are launched for a host-known upper BOUND and clamp to the
+//    device count, so nothing returns to the host inside a step.  The reference reads a count back
+//    and synchronises after every compaction (CUDAScatter.cu:175-178) - >= 6 host syncs per step;
+//  * a whole step (all layers, the agent sorts, PBM builds, agent functions, death / birth /
+//    optional-message compactions) is recorded once into a CUDA graph, with one captured stream
+//    per concurrently running function of a layer, and replayed; graphs are cached per
+//    (buffer-pointer parity, bounds) because double-buffered lists swap pointers every step;
+//  * all data movement goes through the sm_100a library behind the C ABI (flamegpu2_b200.h).
+//
+// Order of operations inside a layer follows the reference exactly: auto agent
+// sort -> PBM build for the input list -> agent function -> optional-message compaction ->
+// death compaction -> state transition -> birth append.
+#ifndef FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_H_
+#define FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_H_
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "flamegpu/model/ModelDescription.h"
+#include "flamegpu/simulation/AgentVector.h"
+#include "flamegpu2_b200.h"
+
+namespace flamegpu {
+
+#define FGB_CUDA_THROW(expr)                                                                                     \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if (_e != cudaSuccess)                                                                                       \
+      throw flamegpu::exception::CUDAError(std::string(#expr) + " failed: " + cudaGetErrorString(_e));          \
+  } while (0)
+#define FGB_ABI_THROW(expr)                                                                                      \
+  do {                                                                                                           \
+    fgb_status _s = (expr);                                                                                      \
+    if (_s != 0) throw flamegpu::exception::CUDAError(std::string(#expr) + " failed: " + fgb_error_string(_s)); \
+  } while (0)
+
+namespace detail {
+
+#if defined(__CUDACC__)
+// end-of-step bookkeeping on the device: ++step, reset the counts of non-persistent message lists
+// (reference CUDASimulation.cu:619-625 does this on the host)
+__global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const unsigned int *zero_slots, unsigned int n_zero) {
+  if (threadIdx.x == 0) ctrl[step_slot] += 1u;
+  for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
+}
+__global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
+#endif
+
+// One SoA list on the device: an agent state list, a message list or a new-agent scratch list.
+struct DevList {
+  std::vector<std::string> names;  // alphabetical (std::map order), like the reference
+  std::vector<Variable> meta;
+  std::vector<char *> data, swap;
+  unsigned int capacity = 0;
+  unsigned int bound = 0;       // host-known upper bound of the device count
+  unsigned int count_slot = 0;  // control-block slot of the device count
+  bool double_buffered = true;
+
+  void init(const VariableMap &vars, bool dbl) {
+    double_buffered = dbl;
+    for (const auto &v : vars) {
+      names.push_back(v.first);
+      meta.push_back(v.second);
+      data.push_back(nullptr);
+      swap.push_back(nullptr);
+    }
+  }
+  int index_of(const std::string &n) const {
+    for (size_t i = 0; i < names.size(); ++i)
+      if (names[i] == n) return static_cast<int>(i);
+    return -1;
+  }
+  // grow to at least `need` items, keeping the first `keep` items of data[]
+  void reserve(unsigned int need, unsigned int keep) {
+    if (need <= capacity) return;
+    unsigned int cap = std::max(capacity, 256u);
+    while (cap < need) cap = static_cast<unsigned int>(std::min<unsigned long long>(0xFFFFFFF0ull, static_cast<unsigned long long>(cap) * 5 / 4 + 64));
+    cap = (cap + 63u) & ~63u;
+    for (size_t v = 0; v < names.size(); ++v) {
+      const size_t b = meta[v].bytes();
+      char *nd = nullptr;
+      FGB_CUDA_THROW(cudaMalloc(&nd, static_cast<size_t>(cap) * b));
+      if (data[v] && keep) FGB_CUDA_THROW(cudaMemcpy(nd, data[v], static_cast<size_t>(std::min(keep, capacity)) * b, cudaMemcpyDeviceToDevice));
+      if (data[v]) cudaFree(data[v]);
+      data[v] = nd;
+      if (double_buffered) {
+        if (swap[v]) cudaFree(swap[v]);
+        FGB_CUDA_THROW(cudaMalloc(&swap[v], static_cast<size_t>(cap) * b));
+      }
+    }
+    capacity = cap;
+  }
+  void swap_buffers() {
+    for (size_t v = 0; v < names.size(); ++v) std::swap(data[v], swap[v]);
+  }
+  void release() {
+    for (auto &p : data)
+      if (p) cudaFree(p), p = nullptr;
+    for (auto &p : swap)
+      if (p) cudaFree(p), p = nullptr;
+    capacity = 0;
+  }
+  // fgb_var table data -> swap (or the reverse)
+  std::vector<fgb_var> vars(bool from_data = true) const {
+    std::vector<fgb_var> out(names.size());
+    for (size_t v = 0; v < names.size(); ++v) {
+      out[v].type_len = meta[v].bytes();
+      out[v].in = from_data ? data[v] : swap[v];
+      out[v].out = from_data ? swap[v] : data[v];
+    }
+    return out;
+  }
+  // perfect-hash slots of the variable names, computed once per list
+  mutable std::vector<uint32_t> slots;
+  mutable DevVars proto{};
+  void fill_table(DevVars &t, bool use_swap = false) const {
+    if (names.size() > static_cast<size_t>(b200::kMaxVars)) throw exception::UnsupportedFeature("more than b200::kMaxVars variables in one list");
+    if (slots.size() != names.size()) {
+      std::vector<uint32_t> h(names.size());
+      for (size_t v = 0; v < names.size(); ++v) h[v] = name_hash_rt(names[v]);
+      slots.assign(names.size(), 0u);
+      std::memset(&proto, 0, sizeof(proto));
+      if (!build_perfect_table(proto, h.data(), static_cast<uint32_t>(h.size()), slots.data()))
+        throw exception::UnsupportedFeature("could not build a collision-free variable table");
+    }
+    t = proto;
+    for (size_t v = 0; v < names.size(); ++v) t.ptr[slots[v]] = use_swap ? swap[v] : data[v];
+  }
+};
+
+struct DevFlags {  // grow-only u32 scan-flag array (one per thread of a function)
+  unsigned int *p = nullptr;
+  unsigned int cap = 0;
+  void reserve(unsigned int n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    cap = (n + n / 4 + 255u) & ~255u;
+    FGB_CUDA_THROW(cudaMalloc(&p, static_cast<size_t>(cap) * 4));
+    FGB_CUDA_THROW(cudaMemset(p, 0, static_cast<size_t>(cap) * 4));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct CUDAMessage {
+  std::shared_ptr<MessageData> desc;
+  DevList list;
+  fgb_spatial *spatial = nullptr;
+  fgb_spatial_metadata md{};
+  bool pbm_dirty = true;
+  bool truncate = true;
+};
+
+struct CUDAAgent {
+  std::shared_ptr<AgentData> desc;
+  std::map<std::string, DevList> states;
+  unsigned int next_id_slot = 0;
+  id_t host_next_id = 1;
+};
+
+struct FunctionRT {
+  std::shared_ptr<AgentFunctionData> fn;
+  CUDAAgent *agent = nullptr;
+  CUDAMessage *msg_in = nullptr, *msg_out = nullptr;
+  CUDAAgent *out_agent = nullptr;
+  DevList scratch_new;  // new-agent slots, one per parent thread
+  char *d_defaults = nullptr;
+  std::vector<size_t> default_offsets;
+  DevFlags death_flag, msg_flag, birth_flag;
+  bool sortable = false;
+  int sort_dims = 0;
+  unsigned int tmp_slot = 0;  // control word scratch (survivor count)
+  int block_size = 128;
+};
+
+}  // namespace detail
+
+class CUDASimulation;
+
+// Host-side API handed to init/step/exit functions (tiny subset of the reference's HostAPI: the
+// reductions are OUT of the hot-path scope; they exist so that the examples' step
+// functions compile and run, and are implemented as a device-to-host copy + host loop).
+class HostAgentAPI {
+ public:
+  HostAgentAPI(CUDASimulation *s, std::string a, std::string st) : sim(s), agent(std::move(a)), state(std::move(st)) {}
+  inline unsigned int count();
+  template <typename T>
+  inline T sum(const std::string &variable);
+  template <typename T>
+  inline T min(const std::string &variable);
+  template <typename T>
+  inline T max(const std::string &variable);
+
+ private:
+  template <typename T>
+  inline std::vector<T> download(const std::string &variable);
+  CUDASimulation *sim;
+  std::string agent, state;
+};
+class HostEnvironment {
+ public:
+  explicit HostEnvironment(CUDASimulation *s) : sim(s) {}
+  template <typename T>
+  inline T getProperty(const std::string &name);
+  template <typename T>
+  inline T setProperty(const std::string &name, T value);
+
+ private:
+  CUDASimulation *sim;
+};
+class HostAPI {
+ public:
+  explicit HostAPI(CUDASimulation *s) : environment(s), sim(s) {}
+  HostAgentAPI agent(const std::string &agent_name, const std::string &state = DEFAULT_STATE) { return HostAgentAPI(sim, agent_name, state); }
+  inline unsigned int getStepCounter() const;
+  HostEnvironment environment;
+
+ private:
+  CUDASimulation *sim;
+};
+
+enum CONDITION_RESULT { CONTINUE, EXIT };
+
+class CUDASimulation {
+ public:
+  struct Config {  // reference include/flamegpu/simulation/Simulation.h:37-71 (subset)
+    std::string input_file;
+    uint64_t random_seed = 0;
+    unsigned int steps = 1;
+    bool timing = false;
+    bool truncate_log_files = true;
+    int verbosity = 1;
+  };
+  struct CUDAConfig_t {  // reference CUDASimulation.h:100-129 (+ b200 extensions)
+    int device_id = 0;
+    bool inLayerConcurrency = true;
+    bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
+    bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
+  };
+
+  explicit CUDASimulation(const ModelDescription &model_desc, int argc = 0, const char **argv = nullptr)
+      : model(model_desc.model), host_api(this) {
+    parse_args(argc, argv);
+  }
+  ~CUDASimulation() { destroy(); }
+  CUDASimulation(const CUDASimulation &) = delete;
+  CUDASimulation &operator=(const CUDASimulation &) = delete;
+
+  Config &SimulationConfig() { return config; }
+  const Config &getSimulationConfig() const { return config; }
+  CUDAConfig_t &CUDAConfig() { return cuda_config; }
+
+  void setPopulationData(AgentVector &pop, const std::string &state = DEFAULT_STATE);
+  void getPopulationData(AgentVector &pop, const std::string &state = DEFAULT_STATE);
+  bool step();
+  void simulate();
+  unsigned int getStepCounter() const { return step_count; }
+  void resetStepCounter() {
+    step_count = 0;
+    if (initialised) FGB_CUDA_THROW(cudaMemset(d_ctrl + kStepSlot, 0, 4));
+  }
+  // seconds per step (reference CUDASimulation.h:362); measured with CUDA events on the step stream
+  std::vector<double> getElapsedTimeSteps();
+  double getElapsedTimeSimulation() const { return elapsed_simulation; }
+  template <typename T>
+  T getEnvironmentProperty(const std::string &name) { return EnvironmentDescription(model).getProperty<T>(name); }
+  template <typename T>
+  T setEnvironmentProperty(const std::string &name, T value) {
+    T old = EnvironmentDescription(model).setProperty<T>(name, value);
+    env_dirty = true;
+    return old;
+  }
+  unsigned int getAgentCount(const std::string &agent_name, const std::string &state = DEFAULT_STATE);
+
+  // ---- b200 extensions used by the parity harness / bench (no reference counterpart) -------------
+  // device pointers of a state list variable / message variable (current read buffers)
+  void *getAgentVariableDevicePtr(const std::string &agent_name, const std::string &state, const std::string &var);
+  void *getMessageVariableDevicePtr(const std::string &message_name, const std::string &var);
+  unsigned int getMessageCount(const std::string &message_name);
+  fgb_spatial *getSpatialHandler(const std::string &message_name);
+  unsigned long long getLaunchCount() const { return (ctx ? fgb_launch_count(ctx) : 0ull) + own_launches; }
+  unsigned int getGraphCount() const { return static_cast<unsigned int>(graphs.size()); }
+  cudaStream_t getStream() const { return main_stream; }
+  void synchronize() { if (initialised) FGB_CUDA_THROW(cudaStreamSynchronize(main_stream)); }
+
+ private:
+  friend class HostAgentAPI;
+  friend class HostEnvironment;
+  friend class HostAPI;
+  static constexpr unsigned int kCtrlWords = 1024;
+  static constexpr unsigned int kStepSlot = 0;
+
+  void parse_args(int argc, const char **argv);
+  void initialise();
+  void destroy();
+  detail::CUDAAgent &agent_rt(const std::string &name) {
+    auto it = agents.find(name);
+    if (it == agents.end()) throw exception::InvalidCudaAgent("agent '" + name + "' was not found");
+    return it->second;
+  }
+  detail::DevList &state_list(const std::string &agent_name, const std::string &state) {
+    auto &a = agent_rt(agent_name);
+    auto it = a.states.find(state);
+    if (it == a.states.end()) throw exception::InvalidStateName("agent '" + agent_name + "' has no state '" + state + "'");
+    return it->second;
+  }
+  unsigned int alloc_slot() {
+    if (next_slot >= kCtrlWords) throw exception::UnsupportedFeature("control block exhausted");
+    return next_slot++;
+  }
+  unsigned int *slot_ptr(unsigned int s) const { return d_ctrl + s; }
+  unsigned int read_slot(unsigned int s) {
+    unsigned int v = 0;
+    FGB_CUDA_THROW(cudaMemcpyAsync(&v, d_ctrl + s, 4, cudaMemcpyDeviceToHost, main_stream));
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    return v;
+  }
+  void write_slot(unsigned int s, unsigned int v) { FGB_CUDA_THROW(cudaMemcpy(d_ctrl + s, &v, 4, cudaMemcpyHostToDevice)); }
+
+  void upload_environment();
+  void plan_step();                         // reserve capacities for the coming step (may allocate)
+  void record_step(cudaStream_t main);      // enqueue one whole step
+  void run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int stream_id);
+  void refresh_bounds();                    // births only: read the counts back once per step
+  std::vector<unsigned long long> graph_key() const;
+  static unsigned int quantise(unsigned int n) {
+    if (n <= 4096u) return (n + 255u) & ~255u;
+    unsigned int p = 1u;
+    while (p < n) p <<= 1;
+    const unsigned int q = p >> 5;  // 32 steps per octave
+    return (n + q - 1) / q * q;
+  }
+
+  std::shared_ptr<ModelData> model;
+  Config config;
+  CUDAConfig_t cuda_config;
+  bool initialised = false;
+  fgb_ctx *ctx = nullptr;
+  cudaStream_t main_stream = nullptr;
+  std::vector<cudaStream_t> side_streams;
+  std::vector<cudaEvent_t> join_events;
+  cudaEvent_t fork_event = nullptr;
+  unsigned int *d_ctrl = nullptr;
+  unsigned int next_slot = 1;
+  unsigned int *d_zero_slots = nullptr;
+  unsigned int n_zero_slots = 0;
+  char *d_env = nullptr;
+  detail::DevEnv env_table{};
+  std::vector<char> env_host;
+  std::vector<size_t> env_offsets;
+  bool env_dirty = true;
+  std::map<std::string, detail::CUDAAgent> agents;
+  std::map<std::string, detail::CUDAMessage> messages;
+  std::vector<std::vector<detail::FunctionRT>> layers;  // [layer][function]
+  bool model_has_births = false;
+  bool model_has_host_layers = false;
+  unsigned int step_count = 0;
+  unsigned long long own_launches = 0;
+  HostAPI host_api;
+  struct GraphEntry {
+    std::vector<unsigned long long> key;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches = 0;
+    // host-side state after the step (pointer parity, bounds, flags) to restore on replay
+    std::vector<unsigned long long> post_state;
+  };
+  std::vector<GraphEntry> graphs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> step_events;
+  std::vector<double> step_seconds;
+  double elapsed_simulation = 0.0;
+
+  std::vector<unsigned long long> snapshot_host_state() const;
+  void restore_host_state(const std::vector<unsigned long long> &s);
+};
+
+}  // namespace flamegpu
+
+#include "flamegpu/simulation/CUDASimulation_impl.h"
+
+#endif  // FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_H_

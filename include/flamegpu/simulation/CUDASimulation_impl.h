@@ -1,0 +1,752 @@
+// flamegpu/simulation/CUDASimulation_impl.h -- inline implementation of the step scheduler
+// declared in CUDASimulation.h.  Included at the end of that header; do not include directly.
+#ifndef FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_IMPL_H_
+#define FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_IMPL_H_
+
+namespace flamegpu {
+
+inline void CUDASimulation::parse_args(int argc, const char **argv) {
+  // the reference's argv parser (Simulation.cu:233-316): -s steps, -r seed, -d device, -t timing
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&](void) -> std::string { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
+    if (a == "-s" || a == "--steps") config.steps = static_cast<unsigned int>(std::strtoul(next().c_str(), nullptr, 10));
+    else if (a == "-r" || a == "--random") config.random_seed = std::strtoull(next().c_str(), nullptr, 10);
+    else if (a == "-d" || a == "--device") cuda_config.device_id = std::atoi(next().c_str());
+    else if (a == "-t" || a == "--timing") config.timing = true;
+    else if (a == "-i" || a == "--in") config.input_file = next();
+    else if (a == "-q" || a == "--quiet") config.verbosity = 0;
+    else if (a == "-v" || a == "--verbose") config.verbosity = 2;
+  }
+}
+
+inline void CUDASimulation::initialise() {
+  if (initialised) return;
+  FGB_CUDA_THROW(cudaSetDevice(cuda_config.device_id));
+  FGB_ABI_THROW(fgb_ctx_create(cuda_config.device_id, &ctx));
+  FGB_CUDA_THROW(cudaStreamCreateWithFlags(&main_stream, cudaStreamNonBlocking));
+  FGB_CUDA_THROW(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+  FGB_CUDA_THROW(cudaMalloc(&d_ctrl, kCtrlWords * 4));
+  FGB_CUDA_THROW(cudaMemset(d_ctrl, 0, kCtrlWords * 4));
+  next_slot = 1;
+
+  // agents whose functions touch spatial messages carry the auto-sort key variable
+  // (reference src/flamegpu/model/AgentFunctionDescription.cpp:534-535)
+  for (auto &ap : model->agents)
+    for (auto &fp : ap.second->functions) {
+      auto spatial = [&](const std::string &m) {
+        auto it = model->messages.find(m);
+        return it != model->messages.end() && it->second->dims() > 0;
+      };
+      if (spatial(fp.second->message_input) || spatial(fp.second->message_output))
+        if (!ap.second->variables.count("_auto_sort_bin_index"))
+          ap.second->variables.emplace("_auto_sort_bin_index", make_variable<unsigned int>(1, nullptr));
+    }
+
+  std::vector<unsigned int> zero_slots;
+  for (auto &mp : model->messages) {
+    detail::CUDAMessage &m = messages[mp.first];
+    m.desc = mp.second;
+    m.list.init(mp.second->variables, true);
+    m.list.count_slot = alloc_slot();
+    if (!mp.second->persistent) zero_slots.push_back(m.list.count_slot);
+    if (mp.second->dims() > 0) {
+      if (!(mp.second->radius > 0.f)) throw exception::InvalidMessageType("spatial message '" + mp.first + "' has no radius");
+      FGB_ABI_THROW(fgb_spatial_create(ctx, mp.second->dims(), mp.second->min, mp.second->max, mp.second->radius, &m.spatial));
+      unsigned int bins = 0;
+      FGB_ABI_THROW(fgb_spatial_get_metadata(m.spatial, &m.md, &bins));
+    }
+  }
+  for (auto &ap : model->agents) {
+    detail::CUDAAgent &a = agents[ap.first];
+    a.desc = ap.second;
+    a.next_id_slot = alloc_slot();
+    a.host_next_id = 1;
+    write_slot(a.next_id_slot, 1u);
+    for (const auto &s : ap.second->states) {
+      detail::DevList &l = a.states[s];
+      l.init(ap.second->variables, true);
+      l.count_slot = alloc_slot();
+    }
+  }
+  n_zero_slots = static_cast<unsigned int>(zero_slots.size());
+  if (n_zero_slots) {
+    FGB_CUDA_THROW(cudaMalloc(&d_zero_slots, n_zero_slots * 4));
+    FGB_CUDA_THROW(cudaMemcpy(d_zero_slots, zero_slots.data(), n_zero_slots * 4, cudaMemcpyHostToDevice));
+  }
+
+  size_t max_width = 1;
+  for (auto &lp : model->layers) {
+    layers.emplace_back();
+    if (!lp->host_functions.empty()) model_has_host_layers = true;
+    for (auto &fp : lp->functions) {
+      layers.back().emplace_back();
+      detail::FunctionRT &f = layers.back().back();
+      f.fn = fp;
+      auto parent = fp->parent.lock();
+      f.agent = &agent_rt(parent->name);
+      if (!fp->message_input.empty()) f.msg_in = &messages.at(fp->message_input);
+      if (!fp->message_output.empty()) f.msg_out = &messages.at(fp->message_output);
+      f.tmp_slot = alloc_slot();
+      if (!fp->agent_output.empty()) {
+        model_has_births = true;
+        f.out_agent = &agent_rt(fp->agent_output);
+        f.scratch_new.init(f.out_agent->desc->variables, false);
+        size_t total = 0;
+        for (const auto &v : f.out_agent->desc->variables) {
+          f.default_offsets.push_back(total);
+          total += (v.second.bytes() + 15) & ~static_cast<size_t>(15);
+        }
+        std::vector<char> packed(std::max<size_t>(total, 16), 0);
+        size_t k = 0;
+        for (const auto &v : f.out_agent->desc->variables) std::memcpy(packed.data() + f.default_offsets[k++], v.second.default_value.data(), v.second.bytes());
+        FGB_CUDA_THROW(cudaMalloc(&f.d_defaults, packed.size()));
+        FGB_CUDA_THROW(cudaMemcpy(f.d_defaults, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+      }
+      // auto-sort trigger (reference CUDASimulation.cu:410-460), scalar float x,y(,z) only
+      if (f.msg_in && f.msg_in->desc->dims() > 0) {
+        auto is_f = [&](const char *n) {
+          auto it = parent->variables.find(n);
+          return it != parent->variables.end() && it->second.type == std::type_index(typeid(float)) && it->second.elements == 1;
+        };
+        const int d = f.msg_in->desc->dims();
+        if (is_f("x") && is_f("y") && (d == 2 || is_f("z"))) {
+          f.sortable = true;
+          f.sort_dims = d;
+        }
+      }
+    }
+    max_width = std::max(max_width, lp->functions.size());
+  }
+  if (cuda_config.inLayerConcurrency && max_width > 1) {
+    side_streams.resize(max_width);
+    join_events.resize(max_width);
+    for (size_t i = 0; i < max_width; ++i) {
+      FGB_CUDA_THROW(cudaStreamCreateWithFlags(&side_streams[i], cudaStreamNonBlocking));
+      FGB_CUDA_THROW(cudaEventCreateWithFlags(&join_events[i], cudaEventDisableTiming));
+    }
+  }
+
+  // environment: packed property buffer + name-hash table (reference EnvironmentManager)
+  size_t off = 0;
+  {
+    if (model->environment.size() > static_cast<size_t>(b200::kMaxEnvProps)) throw exception::UnsupportedFeature("more than b200::kMaxEnvProps environment properties");
+    std::vector<uint32_t> h, slot(model->environment.size());
+    for (const auto &p : model->environment) h.push_back(detail::name_hash_rt(p.first));
+    std::memset(&env_table, 0, sizeof(env_table));
+    if (!detail::build_perfect_table(env_table, h.data(), static_cast<uint32_t>(h.size()), slot.data()))
+      throw exception::UnsupportedFeature("could not build a collision-free environment table");
+    size_t k = 0;
+    env_offsets.clear();
+    for (const auto &p : model->environment) {
+      off = (off + 15) & ~static_cast<size_t>(15);
+      env_table.offset[slot[k++]] = static_cast<uint32_t>(off);
+      env_offsets.push_back(off);
+      off += p.second.data.size();
+    }
+  }
+  env_host.assign(std::max<size_t>(off, 16), 0);
+  FGB_CUDA_THROW(cudaMalloc(&d_env, env_host.size()));
+  env_table.buffer = d_env;
+  env_dirty = true;
+  initialised = true;
+}
+
+inline void CUDASimulation::destroy() {
+  if (!initialised) return;
+  cudaDeviceSynchronize();
+  for (auto &g : graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  graphs.clear();
+  for (auto &e : step_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  for (auto &l : layers)
+    for (auto &f : l) {
+      f.scratch_new.release();
+      f.death_flag.release();
+      f.msg_flag.release();
+      f.birth_flag.release();
+      if (f.d_defaults) cudaFree(f.d_defaults);
+    }
+  for (auto &a : agents)
+    for (auto &s : a.second.states) s.second.release();
+  for (auto &m : messages) {
+    m.second.list.release();
+    if (m.second.spatial) fgb_spatial_destroy(m.second.spatial);
+  }
+  if (d_env) cudaFree(d_env);
+  if (d_zero_slots) cudaFree(d_zero_slots);
+  if (d_ctrl) cudaFree(d_ctrl);
+  for (auto s : side_streams) cudaStreamDestroy(s);
+  for (auto e : join_events) cudaEventDestroy(e);
+  if (fork_event) cudaEventDestroy(fork_event);
+  if (main_stream) cudaStreamDestroy(main_stream);
+  if (ctx) fgb_ctx_destroy(ctx);
+  ctx = nullptr;
+  initialised = false;
+}
+
+inline void CUDASimulation::upload_environment() {
+  size_t k = 0;
+  for (const auto &p : model->environment) std::memcpy(env_host.data() + env_offsets[k++], p.second.data.data(), p.second.data.size());
+  FGB_CUDA_THROW(cudaMemcpyAsync(d_env, env_host.data(), env_host.size(), cudaMemcpyHostToDevice, main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  env_dirty = false;
+}
+
+inline void CUDASimulation::setPopulationData(AgentVector &pop, const std::string &state) {
+  initialise();
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  const std::string &an = pop.getAgentData()->name;
+  detail::CUDAAgent &a = agent_rt(an);
+  detail::DevList &l = state_list(an, state);
+  const unsigned int n = pop.size();
+  // ids: agents still at ID_NOT_SET get the next free ids in order (reference assignAgentIDs,
+  // CUDAFatAgent.cu:311-391, does this lazily at the first step)
+  {
+    std::vector<char> &ids = pop.raw(ID_VARIABLE_NAME);
+    id_t *p = reinterpret_cast<id_t *>(ids.data());
+    id_t mx = 0;
+    for (unsigned int i = 0; i < n; ++i) mx = std::max(mx, p[i]);
+    a.host_next_id = std::max(a.host_next_id, mx + 1);
+    for (unsigned int i = 0; i < n; ++i)
+      if (p[i] == ID_NOT_SET) p[i] = a.host_next_id++;
+    write_slot(a.next_id_slot, a.host_next_id);
+  }
+  l.bound = model_has_births ? quantise(n) : n;
+  l.reserve(std::max(l.bound, 1u), 0);
+  for (size_t v = 0; v < l.names.size(); ++v) {
+    const size_t b = l.meta[v].bytes();
+    std::vector<char> tmp;
+    const char *src = nullptr;
+    try {
+      src = pop.raw(l.names[v]).data();
+      if (pop.raw(l.names[v]).size() != static_cast<size_t>(n) * b) src = nullptr;
+    } catch (const std::out_of_range &) {
+      src = nullptr;
+    }
+    if (!src) {  // variable added after the AgentVector was made (e.g. _auto_sort_bin_index): defaults
+      tmp.resize(static_cast<size_t>(n) * b);
+      for (unsigned int i = 0; i < n; ++i) std::memcpy(tmp.data() + static_cast<size_t>(i) * b, l.meta[v].default_value.data(), b);
+      src = tmp.data();
+    }
+    if (n) FGB_CUDA_THROW(cudaMemcpy(l.data[v], src, static_cast<size_t>(n) * b, cudaMemcpyHostToDevice));
+  }
+  write_slot(l.count_slot, n);
+}
+
+inline unsigned int CUDASimulation::getAgentCount(const std::string &agent_name, const std::string &state) {
+  initialise();
+  return read_slot(state_list(agent_name, state).count_slot);
+}
+
+inline void CUDASimulation::getPopulationData(AgentVector &pop, const std::string &state) {
+  initialise();
+  const std::string &an = pop.getAgentData()->name;
+  detail::DevList &l = state_list(an, state);
+  const unsigned int n = read_slot(l.count_slot);  // synchronises the step stream
+  pop.resize(n);
+  for (size_t v = 0; v < l.names.size(); ++v) {
+    const size_t b = l.meta[v].bytes();
+    std::vector<char> *dst = nullptr;
+    try {
+      dst = &pop.raw(l.names[v]);
+    } catch (const std::out_of_range &) {
+      continue;
+    }
+    if (dst->size() != static_cast<size_t>(n) * b) continue;
+    if (n) FGB_CUDA_THROW(cudaMemcpy(dst->data(), l.data[v], static_cast<size_t>(n) * b, cudaMemcpyDeviceToHost));
+  }
+}
+
+inline void *CUDASimulation::getAgentVariableDevicePtr(const std::string &agent_name, const std::string &state, const std::string &var) {
+  initialise();
+  detail::DevList &l = state_list(agent_name, state);
+  const int i = l.index_of(var);
+  if (i < 0) throw exception::InvalidAgentVar("agent '" + agent_name + "' has no variable '" + var + "'");
+  return l.data[i];
+}
+inline void *CUDASimulation::getMessageVariableDevicePtr(const std::string &message_name, const std::string &var) {
+  initialise();
+  detail::CUDAMessage &m = messages.at(message_name);
+  const int i = m.list.index_of(var);
+  if (i < 0) throw exception::InvalidMessageVar("message '" + message_name + "' has no variable '" + var + "'");
+  return m.list.data[i];
+}
+inline unsigned int CUDASimulation::getMessageCount(const std::string &message_name) {
+  initialise();
+  return read_slot(messages.at(message_name).list.count_slot);
+}
+inline fgb_spatial *CUDASimulation::getSpatialHandler(const std::string &message_name) {
+  initialise();
+  return messages.at(message_name).spatial;
+}
+
+// ---- host-side state that a recorded step mutates (pointer parity, bounds, list flags) -----------
+inline std::vector<unsigned long long> CUDASimulation::snapshot_host_state() const {
+  std::vector<unsigned long long> s;
+  auto put_list = [&](const detail::DevList &l) {
+    s.push_back(l.bound);
+    s.push_back(l.capacity);
+    for (size_t v = 0; v < l.data.size(); ++v) {
+      s.push_back(reinterpret_cast<unsigned long long>(l.data[v]));
+      s.push_back(reinterpret_cast<unsigned long long>(l.swap[v]));
+    }
+  };
+  for (const auto &a : agents)
+    for (const auto &st : a.second.states) put_list(st.second);
+  for (const auto &m : messages) {
+    put_list(m.second.list);
+    s.push_back((m.second.pbm_dirty ? 1ull : 0ull) | (m.second.truncate ? 2ull : 0ull));
+  }
+  return s;
+}
+inline void CUDASimulation::restore_host_state(const std::vector<unsigned long long> &s) {
+  size_t k = 0;
+  auto get_list = [&](detail::DevList &l) {
+    l.bound = static_cast<unsigned int>(s[k++]);
+    l.capacity = static_cast<unsigned int>(s[k++]);
+    for (size_t v = 0; v < l.data.size(); ++v) {
+      l.data[v] = reinterpret_cast<char *>(s[k++]);
+      l.swap[v] = reinterpret_cast<char *>(s[k++]);
+    }
+  };
+  for (auto &a : agents)
+    for (auto &st : a.second.states) get_list(st.second);
+  for (auto &m : messages) {
+    get_list(m.second.list);
+    const unsigned long long f = s[k++];
+    m.second.pbm_dirty = (f & 1ull) != 0;
+    m.second.truncate = (f & 2ull) != 0;
+  }
+}
+inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
+  std::vector<unsigned long long> k = snapshot_host_state();
+  // which functions sort this step (sort period), and the options that change the recorded work
+  unsigned long long sort_bits = 0, bit = 0;
+  for (const auto &l : layers)
+    for (const auto &f : l) {
+      const unsigned int p = f.agent->desc->sort_period;
+      if (f.sortable && p != 0 && step_count % p == 0) sort_bits |= 1ull << (bit & 63);
+      ++bit;
+    }
+  k.push_back(sort_bits);
+  k.push_back(cuda_config.stableMessageOrder ? 1ull : 0ull);
+  return k;
+}
+
+// Reserve capacities for everything the coming step can produce (same bound arithmetic as
+// run_function, no launches).  Allocation is illegal during stream capture, so it happens here.
+inline void CUDASimulation::plan_step() {
+  std::map<const detail::DevList *, unsigned int> b;  // running bounds
+  auto bound_of = [&](const detail::DevList &l) -> unsigned int & {
+    auto it = b.find(&l);
+    if (it == b.end()) it = b.emplace(&l, l.bound).first;
+    return it->second;
+  };
+  std::map<const detail::CUDAMessage *, bool> trunc;
+  for (auto &m : messages) trunc[&m.second] = true;
+  for (auto &layer : layers)
+    for (auto &f : layer) {
+      detail::DevList &L = f.agent->states.at(f.fn->initial_state);
+      const unsigned int n = bound_of(L);
+      if (n == 0) continue;
+      if (f.fn->has_agent_death || f.fn->condition) f.death_flag.reserve(n);
+      if (f.msg_out) {
+        detail::DevList &O = f.msg_out->list;
+        unsigned int &ob = bound_of(O);
+        ob = (trunc[f.msg_out] ? 0u : ob) + n;
+        trunc[f.msg_out] = false;
+        O.reserve(ob, O.capacity);
+        if (f.fn->message_output_optional) f.msg_flag.reserve(n);
+        if (f.msg_out->spatial) FGB_ABI_THROW(fgb_spatial_reserve(f.msg_out->spatial, ob));
+      }
+      if (f.fn->initial_state != f.fn->end_state) {
+        detail::DevList &E = f.agent->states.at(f.fn->end_state);
+        unsigned int &eb = bound_of(E);
+        eb += n;
+        E.reserve(eb, E.capacity);
+      }
+      if (f.out_agent) {
+        f.scratch_new.reserve(n, 0);
+        f.birth_flag.reserve(n);
+        detail::DevList &T = f.out_agent->states.at(f.fn->agent_output_state);
+        unsigned int &tb = bound_of(T);
+        if (&T == &L && f.fn->initial_state != f.fn->end_state) tb = n;
+        else tb += n;
+        T.reserve(tb, T.capacity);
+      }
+      if (f.fn->initial_state != f.fn->end_state && !(f.out_agent && &f.out_agent->states.at(f.fn->agent_output_state) == &L)) bound_of(L) = 0;
+      if (f.sortable) {
+        const fgb_spatial_metadata &md = f.msg_in->md;
+        unsigned long long bins = 1;
+        for (int a = 0; a < f.sort_dims; ++a) bins *= md.environment_width[a] ? static_cast<unsigned int>(ceilf(md.environment_width[a] / md.radius)) : 1u;
+        const int max_bit = static_cast<int>(std::floor(std::log2(static_cast<double>(bins)))) + 1;
+        for (unsigned int sid = 0; sid < std::max<size_t>(1, side_streams.size()); ++sid)
+          FGB_ABI_THROW(fgb_ctx_reserve(ctx, sid, n, max_bit));
+      }
+      for (unsigned int sid = 0; sid < std::max<size_t>(1, side_streams.size()); ++sid) FGB_ABI_THROW(fgb_ctx_reserve(ctx, sid, std::max(n, 1u), 0));
+    }
+  // reserving may have raised list bounds' capacity only; bounds themselves are untouched
+}
+
+inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int sid) {
+  const AgentFunctionData &fn = *f.fn;
+  detail::DevList &L = f.agent->states.at(fn.initial_state);
+  const unsigned int n = L.bound;
+  if (n == 0) return;  // nothing can be in this state list
+  unsigned int *d_n = slot_ptr(L.count_slot);
+  const bool same_state = fn.initial_state == fn.end_state;
+
+  // 1. automatic spatial sort of the executing agents (reference CUDASimulation.cu:463-573)
+  const unsigned int period = f.agent->desc->sort_period;
+  if (f.sortable && period != 0 && step_count % period == 0) {
+    const fgb_spatial_metadata &md = f.msg_in->md;
+    float width[3] = {md.environment_width[0], md.environment_width[1], md.environment_width[2]};
+    unsigned int gd[3] = {1, 1, 1};
+    for (int a = 0; a < f.sort_dims; ++a) gd[a] = width[a] ? static_cast<unsigned int>(ceilf(width[a] / md.radius)) : 1u;  // :498-505
+    const int max_bit = static_cast<int>(std::floor(std::log2(static_cast<double>(gd[0]) * gd[1] * gd[2]))) + 1;         // :571
+    const int ix = L.index_of("x"), iy = L.index_of("y"), iz = f.sort_dims == 3 ? L.index_of("z") : -1;
+    const int ik = L.index_of("_auto_sort_bin_index");
+    unsigned int *keys = reinterpret_cast<unsigned int *>(L.data[ik]);
+    FGB_ABI_THROW(fgb_sort_keys(ctx, reinterpret_cast<const float *>(L.data[ix]), reinterpret_cast<const float *>(L.data[iy]),
+                                iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, md.min, width, gd, n, d_n, keys, st));
+    std::vector<fgb_var> vars = L.vars(true);
+    FGB_ABI_THROW(fgb_sort_by_key(ctx, sid, keys, max_bit, n, d_n, vars.data(), static_cast<unsigned int>(vars.size()), nullptr, st));
+    L.swap_buffers();
+  }
+
+  // 2. index of the input list, built lazily before its first reader (reference :864)
+  if (f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty) {
+    detail::CUDAMessage &M = *f.msg_in;
+    if (M.list.bound > 0) {
+      std::vector<fgb_var> vars = M.list.vars(true);
+      const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
+      FGB_ABI_THROW(fgb_build_index(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
+                                    reinterpret_cast<const float *>(M.list.data[iy]),
+                                    iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
+                                    static_cast<unsigned int>(vars.size()),
+                                    cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+      M.list.swap_buffers();
+    }
+    M.pbm_dirty = false;
+  }
+
+  // 3. kernel arguments
+  detail::FunctionArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.d_count = d_n;
+  a.bound = n;
+  L.fill_table(a.agent);
+  if (f.msg_in) {
+    detail::CUDAMessage &M = *f.msg_in;
+    M.list.fill_table(a.msg_in);
+    a.d_msg_in_count = slot_ptr(M.list.count_slot);
+    if (M.spatial) {
+      for (int k = 0; k < 3; ++k) {
+        a.in_meta.min[k] = M.md.min[k];
+        a.in_meta.max[k] = M.md.max[k];
+        a.in_meta.env_width[k] = M.md.environment_width[k];
+        a.in_meta.grid_dim[k] = static_cast<int>(M.md.grid_dim[k]);
+      }
+      a.in_meta.radius = M.md.radius;
+      a.in_meta.wrap_compatible = M.md.wrap_compatible ? 1 : 0;
+      a.in_meta.pbm = M.md.PBM;
+    }
+  }
+  if (f.msg_out) {
+    detail::DevList &O = f.msg_out->list;
+    O.reserve((f.msg_out->truncate ? 0u : O.bound) + n, O.capacity);
+    O.fill_table(a.msg_out, /*use_swap=*/true);  // functions write the swap list at their thread index
+    if (fn.message_output_optional) {
+      f.msg_flag.reserve(n);
+      a.msg_out_flag = f.msg_flag.p;
+    }
+  }
+  if (f.out_agent) {
+    f.scratch_new.reserve(n, 0);
+    f.birth_flag.reserve(n);
+    f.scratch_new.fill_table(a.agent_out);
+    a.agent_out_nvars = static_cast<uint32_t>(f.default_offsets.size());
+    for (size_t v = 0; v < f.default_offsets.size(); ++v) {
+      a.agent_out_slot[v] = f.scratch_new.slots[v];
+      a.agent_out_len[v] = static_cast<uint32_t>(f.scratch_new.meta[v].bytes());
+      a.agent_out_defaults[v] = f.d_defaults + f.default_offsets[v];
+    }
+    a.agent_out_flag = f.birth_flag.p;
+    a.next_id = slot_ptr(f.out_agent->next_id_slot);
+  }
+  if (fn.has_agent_death) {
+    f.death_flag.reserve(n);
+    a.death_flag = f.death_flag.p;
+  }
+  a.d_step = slot_ptr(kStepSlot);
+  a.env = env_table;
+
+  // 4. the agent function itself
+  {
+    void *kargs[] = {&a};
+    const unsigned int bs = static_cast<unsigned int>(f.block_size);
+    FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, 0, st));
+    ++own_launches;
+  }
+
+  // 5. output message list (reference CUDAMessage::swap, CUDAMessage.cu:171-208)
+  if (f.msg_out) {
+    detail::CUDAMessage &O = *f.msg_out;
+    unsigned int *d_mc = slot_ptr(O.list.count_slot);
+    if (fn.message_output_optional) {
+      std::vector<fgb_var> vars = O.list.vars(/*from_data=*/false);  // swap (written) -> data (read list)
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.msg_flag.p, 0, n, d_n, 0, 0, O.truncate ? nullptr : d_mc, vars.data(),
+                                static_cast<unsigned int>(vars.size()), nullptr, d_mc, st));
+      O.list.bound = (O.truncate ? 0u : O.list.bound) + n;
+    } else if (O.truncate) {
+      O.list.swap_buffers();
+      detail::k_copy_word<<<1, 1, 0, st>>>(d_mc, d_n);
+      ++own_launches;
+      O.list.bound = n;
+    } else {
+      std::vector<fgb_var> vars = O.list.vars(false);
+      FGB_ABI_THROW(fgb_compact(ctx, sid, nullptr, 0, n, d_n, n, 0, d_mc, vars.data(), static_cast<unsigned int>(vars.size()), nullptr,
+                                d_mc, st));
+      O.list.bound += n;
+    }
+    O.truncate = false;
+    O.pbm_dirty = true;  // reference CUDASimulation.cu:1057-1059
+  }
+
+  // 6. death (+ state transition) : reference processDeath then transitionState (:1064-1067)
+  unsigned int *d_tmp = slot_ptr(f.tmp_slot);
+  const bool births = f.out_agent != nullptr;
+  detail::DevList *T = births ? &f.out_agent->states.at(fn.agent_output_state) : nullptr;
+  if (same_state) {
+    if (fn.has_agent_death) {
+      std::vector<fgb_var> vars = L.vars(true);
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.death_flag.p, 0, n, d_n, 0, 0, nullptr, vars.data(), static_cast<unsigned int>(vars.size()),
+                                births ? d_tmp : nullptr, births ? nullptr : d_n, st));
+      L.swap_buffers();
+    }
+  } else {
+    detail::DevList &E = f.agent->states.at(fn.end_state);
+    E.reserve(E.bound + n, E.capacity);
+    std::vector<fgb_var> vars(L.names.size());
+    for (size_t v = 0; v < vars.size(); ++v) {
+      vars[v].type_len = L.meta[v].bytes();
+      vars[v].in = L.data[v];
+      vars[v].out = E.data[v];
+    }
+    unsigned int *d_ec = slot_ptr(E.count_slot);
+    FGB_ABI_THROW(fgb_compact(ctx, sid, fn.has_agent_death ? f.death_flag.p : nullptr, 0, n, d_n, fn.has_agent_death ? 0u : n, 0, d_ec,
+                              vars.data(), static_cast<unsigned int>(vars.size()), nullptr, d_ec, st));
+    E.bound += n;
+  }
+
+  // 7. births appended after the survivors, in parent order (reference CUDAAgentStateList.cu:189-250)
+  bool births_into_vacated = false;
+  if (births) {
+    T->reserve(T->bound + n, T->capacity);
+    std::vector<fgb_var> vars(f.scratch_new.names.size());
+    for (size_t v = 0; v < vars.size(); ++v) {
+      vars[v].type_len = f.scratch_new.meta[v].bytes();
+      vars[v].in = f.scratch_new.data[v];
+      vars[v].out = T->data[v];
+    }
+    const unsigned int nv = static_cast<unsigned int>(vars.size());
+    unsigned int *d_tc = slot_ptr(T->count_slot);
+    if (T == &L && same_state) {
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, fn.has_agent_death ? d_tmp : d_n, vars.data(), nv, nullptr, d_n, st));
+      L.bound += n;
+    } else if (T == &L) {  // the initial state was vacated by the transition: children start at 0
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
+      births_into_vacated = true;
+      L.bound = n;
+    } else {
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, d_tc, vars.data(), nv, nullptr, d_tc, st));
+      T->bound += n;
+      if (same_state && fn.has_agent_death) {
+        detail::k_copy_word<<<1, 1, 0, st>>>(d_n, d_tmp);
+        ++own_launches;
+      }
+    }
+  }
+  if (!same_state && !births_into_vacated) {
+    FGB_CUDA_THROW(cudaMemsetAsync(d_n, 0, 4, st));
+    L.bound = 0;
+  }
+}
+
+inline void CUDASimulation::record_step(cudaStream_t main) {
+  for (auto &m : messages) m.second.truncate = true;  // reference CUDASimulation.cu:599-601
+  for (size_t li = 0; li < layers.size(); ++li) {
+    auto &layer = layers[li];
+    const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty();
+    if (fork) FGB_CUDA_THROW(cudaEventRecord(fork_event, main));
+    for (size_t i = 0; i < layer.size(); ++i) {
+      cudaStream_t st = fork ? side_streams[i] : main;
+      if (fork) FGB_CUDA_THROW(cudaStreamWaitEvent(st, fork_event, 0));
+      run_function(layer[i], st, fork ? static_cast<unsigned int>(i) : 0u);
+      if (fork) {
+        FGB_CUDA_THROW(cudaEventRecord(join_events[i], st));
+        FGB_CUDA_THROW(cudaStreamWaitEvent(main, join_events[i], 0));
+      }
+    }
+    // host-function layers run between graphs (eager mode only)
+    if (!model->layers[li]->host_functions.empty()) {
+      FGB_CUDA_THROW(cudaStreamSynchronize(main));
+      for (auto hf : model->layers[li]->host_functions) hf(&host_api);
+      if (env_dirty) upload_environment();
+    }
+  }
+  // end of step on the device: ++step counter, non-persistent lists emptied (reference :619-625)
+  detail::k_end_of_step<<<1, 32, 0, main>>>(d_ctrl, kStepSlot, d_zero_slots, n_zero_slots);
+  ++own_launches;
+  for (auto &m : messages)
+    if (!m.second.desc->persistent) {
+      m.second.truncate = true;
+      m.second.pbm_dirty = true;
+    }
+}
+
+inline void CUDASimulation::refresh_bounds() {
+  std::vector<unsigned int> h(kCtrlWords);
+  FGB_CUDA_THROW(cudaMemcpyAsync(h.data(), d_ctrl, next_slot * 4, cudaMemcpyDeviceToHost, main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  for (auto &a : agents) {
+    a.second.host_next_id = h[a.second.next_id_slot];
+    for (auto &s : a.second.states) s.second.bound = quantise(h[s.second.count_slot]);
+  }
+}
+
+inline bool CUDASimulation::step() {
+  initialise();
+  if (env_dirty) upload_environment();
+  plan_step();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (config.timing) {
+    FGB_CUDA_THROW(cudaEventCreate(&e0));
+    FGB_CUDA_THROW(cudaEventCreate(&e1));
+    FGB_CUDA_THROW(cudaEventRecord(e0, main_stream));
+  }
+  if (cuda_config.useCUDAGraphs && !model_has_host_layers) {
+    const std::vector<unsigned long long> key = graph_key();
+    GraphEntry *hit = nullptr;
+    for (auto &g : graphs)
+      if (g.key == key) {
+        hit = &g;
+        break;
+      }
+    if (!hit) {
+      const unsigned long long l0 = getLaunchCount();
+      cudaGraph_t graph = nullptr;
+      FGB_CUDA_THROW(cudaStreamBeginCapture(main_stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        record_step(main_stream);
+      } catch (...) {
+        cudaStreamEndCapture(main_stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      FGB_CUDA_THROW(cudaStreamEndCapture(main_stream, &graph));
+      GraphEntry g;
+      g.key = key;
+      FGB_CUDA_THROW(cudaGraphInstantiate(&g.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      g.launches = getLaunchCount() - l0;
+      g.post_state = snapshot_host_state();
+      if (graphs.size() >= 64) {  // bounded cache
+        cudaGraphExecDestroy(graphs.front().exec);
+        graphs.erase(graphs.begin());
+      }
+      graphs.push_back(std::move(g));
+      hit = &graphs.back();
+    } else {
+      restore_host_state(hit->post_state);
+      own_launches += hit->launches;
+    }
+    FGB_CUDA_THROW(cudaGraphLaunch(hit->exec, main_stream));
+  } else {
+    record_step(main_stream);
+  }
+  if (config.timing) {
+    FGB_CUDA_THROW(cudaEventRecord(e1, main_stream));
+    step_events.emplace_back(e0, e1);
+  }
+  ++step_count;
+  if (!model->step_functions.empty()) {
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    for (auto sf : model->step_functions) sf(&host_api);
+  }
+  if (model_has_births) refresh_bounds();
+  bool go_on = true;
+  for (auto ec : model->exit_conditions) {
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    if (ec(&host_api)) go_on = false;
+  }
+  return go_on;
+}
+
+inline void CUDASimulation::simulate() {
+  initialise();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (auto f : model->init_functions) f(&host_api);
+  for (unsigned int i = 0; config.steps == 0 || i < config.steps; ++i)
+    if (!step()) break;
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  for (auto f : model->exit_functions) f(&host_api);
+  elapsed_simulation = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (config.timing) std::printf("Total Processing time: %.3f ms\n", elapsed_simulation * 1e3);
+}
+
+inline std::vector<double> CUDASimulation::getElapsedTimeSteps() {
+  if (initialised) FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  for (auto &e : step_events) {
+    float ms = 0.f;
+    FGB_CUDA_THROW(cudaEventElapsedTime(&ms, e.first, e.second));
+    step_seconds.push_back(ms * 1e-3);
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  step_events.clear();
+  return step_seconds;
+}
+
+// ---- minimal HostAPI -------------------------------------------------------------------------
+inline unsigned int HostAPI::getStepCounter() const { return sim->getStepCounter(); }
+inline unsigned int HostAgentAPI::count() { return sim->getAgentCount(agent, state); }
+template <typename T>
+inline std::vector<T> HostAgentAPI::download(const std::string &variable) {
+  detail::DevList &l = sim->state_list(agent, state);
+  const int i = l.index_of(variable);
+  if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
+  if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
+  const unsigned int n = sim->read_slot(l.count_slot);
+  std::vector<T> h(n);
+  if (n) FGB_CUDA_THROW(cudaMemcpy(h.data(), l.data[i], static_cast<size_t>(n) * sizeof(T), cudaMemcpyDeviceToHost));
+  return h;
+}
+template <typename T>
+inline T HostAgentAPI::sum(const std::string &variable) {
+  T s = T{};
+  for (const T &v : download<T>(variable)) s += v;
+  return s;
+}
+template <typename T>
+inline T HostAgentAPI::min(const std::string &variable) {
+  std::vector<T> h = download<T>(variable);
+  return h.empty() ? T{} : *std::min_element(h.begin(), h.end());
+}
+template <typename T>
+inline T HostAgentAPI::max(const std::string &variable) {
+  std::vector<T> h = download<T>(variable);
+  return h.empty() ? T{} : *std::max_element(h.begin(), h.end());
+}
+template <typename T>
+inline T HostEnvironment::getProperty(const std::string &name) { return sim->getEnvironmentProperty<T>(name); }
+template <typename T>
+inline T HostEnvironment::setProperty(const std::string &name, T value) { return sim->setEnvironmentProperty<T>(name, value); }
+
+}  // namespace flamegpu
+
+#endif  // FGB_INCLUDE_FLAMEGPU_SIMULATION_CUDASIMULATION_IMPL_H_

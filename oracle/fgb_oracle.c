@@ -295,6 +295,34 @@ void orc_circles_step(const orc_grid *g, uint32_t n, uint32_t *id, float *x, flo
   free(mid); free(perm); free(keys); free(mx); free(my); free(mz); free(tmp); free(pbm);
 }
 
+void orc_neighbour_count(const orc_grid *g, const uint32_t *pbm, const uint32_t *mid, const float *mx, const float *my,
+                         const float *mz, uint32_t n_agent, const uint32_t *aid, const float *ax, const float *ay,
+                         const float *az, uint32_t *out) {
+  const float r2 = g->radius * g->radius;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < (int64_t)n_agent; ++i) {
+    int c[3];
+    uint32_t cnt = 0;
+    orc_grid_pos(g, ax[i], ay[i], az[i], c);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dz = -1; dz <= 1; ++dz) {
+        int cy = c[1] + dy, cz = c[2] + dz;
+        if (cy < 0 || cz < 0 || cy >= (int)g->grid_dim[1] || cz >= (int)g->grid_dim[2]) continue;
+        uint32_t s = pbm[orc_hash(g, c[0] - 1, cy, cz)];
+        uint32_t e = pbm[orc_hash(g, c[0] + 1, cy, cz) + 1];
+        for (uint32_t m = s; m < e; ++m) {
+          if (mid[m] == aid[i]) continue;
+          const float dx = mx[m] - ax[i], ddy = my[m] - ay[i], ddz = mz[m] - az[i];
+          const float px = dx * dx, py = ddy * ddy, pz = ddz * ddz;
+          const float s1 = px + py;
+          const float s2 = s1 + pz;
+          if (s2 < r2) ++cnt;
+        }
+      }
+    out[i] = cnt;
+  }
+}
+
 /* Stress model decisions (ours): a 32-bit mix of (id, step); independent of thread order */
 uint32_t orc_hash32(uint32_t a, uint32_t b) {
   uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u + (a << 6) + (a >> 2));

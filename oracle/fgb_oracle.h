@@ -93,6 +93,13 @@ void orc_circles_move(const orc_grid *g, const uint32_t *pbm, uint32_t n_msg, co
 void orc_circles_step(const orc_grid *g, uint32_t n, uint32_t *id, float *x, float *y, float *z, float *drift,
                       float repulse, int do_sort, uint32_t *pbm_out /* may be NULL */);
 
+/* Number of messages with id != own id and strictly inside the radius, per agent, visiting the
+ * reference Filter's bins (examples/stress_model.cuh stress_update).  Each product and sum is
+ * rounded separately (no FMA contraction), matching the __fmul_rn/__fadd_rn device code. */
+void orc_neighbour_count(const orc_grid *g, const uint32_t *pbm, const uint32_t *mid, const float *mx, const float *my,
+                         const float *mz, uint32_t n_agent, const uint32_t *aid, const float *ax, const float *ay,
+                         const float *az, uint32_t *out);
+
 /* integer hash used by the birth/death stress model (ours) */
 uint32_t orc_hash32(uint32_t a, uint32_t b);
 

@@ -129,6 +129,12 @@ class Grid:
             out.append(int(np.ceil(np.float32(w / np.float32(self.radius)))) if w else 1)
         return out + [1] * (3 - self.dims)
 
+    def neighbour_count(self, pbm, mid, mx, my, mz, aid, ax, ay, az):
+        out = np.empty(len(ax), dtype=np.uint32)
+        lib().orc_neighbour_count(self.ref, _p(u32(pbm)), _p(u32(mid)), _p(f32(mx)), _p(f32(my)), _p(f32(mz)),
+                                  C.c_uint32(len(ax)), _p(u32(aid)), _p(f32(ax)), _p(f32(ay)), _p(f32(az)), _p(out))
+        return out
+
     def circles_step(self, ids, x, y, z, drift, repulse=0.05, do_sort=True, want_pbm=False):
         ids, x, y, z, drift = u32(ids).copy(), f32(x).copy(), f32(y).copy(), f32(z).copy(), f32(drift).copy()
         pbm = np.empty(self.bin_count + 1, dtype=np.uint32) if want_pbm else None
