@@ -33,7 +33,7 @@ compile_one() {
 }
 export -f compile_one; export OBJ REF FLAGS
 find "$REF/src/flamegpu" \( -name '*.cu' -o -name '*.cpp' \) \
-  | grep -v -e 'detail/JitifyCache.cu' -e 'io/XMLLogger.cu' -e 'io/XMLStateReader.cu' -e 'io/XMLStateWriter.cu' -e '/MPI' \
+  | grep -v -e 'detail/JitifyCache.cu' -e 'io/XMLLogger.cu' -e 'io/XMLStateReader.cu' -e 'io/XMLStateWriter.cu' -e '/MPI' -e '/visualiser/' \
   | sort > "$OUT/tus.txt"
 xargs -P ${FGB_JOBS:-8} -I{} bash -c 'compile_one {}' < "$OUT/tus.txt"
 nvcc $FLAGS -c "$HERE/link_stubs.cu" -o "$OBJ/link_stubs.o"
