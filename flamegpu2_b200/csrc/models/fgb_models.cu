@@ -109,6 +109,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->CUDAConfig().device_id = device;
     s->sim->CUDAConfig().useCUDAGraphs = getu(kv, "graphs", 1) != 0;
     s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
+    s->sim->CUDAConfig().trueSpatialSortKey = getu(kv, "true3d_sort", 0) != 0;
     s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
     *out = s.release();
   });

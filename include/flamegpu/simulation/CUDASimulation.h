@@ -258,6 +258,8 @@ class CUDASimulation {
     bool inLayerConcurrency = true;
     bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
+    bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
+                                      // key collapses z, CUDASimulation.cu:487; see sort_geometry())
   };
 
   explicit CUDASimulation(const ModelDescription &model_desc, int argc = 0, const char **argv = nullptr)
@@ -344,6 +346,7 @@ class CUDASimulation {
   void record_step(cudaStream_t main);      // enqueue one whole step
   void run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int stream_id);
   void refresh_bounds();                    // births only: read the counts back once per step
+  int sort_geometry(const detail::FunctionRT &f, float mn[3], float width[3], unsigned int gd[3]) const;
   std::vector<unsigned long long> graph_key() const;
   static unsigned int quantise(unsigned int n) {
     if (n <= 4096u) return (n + 255u) & ~255u;

@@ -333,8 +333,31 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
       ++bit;
     }
   k.push_back(sort_bits);
-  k.push_back(cuda_config.stableMessageOrder ? 1ull : 0ull);
+  k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull));
   return k;
+}
+
+// Geometry handed to the sort-key kernel, as spatialSortAgent_async computes it (reference
+// CUDASimulation.cu:480-506,571).  REFERENCE QUIRK kept on purpose (agent order is a parity gate):
+// MessageSpatial3D::Data derives from MessageSpatial2D::Data, so the reference's dynamic_cast at
+// CUDASimulation.cu:487 always takes the 2D branch; for a 3D list envMin.z = envMax.z = 0, hence
+// envWidth.z = 0 and gridDim.z = 1, while the kernel still reads z: the z term degenerates to
+// floorf(((z-0)/0)*1) = +-inf/NaN -> saturated int and only x,y order the agents (on max_bit =
+// floor(log2(gx*gy))+1 bits).  CUDAConfig().trueSpatialSortKey = true uses the intended 3D key.
+inline int CUDASimulation::sort_geometry(const detail::FunctionRT &f, float mn[3], float width[3], unsigned int gd[3]) const {
+  const fgb_spatial_metadata &md = f.msg_in->md;
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = 0.f;
+    width[a] = 0.f;
+    gd[a] = 1u;
+  }
+  const int used = (f.sort_dims == 3 && !cuda_config.trueSpatialSortKey) ? 2 : f.sort_dims;
+  for (int a = 0; a < used; ++a) {
+    mn[a] = md.min[a];
+    width[a] = md.environment_width[a];
+    gd[a] = width[a] ? static_cast<unsigned int>(ceilf(width[a] / md.radius)) : 1u;
+  }
+  return static_cast<int>(std::floor(std::log2(static_cast<double>(gd[0]) * gd[1] * gd[2]))) + 1;
 }
 
 // Reserve capacities for everything the coming step can produce (same bound arithmetic as
@@ -380,10 +403,9 @@ inline void CUDASimulation::plan_step() {
       }
       if (f.fn->initial_state != f.fn->end_state && !(f.out_agent && &f.out_agent->states.at(f.fn->agent_output_state) == &L)) bound_of(L) = 0;
       if (f.sortable) {
-        const fgb_spatial_metadata &md = f.msg_in->md;
-        unsigned long long bins = 1;
-        for (int a = 0; a < f.sort_dims; ++a) bins *= md.environment_width[a] ? static_cast<unsigned int>(ceilf(md.environment_width[a] / md.radius)) : 1u;
-        const int max_bit = static_cast<int>(std::floor(std::log2(static_cast<double>(bins)))) + 1;
+        float mn[3], width[3];
+        unsigned int gd[3];
+        const int max_bit = sort_geometry(f, mn, width, gd);
         for (unsigned int sid = 0; sid < std::max<size_t>(1, side_streams.size()); ++sid)
           FGB_ABI_THROW(fgb_ctx_reserve(ctx, sid, n, max_bit));
       }
@@ -403,16 +425,14 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   // 1. automatic spatial sort of the executing agents (reference CUDASimulation.cu:463-573)
   const unsigned int period = f.agent->desc->sort_period;
   if (f.sortable && period != 0 && step_count % period == 0) {
-    const fgb_spatial_metadata &md = f.msg_in->md;
-    float width[3] = {md.environment_width[0], md.environment_width[1], md.environment_width[2]};
-    unsigned int gd[3] = {1, 1, 1};
-    for (int a = 0; a < f.sort_dims; ++a) gd[a] = width[a] ? static_cast<unsigned int>(ceilf(width[a] / md.radius)) : 1u;  // :498-505
-    const int max_bit = static_cast<int>(std::floor(std::log2(static_cast<double>(gd[0]) * gd[1] * gd[2]))) + 1;         // :571
+    float mn[3], width[3];
+    unsigned int gd[3];
+    const int max_bit = sort_geometry(f, mn, width, gd);
     const int ix = L.index_of("x"), iy = L.index_of("y"), iz = f.sort_dims == 3 ? L.index_of("z") : -1;
     const int ik = L.index_of("_auto_sort_bin_index");
     unsigned int *keys = reinterpret_cast<unsigned int *>(L.data[ik]);
     FGB_ABI_THROW(fgb_sort_keys(ctx, reinterpret_cast<const float *>(L.data[ix]), reinterpret_cast<const float *>(L.data[iy]),
-                                iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, md.min, width, gd, n, d_n, keys, st));
+                                iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, mn, width, gd, n, d_n, keys, st));
     std::vector<fgb_var> vars = L.vars(true);
     FGB_ABI_THROW(fgb_sort_by_key(ctx, sid, keys, max_bit, n, d_n, vars.data(), static_cast<unsigned int>(vars.size()), nullptr, st));
     L.swap_buffers();

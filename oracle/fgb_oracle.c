@@ -171,17 +171,45 @@ uint32_t orc_compact(const uint32_t *flags, int invert, uint32_t n, uint32_t kee
   return out;
 }
 
-/* CUDASimulation.cu:376-408: floorf(((p-min)/width)*gridDim), no clamp; int arithmetic then cast */
-void orc_sort_keys(const orc_grid *g, uint32_t n, const float *x, const float *y, const float *z, uint32_t *keys) {
-  /* CUDASimulation.cu:498-505 recomputes gridDim with ceilf(width/radius) (float), 1 if width==0 */
-  uint32_t gd[3] = {1, 1, 1};
-  for (int a = 0; a < g->dims; ++a) gd[a] = g->env_width[a] ? (uint32_t)ceilf(g->env_width[a] / g->radius) : 1;
+/* CUDA's float -> int conversion (cvt.rzi.s32.f32) saturates and maps NaN to 0; C leaves it undefined */
+static int cuda_f2i(float v) {
+  if (v != v) return 0;
+  if (v >= 2147483648.0f) return 2147483647;
+  if (v <= -2147483648.0f) return (-2147483647 - 1);
+  return (int)v;
+}
+
+/* Geometry spatialSortAgent_async hands to the key kernel (CUDASimulation.cu:480-506).  REFERENCE QUIRK,
+ * reproduced because agent order is a parity gate: a MessageSpatial3D::Data IS-A MessageSpatial2D::Data
+ * (MessageSpatial3DHost.h:120), so the dynamic_cast at CUDASimulation.cu:487 always takes the 2D branch and
+ * envMin.z = envMax.z = 0 => envWidth.z = 0, gridDim.z = 1, while the kernel still reads z (mode Agent3D).
+ * The z term becomes floorf(((z-0)/0)*1) = +-inf/NaN -> saturated int, and only x,y order the agents. */
+void orc_sort_geometry(const orc_grid *g, int true3d, float mn[3], float width[3], uint32_t gd[3]) {
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = 0.0f;
+    width[a] = 0.0f;
+    gd[a] = 1;
+  }
+  const int dims_used = (g->dims == 3 && !true3d) ? 2 : g->dims;
+  for (int a = 0; a < dims_used; ++a) {
+    mn[a] = g->min[a];
+    width[a] = g->env_width[a];
+    gd[a] = width[a] ? (uint32_t)ceilf(width[a] / g->radius) : 1; /* CUDASimulation.cu:498-505 */
+  }
+}
+
+/* calculateSpatialHash, CUDASimulation.cu:376-408: floorf(((p-min)/width)*gridDim), no clamp */
+void orc_sort_keys(const orc_grid *g, int true3d, uint32_t n, const float *x, const float *y, const float *z,
+                   uint32_t *keys) {
+  float mn[3], w[3];
+  uint32_t gd[3];
+  orc_sort_geometry(g, true3d, mn, w, gd);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n; ++i) {
-    int gx = (int)floorf(((x[i] - g->min[0]) / g->env_width[0]) * gd[0]);
-    int gy = (int)floorf(((y[i] - g->min[1]) / g->env_width[1]) * gd[1]);
+    int gx = cuda_f2i(floorf(((x[i] - mn[0]) / w[0]) * gd[0]));
+    int gy = cuda_f2i(floorf(((y[i] - mn[1]) / w[1]) * gd[1]));
     if (g->dims == 3 && z) {
-      int gz = (int)floorf(((z[i] - g->min[2]) / g->env_width[2]) * gd[2]);
+      int gz = cuda_f2i(floorf(((z[i] - mn[2]) / w[2]) * gd[2]));
       /* (gridPos[2] * gridDim.x * gridDim.y + gridPos[1] * gridDim.x + gridPos[0]) in unsigned arithmetic */
       keys[i] = (uint32_t)gz * gd[0] * gd[1] + (uint32_t)gy * gd[0] + (uint32_t)gx;
     } else {
@@ -190,9 +218,11 @@ void orc_sort_keys(const orc_grid *g, uint32_t n, const float *x, const float *y
   }
 }
 
-int orc_sort_max_bit(const orc_grid *g) {
-  uint32_t gd[3] = {1, 1, 1};
-  for (int a = 0; a < g->dims; ++a) gd[a] = g->env_width[a] ? (uint32_t)ceilf(g->env_width[a] / g->radius) : 1;
+/* max_bit = floor(log2(gridDim.x*gridDim.y*gridDim.z)) + 1, CUDASimulation.cu:571 */
+int orc_sort_max_bit(const orc_grid *g, int true3d) {
+  float mn[3], w[3];
+  uint32_t gd[3];
+  orc_sort_geometry(g, true3d, mn, w, gd);
   return (int)floor(log2((double)(gd[0] * gd[1] * gd[2]))) + 1;
 }
 
@@ -282,8 +312,8 @@ void orc_circles_step(const orc_grid *g, uint32_t n, uint32_t *id, float *x, flo
   orc_gather(perm, n, 4, z, mz);
   /* layer 2: auto sort of the agents (positions unchanged by output_message) */
   if (do_sort) {
-    orc_sort_keys(g, n, x, y, z, keys);
-    orc_sort_perm(keys, n, orc_sort_max_bit(g), perm);
+    orc_sort_keys(g, 0, n, x, y, z, keys);
+    orc_sort_perm(keys, n, orc_sort_max_bit(g, 0), perm);
     void *vars[5] = {id, x, y, z, drift};
     for (int v = 0; v < 5; ++v) {
       orc_gather(perm, n, 4, vars[v], tmp);

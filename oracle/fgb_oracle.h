@@ -70,11 +70,14 @@ float orc_virtual(float x2, float x1, float env_width);
  * output j (stable).  Returns the output count. */
 uint32_t orc_compact(const uint32_t *flags, int invert, uint32_t n, uint32_t keep_front, uint32_t *perm);
 
-/* Auto agent sort key, CUDASimulation.cu:376-408 (no clamp); z may be NULL for 2D.
- * grid_dim = ceilf(width/radius) per CUDASimulation.cu:498-505. */
-void orc_sort_keys(const orc_grid *g, uint32_t n, const float *x, const float *y, const float *z, uint32_t *keys);
+/* Geometry the reference hands to its sort-key kernel (CUDASimulation.cu:480-506), including its
+ * quirk for 3D lists (z extent collapses to 0, see fgb_oracle.c); true3d != 0 gives the intended 3D key. */
+void orc_sort_geometry(const orc_grid *g, int true3d, float mn[3], float width[3], uint32_t gd[3]);
+/* Auto agent sort key, calculateSpatialHash CUDASimulation.cu:376-408 (no clamp); z may be NULL for 2D. */
+void orc_sort_keys(const orc_grid *g, int true3d, uint32_t n, const float *x, const float *y, const float *z,
+                   uint32_t *keys);
 /* max_bit = floor(log2(bins))+1, CUDASimulation.cu:571 */
-int orc_sort_max_bit(const orc_grid *g);
+int orc_sort_max_bit(const orc_grid *g, int true3d);
 /* Stable sort on the low max_bit bits (cub::DeviceRadixSort::SortPairs, HostAgentAPI.cuh:900-909):
  * perm[j] = source index of the agent at sorted position j. */
 void orc_sort_perm(const uint32_t *keys, uint32_t n, int max_bit, uint32_t *perm);

@@ -48,6 +48,7 @@ def lib():
         _lib.orc_hash32.restype = C.c_uint32
         _lib.orc_hash32.argtypes = [C.c_uint32, C.c_uint32]
         _lib.orc_sort_max_bit.restype = C.c_int
+        _lib.orc_sort_max_bit.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_num_threads.restype = C.c_int
     return _lib
 
@@ -111,23 +112,22 @@ class Grid:
         assert n <= cap
         return out[:n].copy()
 
-    def sort_keys(self, x, y, z=None):
+    def sort_keys(self, x, y, z=None, true3d=False):
         x, y = f32(x), f32(y)
         zz = f32(z) if z is not None else None
         keys = np.empty(len(x), dtype=np.uint32)
-        lib().orc_sort_keys(self.ref, C.c_uint32(len(x)), _p(x), _p(y), _p(zz), _p(keys))
+        lib().orc_sort_keys(self.ref, C.c_int(int(true3d)), C.c_uint32(len(x)), _p(x), _p(y), _p(zz), _p(keys))
         return keys
 
-    def sort_max_bit(self):
-        return int(lib().orc_sort_max_bit(self.ref))
+    def sort_max_bit(self, true3d=False):
+        return int(lib().orc_sort_max_bit(self.ref, C.c_int(int(true3d))))
 
-    def sort_grid_dim(self):
-        """gridDim as CUDASimulation.cu:498-505 computes it (ceilf(width/radius))."""
-        out = []
-        for a in range(self.dims):
-            w = np.float32(self.env_width[a])
-            out.append(int(np.ceil(np.float32(w / np.float32(self.radius)))) if w else 1)
-        return out + [1] * (3 - self.dims)
+    def sort_geometry(self, true3d=False):
+        """(min[3], width[3], grid_dim[3]) as the reference passes them to calculateSpatialHash
+        (CUDASimulation.cu:480-506), including its 3D quirk unless true3d."""
+        mn, w, gd = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_uint32 * 3)()
+        lib().orc_sort_geometry(self.ref, C.c_int(int(true3d)), mn, w, gd)
+        return [float(v) for v in mn], [float(v) for v in w], [int(v) for v in gd]
 
     def neighbour_count(self, pbm, mid, mx, my, mz, aid, ax, ay, az):
         out = np.empty(len(ax), dtype=np.uint32)

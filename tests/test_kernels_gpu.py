@@ -239,9 +239,11 @@ def test_scatter_all_gather_broadcast(ctx):
     assert np.all(o2.cpu().numpy()[40:] == [1, 2, 3])
 
 
+@pytest.mark.parametrize("true3d", [False, True])
 @pytest.mark.parametrize("n", [4, 1000, 200003])
-def test_agent_sort(ctx, n):
-    # auto-sort: key kernel bit-exact, stable order bit-exact (test_spatial_agent_sort.cu:69-111)
+def test_agent_sort(ctx, n, true3d):
+    # auto-sort: key kernel bit-exact (including the reference's collapsed-z quirk for 3D lists,
+    # CUDASimulation.cu:487), stable order bit-exact (test_spatial_agent_sort.cu:69-111)
     g = orc.Grid(3, (-5, -5, -5), (5, 5, 5), 0.2)
     rng = np.random.default_rng(n)
     if n == 4:
@@ -249,12 +251,13 @@ def test_agent_sort(ctx, n):
         pos = [p, p.copy(), p.copy()]
     else:
         pos = [rng.uniform(-5.3, 5.3, n).astype(np.float32) for _ in range(3)]  # out-of-range keys wrap in uint
-    keys_ref = g.sort_keys(*pos)
+    keys_ref = g.sort_keys(*pos, true3d=true3d)
     keys = torch.zeros(n, dtype=torch.int32, device=DEV)
     ins = [t(p) for p in pos]
-    ctx.sort_keys(ins[0], ins[1], ins[2], g.min, g.env_width, g.sort_grid_dim(), n, keys)
+    mn, w, gd = g.sort_geometry(true3d)
+    ctx.sort_keys(ins[0], ins[1], ins[2], mn, w, gd, n, keys)
     assert np.array_equal(as_u32(keys), keys_ref)
-    mb = g.sort_max_bit()
+    mb = g.sort_max_bit(true3d)
     perm_ref = orc.sort_perm(keys_ref, mb)
     order = np.arange(n, dtype=np.uint32)
     ins2 = ins + [t(order)]
@@ -281,7 +284,8 @@ def test_agent_sort_2d_and_many_ties(ctx):
     pos = [rng.uniform(0, 8, n).astype(np.float32) for _ in range(2)]
     keys_ref = g.sort_keys(pos[0], pos[1])
     keys = torch.zeros(n, dtype=torch.int32, device=DEV)
-    ctx.sort_keys(t(pos[0]), t(pos[1]), None, g.min, g.env_width, g.sort_grid_dim(), n, keys)
+    mn, w, gd = g.sort_geometry()
+    ctx.sort_keys(t(pos[0]), t(pos[1]), None, mn, w, gd, n, keys)
     assert np.array_equal(as_u32(keys), keys_ref)
     mb = g.sort_max_bit()
     order = np.arange(n, dtype=np.uint32)

@@ -309,3 +309,18 @@ def test_boids_run_and_stay_in_bounds():
         assert sp.max() <= 1.0 + 0.05 * np.sqrt(dims) + 1e-4
         assert sorted(s.get("Boid", "_id", np.uint32)) == list(range(1, n + 1))
         s.close()
+
+
+def test_true3d_sort_key_extension():
+    # b200 extension: the intended x,y,z sort key (the reference's key collapses z, CUDASimulation.cu:487)
+    n, L = 30000, 31.0
+    pos = _circles_pop(n, L, seed=33)
+    g = orc.Grid(3, (0, 0, 0), (L, L, L), 2.0)
+    s = _sim("circles", env_max=L, radius=2.0, true3d_sort=1)
+    s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+    s.step(1)
+    keys = g.sort_keys(*pos, true3d=True)
+    perm = orc.sort_perm(keys, g.sort_max_bit(True))
+    assert np.array_equal(s.get("Circle", "_id", np.uint32), perm + 1)
+    assert np.array_equal(s.get("Circle", "_auto_sort_bin_index", np.uint32), keys[perm])
+    s.close()
