@@ -111,6 +111,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
     s->sim->CUDAConfig().trueSpatialSortKey = getu(kv, "true3d_sort", 0) != 0;
     s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
+    s->sim->CUDAConfig().profile = getu(kv, "profile", 0) != 0;
     *out = s.release();
   });
 }
@@ -178,6 +179,24 @@ int fgbm_step_times(void *h, double *out, unsigned int cap, unsigned int *n) {
     std::vector<double> t = static_cast<Sim *>(h)->sim->getElapsedTimeSteps();
     *n = static_cast<unsigned int>(t.size());
     for (unsigned int i = 0; i < cap && i < t.size(); ++i) out[i] = t[i];
+  });
+}
+
+// Phase profile (model created with profile=1): JSON {"phase": [total_ms, calls], ...} into buf.
+int fgbm_profile(void *h, char *buf, size_t cap) {
+  return guarded([&] {
+    auto p = static_cast<Sim *>(h)->sim->getProfile();
+    std::string js = "{";
+    bool first = true;
+    for (const auto &kv : p) {
+      char tmp[256];
+      std::snprintf(tmp, sizeof(tmp), "%s\"%s\": [%.6f, %u]", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+      js += tmp;
+      first = false;
+    }
+    js += "}";
+    if (js.size() + 1 > cap) throw std::runtime_error("profile buffer too small");
+    std::memcpy(buf, js.c_str(), js.size() + 1);
   });
 }
 

@@ -50,6 +50,7 @@ def lib():
         L.fgbm_step_counter.argtypes = [C.c_void_p]
         L.fgbm_step_counter.restype = C.c_uint
         L.fgbm_step_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint, C.POINTER(C.c_uint)]
+        L.fgbm_profile.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.fgbm_message_count.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint)]
         L.fgbm_message_pbm.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_uint)]
         L.fgbm_message_variable.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
@@ -134,6 +135,14 @@ class Simulation:
         n = C.c_uint()
         _check(lib().fgbm_step_times(self.h, buf, cap, C.byref(n)), "fgbm_step_times")
         return np.array(buf[: min(cap, n.value)])
+
+    def profile(self) -> dict:
+        """{phase: (total_ms, calls)} since the last call (model created with profile=1)."""
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().fgbm_profile(self.h, buf, len(buf)), "fgbm_profile")
+        return {k: (v[0], v[1]) for k, v in json.loads(buf.value.decode()).items()}
 
     def message_count(self, message: str) -> int:
         n = C.c_uint()

@@ -258,6 +258,7 @@ class CUDASimulation {
     bool inLayerConcurrency = true;
     bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
+    bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
                                       // key collapses z, CUDASimulation.cu:487; see sort_geometry())
   };
@@ -305,6 +306,8 @@ class CUDASimulation {
   unsigned long long getLaunchCount() const { return (ctx ? fgb_launch_count(ctx) : 0ull) + own_launches; }
   unsigned int getGraphCount() const { return static_cast<unsigned int>(graphs.size()); }
   cudaStream_t getStream() const { return main_stream; }
+  // phase name -> (total milliseconds, calls) since the last call; only filled when CUDAConfig().profile
+  std::map<std::string, std::pair<double, unsigned int>> getProfile();
   void synchronize() { if (initialised) FGB_CUDA_THROW(cudaStreamSynchronize(main_stream)); }
 
  private:
@@ -390,6 +393,24 @@ class CUDASimulation {
     std::vector<unsigned long long> post_state;
   };
   std::vector<GraphEntry> graphs;
+  struct ProfRec {
+    std::string name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRec> prof;
+  void prof_begin(const std::string &name, cudaStream_t st) {
+    if (!cuda_config.profile) return;
+    ProfRec r;
+    r.name = name;
+    FGB_CUDA_THROW(cudaEventCreate(&r.e0));
+    FGB_CUDA_THROW(cudaEventCreate(&r.e1));
+    FGB_CUDA_THROW(cudaEventRecord(r.e0, st));
+    prof.push_back(r);
+  }
+  void prof_end(cudaStream_t st) {
+    if (!cuda_config.profile) return;
+    FGB_CUDA_THROW(cudaEventRecord(prof.back().e1, st));
+  }
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> step_events;
   std::vector<double> step_seconds;
   double elapsed_simulation = 0.0;

@@ -428,6 +428,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     float mn[3], width[3];
     unsigned int gd[3];
     const int max_bit = sort_geometry(f, mn, width, gd);
+    prof_begin("agent_sort", st);
     const int ix = L.index_of("x"), iy = L.index_of("y"), iz = f.sort_dims == 3 ? L.index_of("z") : -1;
     const int ik = L.index_of("_auto_sort_bin_index");
     unsigned int *keys = reinterpret_cast<unsigned int *>(L.data[ik]);
@@ -436,12 +437,14 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     std::vector<fgb_var> vars = L.vars(true);
     FGB_ABI_THROW(fgb_sort_by_key(ctx, sid, keys, max_bit, n, d_n, vars.data(), static_cast<unsigned int>(vars.size()), nullptr, st));
     L.swap_buffers();
+    prof_end(st);
   }
 
   // 2. index of the input list, built lazily before its first reader (reference :864)
   if (f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty) {
     detail::CUDAMessage &M = *f.msg_in;
     if (M.list.bound > 0) {
+      prof_begin("build_index", st);
       std::vector<fgb_var> vars = M.list.vars(true);
       const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
       FGB_ABI_THROW(fgb_build_index(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
@@ -450,6 +453,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
                                     static_cast<unsigned int>(vars.size()),
                                     cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
       M.list.swap_buffers();
+      prof_end(st);
     }
     M.pbm_dirty = false;
   }
@@ -509,11 +513,14 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   {
     void *kargs[] = {&a};
     const unsigned int bs = static_cast<unsigned int>(f.block_size);
+    prof_begin("function:" + fn.name, st);
     FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, 0, st));
+    prof_end(st);
     ++own_launches;
   }
 
   // 5. output message list (reference CUDAMessage::swap, CUDAMessage.cu:171-208)
+  prof_begin("post:" + fn.name, st);
   if (f.msg_out) {
     detail::CUDAMessage &O = *f.msg_out;
     unsigned int *d_mc = slot_ptr(O.list.count_slot);
@@ -595,6 +602,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     FGB_CUDA_THROW(cudaMemsetAsync(d_n, 0, 4, st));
     L.bound = 0;
   }
+  prof_end(st);
 }
 
 inline void CUDASimulation::record_step(cudaStream_t main) {
@@ -649,7 +657,7 @@ inline bool CUDASimulation::step() {
     FGB_CUDA_THROW(cudaEventCreate(&e1));
     FGB_CUDA_THROW(cudaEventRecord(e0, main_stream));
   }
-  if (cuda_config.useCUDAGraphs && !model_has_host_layers) {
+  if (cuda_config.useCUDAGraphs && !model_has_host_layers && !cuda_config.profile) {
     const std::vector<unsigned long long> key = graph_key();
     GraphEntry *hit = nullptr;
     for (auto &g : graphs)
@@ -730,6 +738,22 @@ inline std::vector<double> CUDASimulation::getElapsedTimeSteps() {
   }
   step_events.clear();
   return step_seconds;
+}
+
+inline std::map<std::string, std::pair<double, unsigned int>> CUDASimulation::getProfile() {
+  std::map<std::string, std::pair<double, unsigned int>> out;
+  if (initialised) FGB_CUDA_THROW(cudaDeviceSynchronize());
+  for (auto &r : prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      out[r.name].first += ms;
+      out[r.name].second += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  prof.clear();
+  return out;
 }
 
 // ---- minimal HostAPI -------------------------------------------------------------------------
