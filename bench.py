@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda / e2e legs")
     ap.add_argument("--stable", type=int, default=0)
     ap.add_argument("--true3d-sort", type=int, default=0)
+    ap.add_argument("--bin-order", type=int, default=1, help="run message-reading functions in bin order (b200 extension)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -202,7 +203,7 @@ def main():
     bins = int(np.ceil(L / RADIUS)) ** 3
     x, y, z = population(n, L, seed=rank)
     s = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
-                        true3d_sort=args.true3d_sort)
+                        true3d_sort=args.true3d_sort, bin_order=args.bin_order)
     s.set_population("Circle", {"x": x, "y": y, "z": z})
     stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=f"cuda:{local}")
@@ -246,7 +247,7 @@ def main():
         "config": {
             "workload": f"Circles-3D, {n} agents per GPU, [0,{L:g})^3, radius {RADIUS:g} ({bins} bins, ~8 agents/bin), "
                         f"whole CUDASimulation::step() (output_message, auto agent sort, PBM buildIndex, move)",
-            "agents_per_gpu": n, "bins": bins, "graphs": s.graphs,
+            "agents_per_gpu": n, "bins": bins, "graphs": s.graphs, "bin_order_execution": bool(args.bin_order),
             "l2": "flushed between steps (256 MiB write outside the timed events)",
             "timing": "sum of per-step CUDA-event times on the simulation stream, max over ranks",
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
@@ -259,7 +260,7 @@ def main():
         peak, peak_src = measured_peak()
         # -- per-phase device times from a profiled (eager, event-bracketed) pass of the same workload
         p = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, profile=1, stable=args.stable,
-                            true3d_sort=args.true3d_sort)
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order)
         p.set_population("Circle", {"x": x, "y": y, "z": z})
         pstream = torch.cuda.ExternalStream(p.stream, device=f"cuda:{local}")
         for i in range(args.warmup + 30):

@@ -55,6 +55,8 @@ SIGNATURES = {
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),
     "fgb_build_index": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p]),
+    "fgb_bin_permutation": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_uint, C.c_void_p]),
     "fgb_exclusive_scan_u32": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "fgb_compact": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_uint, C.c_uint,
                               C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -120,6 +120,42 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
 
 }  // namespace
 
+namespace {
+template <int DIMS>
+int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                         const float *z, unsigned int *perm, unsigned int flags, cudaStream_t st) {
+  fgb_ctx *ctx = sp->ctx;
+  KeySrc<DIMS> src{};
+  src.x = x;
+  src.y = y;
+  src.z = z;
+  src.g = Geo{sp->md.min[0], sp->md.min[1], sp->md.min[2], sp->md.radius, static_cast<int>(sp->md.grid_dim[0]),
+              static_cast<int>(sp->md.grid_dim[1]), static_cast<int>(sp->md.grid_dim[2])};
+  const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
+  const unsigned int grid = bin_grid(n);
+  const unsigned int B = sp->bin_count;
+  VarTable none{};
+  none.n = 0;
+  if (flags & FGB_BUILD_STABLE) {
+    int r = sp->worklist.reserve(worklist_bytes(n));
+    if (r) return r;
+  }
+  if (vec) {
+    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+    k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
+    k_bin_scatter<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm);
+  } else {
+    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+    k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
+    k_bin_scatter<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm);
+  }
+  ctx->launches += 3;
+  if (flags & FGB_BUILD_STABLE)
+    return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
+  return launch_ok();
+}
+}  // namespace
+
 extern "C" {
 
 int fgb_version(void) { return FGB_VERSION; }
@@ -265,6 +301,16 @@ fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *
   if (!x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;
   if (sp->dims == 3) return build_index_impl<3>(sp, n, d_n, x, y, z, vars, nvars, flags, st);
   return build_index_impl<2>(sp, n, d_n, x, y, nullptr, vars, nvars, flags, st);
+}
+
+fgb_status fgb_bin_permutation(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                               const float *z, unsigned int *perm_out, unsigned int flags, void *stream) {
+  if (!sp || !perm_out) return FGB_ERR_INVALID_ARG;
+  if (n == 0) return FGB_OK;
+  if (!x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sp->dims == 3) return bin_permutation_impl<3>(sp, n, d_n, x, y, z, perm_out, flags, st);
+  return bin_permutation_impl<2>(sp, n, d_n, x, y, nullptr, perm_out, flags, st);
 }
 
 fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_max, int max_bit) {

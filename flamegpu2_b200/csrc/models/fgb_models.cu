@@ -112,6 +112,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->CUDAConfig().trueSpatialSortKey = getu(kv, "true3d_sort", 0) != 0;
     s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
     s->sim->CUDAConfig().profile = getu(kv, "profile", 0) != 0;
+    s->sim->CUDAConfig().binOrderExecution = getu(kv, "bin_order", 1) != 0;
     *out = s.release();
   });
 }

@@ -169,6 +169,11 @@ class Spatial:
                "fgb_spatial_read_pbm")
         return out
 
+    def bin_permutation(self, x, y, z, perm_out, n: int, *, stable=False, d_n=None):
+        flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT
+        _check(lib().fgb_bin_permutation(self.h, n, _ptr(d_n), _ptr(x), _ptr(y), _ptr(z), _ptr(perm_out), flags, _stream_ptr()),
+               "fgb_bin_permutation")
+
     def build_index(self, x, y, z, ins, outs, n: int, *, stable=False, d_n=None):
         arr, nv = make_vars(ins, outs)
         flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT

@@ -191,6 +191,8 @@ struct FunctionRT {
   DevFlags death_flag, msg_flag, birth_flag;
   bool sortable = false;
   int sort_dims = 0;
+  fgb_spatial *exec_binner = nullptr;  // bins the executing agents on the input list's grid
+  DevFlags exec_perm;
   unsigned int tmp_slot = 0;  // control word scratch (survivor count)
   int block_size = 128;
 };
@@ -258,6 +260,7 @@ class CUDASimulation {
     bool inLayerConcurrency = true;
     bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
+    bool binOrderExecution = true;    // b200: run functions that read spatial messages in bin order
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
                                       // key collapses z, CUDASimulation.cu:487; see sort_geometry())

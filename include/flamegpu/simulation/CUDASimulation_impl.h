@@ -113,6 +113,8 @@ inline void CUDASimulation::initialise() {
         if (is_f("x") && is_f("y") && (d == 2 || is_f("z"))) {
           f.sortable = true;
           f.sort_dims = d;
+          const MessageData &md = *f.msg_in->desc;
+          FGB_ABI_THROW(fgb_spatial_create(ctx, d, md.min, md.max, md.radius, &f.exec_binner));
         }
       }
     }
@@ -169,6 +171,8 @@ inline void CUDASimulation::destroy() {
       f.msg_flag.release();
       f.birth_flag.release();
       if (f.d_defaults) cudaFree(f.d_defaults);
+      f.exec_perm.release();
+      if (f.exec_binner) fgb_spatial_destroy(f.exec_binner);
     }
   for (auto &a : agents)
     for (auto &s : a.second.states) s.second.release();
@@ -333,7 +337,8 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
       ++bit;
     }
   k.push_back(sort_bits);
-  k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull));
+  k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull) |
+              (cuda_config.binOrderExecution ? 4ull : 0ull));
   return k;
 }
 
@@ -377,6 +382,10 @@ inline void CUDASimulation::plan_step() {
       const unsigned int n = bound_of(L);
       if (n == 0) continue;
       if (f.fn->has_agent_death || f.fn->condition) f.death_flag.reserve(n);
+      if (f.exec_binner) {
+        f.exec_perm.reserve(n);
+        FGB_ABI_THROW(fgb_spatial_reserve(f.exec_binner, n));
+      }
       if (f.msg_out) {
         detail::DevList &O = f.msg_out->list;
         unsigned int &ob = bound_of(O);
@@ -458,10 +467,24 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     M.pbm_dirty = false;
   }
 
+  // 2b. execution order: bin the executing agents on the input list's grid (b200 extension)
+  const bool bin_order = f.exec_binner && cuda_config.binOrderExecution;
+  if (bin_order) {
+    prof_begin("exec_order", st);
+    f.exec_perm.reserve(n);
+    const int ix = L.index_of("x"), iy = L.index_of("y"), iz = f.sort_dims == 3 ? L.index_of("z") : -1;
+    FGB_ABI_THROW(fgb_bin_permutation(f.exec_binner, n, d_n, reinterpret_cast<const float *>(L.data[ix]),
+                                      reinterpret_cast<const float *>(L.data[iy]),
+                                      iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, f.exec_perm.p,
+                                      cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+    prof_end(st);
+  }
+
   // 3. kernel arguments
   detail::FunctionArgs a;
   std::memset(&a, 0, sizeof(a));
   a.d_count = d_n;
+  a.exec_perm = bin_order ? f.exec_perm.p : nullptr;
   a.bound = n;
   L.fill_table(a.agent);
   if (f.msg_in) {

@@ -124,6 +124,14 @@ enum fgb_build_flags {
 fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
                            const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, void *stream);
 
+/* B200 extension (no reference counterpart): the permutation that WOULD group `n` points by bin,
+ * without moving any payload: perm_out[j] = index of the point at grouped position j, and the
+ * handler's PBM receives the bin offsets of the points.  Used by the step scheduler to run an agent
+ * function in bin order (warp lanes share message strips) while the agent list itself stays in the
+ * reference's order.  Same kernels as fgb_build_index (histogram, scan, cursor scatter). */
+fgb_status fgb_bin_permutation(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                               const float *z, unsigned int *perm_out, unsigned int flags, void *stream);
+
 /* ---- scan / compaction / data movement ------------------------------------------------------ */
 /* cub::DeviceScan::ExclusiveSum as called at CUDAFatAgent.cu:118-132, CUDAAgentStateList.cu:195-210,
  * CUDAMessage.cu:180-194: out[i] = sum_{j<i} in[j] for i in [0,n]  (n+1 outputs, out[n] = total),

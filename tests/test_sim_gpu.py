@@ -324,3 +324,18 @@ def test_true3d_sort_key_extension():
     assert np.array_equal(s.get("Circle", "_id", np.uint32), perm + 1)
     assert np.array_equal(s.get("Circle", "_auto_sort_bin_index", np.uint32), keys[perm])
     s.close()
+
+
+def test_bin_order_execution_does_not_change_results():
+    # the execution-order permutation only changes which thread runs which agent
+    n, L = 60000, 39.0
+    pos = _circles_pop(n, L, seed=44)
+    res = []
+    for bin_order in (0, 1):
+        s = _sim("circles", env_max=L, radius=2.0, stable=1, bin_order=bin_order)
+        s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+        s.step(3)
+        res.append([s.get("Circle", v, np.float32) for v in ("x", "y", "z", "drift")] + [s.get("Circle", "_id", np.uint32)])
+        s.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
