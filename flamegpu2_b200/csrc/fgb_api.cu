@@ -9,6 +9,7 @@
 #include "fgb_binsort.cuh"
 #include "fgb_common.cuh"
 #include "fgb_compact.cuh"
+#include "fgb_radix.cuh"
 #include "fgb_scan.cuh"
 
 using namespace fgb;
@@ -198,6 +199,9 @@ fgb_status fgb_ctx_destroy(fgb_ctx *ctx) {
     s.perm.release();
     s.worklist.release();
     s.ctrl.release();
+    s.rs_state.release();
+    for (auto &b : s.rs_keys) b.release();
+    for (auto &b : s.rs_idx) b.release();
   }
   delete ctx;
   return FGB_OK;
@@ -321,15 +325,20 @@ fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_
   const size_t tiles = std::max<size_t>(compact_num_tiles(n_max), 1);
   size_t state_words = tiles;
   if (max_bit > 0) {
-    const size_t H = static_cast<size_t>(1) << max_bit;
-    state_words = std::max(state_words, static_cast<size_t>(scan_num_tiles(static_cast<unsigned int>(H))));
-    r = reserve_zeroed(s.sort_hist, (H + 1) * 4);
+    const RadixPlan plan = make_radix_plan(max_bit);
+    const size_t tiles = std::max<size_t>(radix_num_tiles(n_max), 1);
+    size_t words = static_cast<size_t>(kRsMaxPasses) * kRsMaxDigits;
+    for (int p = 0; p < plan.passes; ++p) words += tiles * (static_cast<size_t>(1) << plan.bits[p]);
+    r = s.rs_state.reserve(words * 4);
     if (r) return r;
-    r = s.sort_cursor.reserve((H + 1) * 4);
-    if (r) return r;
-    r = s.worklist.reserve(worklist_bytes(n_max));
-    if (r) return r;
-    r = s.perm.reserve(static_cast<size_t>(std::max(n_max, 1u)) * 4);
+    const size_t nb = static_cast<size_t>(std::max(n_max, 1u)) * 4;
+    for (int i = 0; i < 2; ++i) {
+      r = s.rs_keys[i].reserve(nb);
+      if (r) return r;
+      r = s.rs_idx[i].reserve(nb);
+      if (r) return r;
+    }
+    r = s.perm.reserve(nb);
     if (r) return r;
   }
   return reserve_zeroed(s.tile_state, state_words * 8);
@@ -470,35 +479,41 @@ fgb_status fgb_sort_by_key(fgb_ctx *ctx, unsigned int stream_id, const unsigned 
   int r = fgb_ctx_reserve(ctx, stream_id, n, max_bit);
   if (r) return r;
   fgb_stream_scratch &s = ctx->slot[stream_id];
-  const unsigned int H = 1u << max_bit;
-  uint32_t *hist = static_cast<uint32_t *>(s.sort_hist.p);
-  uint32_t *cursor = static_cast<uint32_t *>(s.sort_cursor.p);
-  unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
-  uint32_t *ctrl = static_cast<uint32_t *>(s.ctrl.p);
+  const RadixPlan plan = make_radix_plan(max_bit);
+  const unsigned int tiles = radix_num_tiles(n);
+  uint32_t *ghist = static_cast<uint32_t *>(s.rs_state.p);
   uint32_t *perm = position_out ? position_out : static_cast<uint32_t *>(s.perm.p);
-  uint32_t *worklist = static_cast<uint32_t *>(s.worklist.p);
-  KeySrc<0> src{};
-  src.keys = keys;
-  src.mask = H - 1u;
-  VarTable none{};
-  none.n = 0;
-  const unsigned int grid = bin_grid(n);
-  const unsigned int n_state = scan_num_tiles(H);
-  if (aligned16(keys)) {
-    k_bin_hist<0, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, hist, state, n_state, ctrl);
-    k_exclusive_scan<true><<<n_state, kScanThreads, 0, st>>>(hist, cursor, H, state, 1, 1);
-    k_bin_scatter<0, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, cursor, none, perm);
-  } else {
-    k_bin_hist<0, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, hist, state, n_state, ctrl);
-    k_exclusive_scan<true><<<n_state, kScanThreads, 0, st>>>(hist, cursor, H, state, 1, 1);
-    k_bin_scatter<0, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, cursor, none, perm);
+  size_t words = static_cast<size_t>(kRsMaxPasses) * kRsMaxDigits;
+  size_t state_off[kRsMaxPasses];
+  for (int p = 0; p < plan.passes; ++p) {
+    state_off[p] = words;
+    words += static_cast<size_t>(tiles) * (static_cast<size_t>(1) << plan.bits[p]);
   }
-  ctx->launches += 3;
-  r = stable_tail(ctx, cursor, H, perm, worklist, ctrl, n, d_n, vars, nvars, st);
-  if (r) return r;
-  // leave the look-back words clean for the compaction kernels sharing this slot
-  FGB_CHECK(cudaMemsetAsync(state, 0, static_cast<size_t>(n_state) * 8, st));
-  return FGB_OK;
+  FGB_CHECK(cudaMemsetAsync(ghist, 0, words * 4, st));
+  const unsigned int hgrid = std::min<unsigned int>(tiles, 4u * kNumSMs);
+  k_radix_hist<<<hgrid, kRsThreads, 0, st>>>(keys, n, d_n, plan, ghist);
+  const uint32_t key_mask = (max_bit >= 32) ? 0xFFFFFFFFu : ((1u << max_bit) - 1u);
+  for (int p = 0; p < plan.passes; ++p) {
+    const bool last = p == plan.passes - 1;
+    const uint32_t *kin = p == 0 ? keys : static_cast<const uint32_t *>(s.rs_keys[(p - 1) & 1].p);
+    const uint32_t *iin = p == 0 ? nullptr : static_cast<const uint32_t *>(s.rs_idx[(p - 1) & 1].p);
+    uint32_t *kout = last ? nullptr : static_cast<uint32_t *>(s.rs_keys[p & 1].p);
+    uint32_t *iout = last ? perm : static_cast<uint32_t *>(s.rs_idx[p & 1].p);
+    k_radix_onesweep<<<tiles, kRsThreads, 0, st>>>(kin, iin, kout, iout, n, d_n, plan.shift[p], plan.bits[p], key_mask,
+                                                    ghist + p * kRsMaxDigits, ghist + state_off[p]);
+  }
+  ctx->launches += 1 + plan.passes;
+  if (nvars) {
+    VarTable vt;
+    r = make_var_table(vars, nvars, &vt);
+    if (r) return r;
+    if (aligned16(perm) && vars_out_aligned(vars, nvars))
+      k_gather<true><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    else
+      k_gather<false><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    ctx->launches += 1;
+  }
+  return launch_ok();
 }
 
 }  // extern "C"

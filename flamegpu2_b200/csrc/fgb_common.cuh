@@ -208,6 +208,9 @@ struct fgb_stream_scratch {
   fgb::DevBuf perm;         // permutation scratch
   fgb::DevBuf worklist;     // big-bin worklist
   fgb::DevBuf ctrl;         // small control words
+  fgb::DevBuf rs_state;     // radix sort: digit histograms + per-pass look-back words
+  fgb::DevBuf rs_keys[2];   // radix sort: key ping-pong
+  fgb::DevBuf rs_idx[2];    // radix sort: index ping-pong
 };
 
 #define FGB_MAX_STREAMS 128

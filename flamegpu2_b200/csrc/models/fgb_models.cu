@@ -238,13 +238,11 @@ int fgbm_circles_step_host(void *h, unsigned int n, const float *x, const float 
     Sim *s = static_cast<Sim *>(h);
     const char *names[4] = {"x", "y", "z", "drift"};
     const void *ptrs[4] = {x, y, z, drift};
-    if (fgbm_set_population(h, "Circle", nullptr, n, 4, names, ptrs) != 0) throw std::runtime_error(g_last_error);
+    s->sim->setPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, n, 4, names, ptrs);
     for (unsigned int i = 0; i < steps; ++i) s->sim->step();
-    const size_t b = static_cast<size_t>(n) * 4;
-    if (fgbm_get_variable(h, "Circle", nullptr, "x", x_out, b) || fgbm_get_variable(h, "Circle", nullptr, "y", y_out, b) ||
-        fgbm_get_variable(h, "Circle", nullptr, "z", z_out, b) || fgbm_get_variable(h, "Circle", nullptr, "drift", drift_out, b) ||
-        (id_out && fgbm_get_variable(h, "Circle", nullptr, "_id", id_out, b)))
-      throw std::runtime_error(g_last_error);
+    const char *onames[5] = {"x", "y", "z", "drift", "_id"};
+    void *optrs[5] = {x_out, y_out, z_out, drift_out, id_out};
+    s->sim->getPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, id_out ? 5 : 4, onames, optrs, n);
   });
 }
 

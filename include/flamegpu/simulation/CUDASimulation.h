@@ -63,6 +63,10 @@ __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const 
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
+__global__ void k_iota(unsigned int *dst, unsigned int n, unsigned int first) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = first + i;
+}
 #endif
 
 // One SoA list on the device: an agent state list, a message list or a new-agent scratch list.
@@ -301,6 +305,14 @@ class CUDASimulation {
   unsigned int getAgentCount(const std::string &agent_name, const std::string &state = DEFAULT_STATE);
 
   // ---- b200 extensions used by the parity harness / bench (no reference counterpart) -------------
+  // Bulk SoA population exchange straight between caller buffers (ideally pinned) and the device
+  // lists, asynchronous on the simulation stream: the AgentVector path above stages every variable
+  // through pageable host vectors.  Variables not listed are reset to their defaults; ids restart at 1.
+  void setPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int n, unsigned int nvars,
+                            const char *const *names, const void *const *host_ptrs);
+  // Returns the agent count; copies the listed variables (device order) into the caller's buffers.
+  unsigned int getPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars,
+                                    const char *const *names, void *const *host_ptrs, unsigned int capacity);
   // device pointers of a state list variable / message variable (current read buffers)
   void *getAgentVariableDevicePtr(const std::string &agent_name, const std::string &state, const std::string &var);
   void *getMessageVariableDevicePtr(const std::string &message_name, const std::string &var);

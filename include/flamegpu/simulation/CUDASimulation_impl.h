@@ -265,6 +265,64 @@ inline void CUDASimulation::getPopulationData(AgentVector &pop, const std::strin
   }
 }
 
+inline void CUDASimulation::setPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int n,
+                                                 unsigned int nvars, const char *const *names, const void *const *host_ptrs) {
+  initialise();
+  detail::CUDAAgent &a = agent_rt(agent_name);
+  detail::DevList &l = state_list(agent_name, state);
+  const unsigned int bound = model_has_births ? quantise(n) : n;
+  if (std::max(bound, 1u) > l.capacity) {
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    l.reserve(std::max(bound, 1u), 0);
+  }
+  l.bound = bound;
+  for (size_t v = 0; v < l.names.size(); ++v) {
+    const size_t b = l.meta[v].bytes();
+    const void *src = nullptr;
+    for (unsigned int k = 0; k < nvars; ++k)
+      if (l.names[v] == names[k]) src = host_ptrs[k];
+    if (!n) continue;
+    if (src) {
+      FGB_CUDA_THROW(cudaMemcpyAsync(l.data[v], src, static_cast<size_t>(n) * b, cudaMemcpyHostToDevice, main_stream));
+    } else if (l.names[v] == ID_VARIABLE_NAME) {
+      detail::k_iota<<<(n + 255) / 256, 256, 0, main_stream>>>(reinterpret_cast<unsigned int *>(l.data[v]), n, 1u);
+      ++own_launches;
+    } else {
+      // defaults: all-zero defaults are a memset, anything else a broadcast of the default value
+      bool zero = true;
+      for (char c : l.meta[v].default_value) zero = zero && c == 0;
+      if (zero) {
+        FGB_CUDA_THROW(cudaMemsetAsync(l.data[v], 0, static_cast<size_t>(n) * b, main_stream));
+      } else {
+        std::vector<char> tmp(static_cast<size_t>(n) * b);
+        for (unsigned int i = 0; i < n; ++i) std::memcpy(tmp.data() + static_cast<size_t>(i) * b, l.meta[v].default_value.data(), b);
+        FGB_CUDA_THROW(cudaMemcpyAsync(l.data[v], tmp.data(), tmp.size(), cudaMemcpyHostToDevice, main_stream));
+        FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+      }
+    }
+  }
+  a.host_next_id = n + 1;
+  const unsigned int words[2] = {n, n + 1};
+  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + l.count_slot, &words[0], 4, cudaMemcpyHostToDevice, main_stream));
+  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + a.next_id_slot, &words[1], 4, cudaMemcpyHostToDevice, main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));  // `words` lives on this stack frame
+}
+
+inline unsigned int CUDASimulation::getPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars,
+                                                         const char *const *names, void *const *host_ptrs, unsigned int capacity) {
+  initialise();
+  detail::DevList &l = state_list(agent_name, state);
+  const unsigned int n = read_slot(l.count_slot);
+  if (n > capacity) throw exception::OutOfBoundsException("getPopulationDataSoA: caller buffers too small");
+  for (unsigned int k = 0; k < nvars; ++k) {
+    const int v = l.index_of(names[k]);
+    if (v < 0) throw exception::InvalidAgentVar(std::string("agent has no variable '") + names[k] + "'");
+    if (n) FGB_CUDA_THROW(cudaMemcpyAsync(host_ptrs[k], l.data[v], static_cast<size_t>(n) * l.meta[v].bytes(), cudaMemcpyDeviceToHost, main_stream));
+  }
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  return n;
+}
+
 inline void *CUDASimulation::getAgentVariableDevicePtr(const std::string &agent_name, const std::string &state, const std::string &var) {
   initialise();
   detail::DevList &l = state_list(agent_name, state);

@@ -339,3 +339,22 @@ def test_bin_order_execution_does_not_change_results():
         s.close()
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+
+
+def test_host_buffer_step_matches_population_path():
+    # the bulk SoA exchange (bench.py e2e path) gives the same step as setPopulationData/getPopulationData
+    n, L = 50000, 36.0
+    pos = _circles_pop(n, L, seed=8)
+    a = _sim("circles", env_max=L, radius=2.0, stable=1)
+    a.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+    a.step(1)
+    b = _sim("circles", env_max=L, radius=2.0, stable=1)
+    out = {k: np.empty(n, np.float32) for k in ("x", "y", "z", "drift")}
+    out["id"] = np.empty(n, np.uint32)
+    for _ in range(2):  # twice: the second call re-uploads over a used simulation
+        b.circles_step_host(pos[0], pos[1], pos[2], np.zeros(n, np.float32), 1, out)
+        assert np.array_equal(out["id"], a.get("Circle", "_id", np.uint32))
+        for v in ("x", "y", "z", "drift"):
+            assert np.array_equal(out[v], a.get("Circle", v, np.float32)), v
+    a.close()
+    b.close()
