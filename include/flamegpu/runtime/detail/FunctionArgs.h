@@ -72,14 +72,41 @@ struct FunctionArgs {
   DevEnv env;
 };
 
-// Slot of a hashed name in a table; -1 if absent.
+// Slot of a hashed name in a table.  Like the reference, an unknown name is only diagnosed when
+// FLAMEGPU_SEATBELTS is on (reference DeviceCurve.cuh:357-371); with seatbelts off (the benchmark
+// configuration of both code bases) the lookup is a multiply-shift and nothing else.
+#ifndef FLAMEGPU_SEATBELTS
+#define FLAMEGPU_SEATBELTS 0
+#endif
 FGB_HD int find_slot(const DevVars &t, uint32_t h) {
   const uint32_t i = (h * t.salt) >> (32 - kSlotBits);
+#if FLAMEGPU_SEATBELTS
   return t.hash[i] == h ? static_cast<int>(i) : -1;
+#else
+  return static_cast<int>(i);
+#endif
 }
 FGB_HD int find_slot(const DevEnv &t, uint32_t h) {
   const uint32_t i = (h * t.salt) >> (32 - kSlotBits);
+#if FLAMEGPU_SEATBELTS
   return t.hash[i] == h ? static_cast<int>(i) : -1;
+#else
+  return static_cast<int>(i);
+#endif
+}
+// message location variables have fixed names: their base pointers are resolved once per thread
+constexpr uint32_t kHashX = name_hash("x");
+constexpr uint32_t kHashY = name_hash("y");
+constexpr uint32_t kHashZ = name_hash("z");
+struct LocPtrs {
+  const char *x, *y, *z;
+};
+FGB_HD LocPtrs make_loc(const FunctionArgs &a) {
+  LocPtrs l;
+  l.x = a.msg_in.ptr[(kHashX * a.msg_in.salt) >> (32 - kSlotBits)];
+  l.y = a.msg_in.ptr[(kHashY * a.msg_in.salt) >> (32 - kSlotBits)];
+  l.z = a.msg_in.ptr[(kHashZ * a.msg_in.salt) >> (32 - kSlotBits)];  // 2D lists: an empty slot, never read
+  return l;
 }
 
 // host: choose a salt that makes the table collision free and fill hash[]; returns false if none found

@@ -46,6 +46,7 @@ class MessageSpatial2D {
      public:
       class Message {
         const detail::FunctionArgs &a;
+        const detail::LocPtrs loc;
         int cx, cy;
         int strip;  // 0..2, 3 == end
         int idx, idx_end, nxt, nxt_end;
@@ -75,7 +76,7 @@ class MessageSpatial2D {
 
        public:
         __device__ __forceinline__ Message(const detail::FunctionArgs &args, int _cx, int _cy, bool begin)
-            : a(args), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+            : a(args), loc(detail::make_loc(args)), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0) {
           if (begin) {
             strip = -1;
             fetch(0, nxt, nxt_end);
@@ -90,7 +91,10 @@ class MessageSpatial2D {
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
+          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
+          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          const int s = detail::find_slot(a.msg_in, h);
           if (s < 0) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }
@@ -133,6 +137,7 @@ class MessageSpatial2D {
      public:
       class Message {
         const detail::FunctionArgs &a;
+        const detail::LocPtrs loc;
         float lx, ly;
         int cx, cy;
         int cell;  // 0..8, 9 == end
@@ -165,7 +170,7 @@ class MessageSpatial2D {
 
        public:
         __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin)
-            : a(args), lx(x), ly(y), cx(_cx), cy(_cy), cell(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+            : a(args), loc(detail::make_loc(args)), lx(x), ly(y), cx(_cx), cy(_cy), cell(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
           if (begin) {
             cell = -1;
             fetch(0, nxt, nxt_end);
@@ -180,7 +185,10 @@ class MessageSpatial2D {
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
+          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
+          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          const int s = detail::find_slot(a.msg_in, h);
           if (s < 0) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }

@@ -49,6 +49,7 @@ class MessageSpatial3D {
      public:
       class Message {
         const detail::FunctionArgs &a;
+        const detail::LocPtrs loc;
         int cx, cy, cz;
         int strip;          // 0..8 current strip, 9 == end
         int idx, idx_end;   // current message, one past the last message of the strip
@@ -81,7 +82,7 @@ class MessageSpatial3D {
 
        public:
         __device__ __forceinline__ Message(const detail::FunctionArgs &args, int _cx, int _cy, int _cz, bool begin)
-            : a(args), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+            : a(args), loc(detail::make_loc(args)), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
           if (begin) {
             strip = -1;
             fetch(0, nxt, nxt_end);
@@ -98,7 +99,11 @@ class MessageSpatial3D {
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
+          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
+          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          if (h == detail::kHashZ) return __ldg(reinterpret_cast<const T *>(loc.z) + idx);
+          const int s = detail::find_slot(a.msg_in, h);
           if (s < 0) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }
@@ -143,6 +148,7 @@ class MessageSpatial3D {
      public:
       class Message {
         const detail::FunctionArgs &a;
+        const detail::LocPtrs loc;
         float lx, ly, lz;
         int cx, cy, cz;
         int cell;  // 0..26, 27 == end
@@ -178,7 +184,7 @@ class MessageSpatial3D {
        public:
         __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, float z, int _cx, int _cy,
                                            int _cz, bool begin)
-            : a(args), lx(x), ly(y), lz(z), cx(_cx), cy(_cy), cz(_cz), cell(27), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+            : a(args), loc(detail::make_loc(args)), lx(x), ly(y), lz(z), cx(_cx), cy(_cy), cz(_cz), cell(27), idx(0), idx_end(0), nxt(0), nxt_end(0) {
           if (begin) {
             cell = -1;
             fetch(0, nxt, nxt_end);
@@ -193,7 +199,11 @@ class MessageSpatial3D {
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
+          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
+          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
+          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          if (h == detail::kHashZ) return __ldg(reinterpret_cast<const T *>(loc.z) + idx);
+          const int s = detail::find_slot(a.msg_in, h);
           if (s < 0) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }
