@@ -201,17 +201,43 @@ def main():
     n = args.agents_per_gpu
     L = env_extent(n)
     bins = int(np.ceil(L / RADIUS)) ** 3
-    x, y, z = population(n, L, seed=rank)
-    s = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
-                        true3d_sort=args.true3d_sort, bin_order=args.bin_order)
-    s.set_population("Circle", {"x": x, "y": y, "z": z})
-    stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=f"cuda:{local}")
+    if world == 1:
+        x, y, z = population(n, L, seed=rank)
+        s = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order)
+        s.set_population("Circle", {"x": x, "y": y, "z": z})
+        stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
+        slab_sim = None
 
-    def one_step():
-        with torch.cuda.stream(stream):
-            flush.add_(1)  # evicts the step's working set from the 126 MB L2; outside the timed events
-        s.step(1)
+        def one_step():
+            with torch.cuda.stream(stream):
+                flush.add_(1)  # evicts the step's working set from the 126 MB L2; outside the timed events
+            s.step(1)
+    else:
+        # weak scaling: the global box is [0,L)^2 x [0, L*world): `world` slabs of n agents stacked along z,
+        # halo messages and migrating agents exchanged over NCCL every step (flamegpu2_b200/slab.py)
+        from flamegpu2_b200 import slab
+
+        planes_per_rank = int(np.ceil(L / RADIUS))
+        planes = planes_per_rank * world
+        Lz = float(planes * RADIUS)
+        cap = int(max(65536, 6 * n // planes_per_rank))
+        slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=cap,
+                                       migrate_capacity=cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
+                                       stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order)
+        s = slab_sim.sim
+        rng = np.random.default_rng(rank)
+        z_lo, z_hi = slab_sim.z0 * RADIUS, slab_sim.z1 * RADIUS
+        x = rng.uniform(0.0, L, n).astype(np.float32)
+        y = rng.uniform(0.0, L, n).astype(np.float32)
+        z = rng.uniform(z_lo, np.nextafter(np.float32(z_hi), np.float32(0)), n).astype(np.float32)
+        ids = (np.arange(n, dtype=np.uint32) + np.uint32(rank * n + 1))
+        s.set_population("Circle", {"x": x, "y": y, "z": z, "_id": ids})
+        stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
+
+        def one_step():
+            slab_sim.step()
 
     for _ in range(args.warmup):
         one_step()
@@ -223,17 +249,23 @@ def main():
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record(stream)
     for _ in range(args.steps):
         one_step()
+    ev1.record(stream)
     s.sync()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clk = clocks.stop()
     if dist is not None:
         dist.barrier()
-    st = s.step_times()
-    dev_total = float(st.sum())
+    if world == 1:
+        dev_total = float(s.step_times().sum())  # per-step events: the L2 flush between steps is excluded
+    else:
+        dev_total = ev0.elapsed_time(ev1) * 1e-3  # device time of the whole K-step region on the simulation stream
+        slab_sim.check_overflow()
     launches = s.launches - launches0
     if dist is not None:
         t = torch.tensor([dev_total, wall], dtype=torch.float64, device=f"cuda:{local}")
@@ -248,15 +280,20 @@ def main():
             "workload": f"Circles-3D, {n} agents per GPU, [0,{L:g})^3, radius {RADIUS:g} ({bins} bins, ~8 agents/bin), "
                         f"whole CUDASimulation::step() (output_message, auto agent sort, PBM buildIndex, move)",
             "agents_per_gpu": n, "bins": bins, "graphs": s.graphs, "bin_order_execution": bool(args.bin_order),
-            "l2": "flushed between steps (256 MiB write outside the timed events)",
-            "timing": "sum of per-step CUDA-event times on the simulation stream, max over ranks",
-            "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
-            "multi_gpu": "independent sub-domains per rank (no data-path collective)" if world > 1 else "single GPU",
+            "l2": "flushed between steps (256 MiB write outside the timed events)" if world == 1 else
+                  "not flushed (exchange-synchronised steps; per-GPU working set ~80 MB)",
+            "timing": "sum of per-step CUDA-event times on the simulation stream" if world == 1 else
+                      "CUDA events around the K-step region on the simulation stream (NCCL waits included), max over ranks",
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "multi_gpu": (f"z-slab decomposition over {world} GPUs, box [0,{L:g})^2 x [0,{L * world:g}); halo messages + "
+                          "migrating agents over NCCL send/recv every step") if world > 1 else "single GPU",
         },
         "gpu_launches": int(launches),
         "clocks": clk,
     }
-    if rank == 0:
+    if rank == 0 and world > 1:
+        print(json.dumps(line), flush=True)
+    if rank == 0 and world == 1:
         peak, peak_src = measured_peak()
         # -- per-phase device times from a profiled (eager, event-bracketed) pass of the same workload
         p = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, profile=1, stable=args.stable,

@@ -59,6 +59,7 @@ FLAMEGPU_AGENT_FUNCTION(circles_move, flamegpu::MessageSpatial3D, flamegpu::Mess
 
 struct CirclesParams {
   float env_max = 25.0f;   // reference example: floor(cbrt(16384)) = 25
+  float env_max_z = 0.0f;  // > 0: non-cubic box [0,env_max)^2 x [0,env_max_z) (multi-GPU weak scaling stacks slabs in z)
   float radius = 2.0f;
   float repulse = 0.05f;
   unsigned int sort_period = 1;
@@ -70,7 +71,7 @@ inline void define_circles(flamegpu::ModelDescription &model, const CirclesParam
     message.newVariable<flamegpu::id_t>("id");
     message.setRadius(p.radius);
     message.setMin(0, 0, 0);
-    message.setMax(p.env_max, p.env_max, p.env_max);
+    message.setMax(p.env_max, p.env_max, p.env_max_z > 0.0f ? p.env_max_z : p.env_max);
   }
   {
     flamegpu::AgentDescription agent = model.newAgent("Circle");

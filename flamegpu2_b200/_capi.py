@@ -47,6 +47,11 @@ SIGNATURES = {
     "fgb_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "fgb_spatial_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                      C.POINTER(C.c_void_p)]),
+    "fgb_spatial_create_window": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                            C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fgb_spatial_get_window": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fgb_plane_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_spatial_destroy": (C.c_int, [C.c_void_p]),
     "fgb_spatial_get_metadata": (C.c_int, [C.c_void_p, C.POINTER(fgb_spatial_metadata), C.POINTER(C.c_uint)]),
     "fgb_spatial_metadata_device_ptr": (C.c_void_p, [C.c_void_p]),
@@ -60,6 +65,8 @@ SIGNATURES = {
     "fgb_exclusive_scan_u32": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),
     "fgb_compact": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_uint, C.c_uint,
                               C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgb_compact_limited": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_uint, C.c_uint,
+                                      C.c_void_p, C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_scatter_all": (C.c_int, [C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p, C.c_uint,
                                   C.c_void_p, C.c_void_p]),
     "fgb_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]),

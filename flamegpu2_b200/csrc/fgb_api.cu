@@ -45,6 +45,11 @@ bool approx_exactly_divisible(float x, float y) {
 
 inline int launch_ok() { return static_cast<int>(cudaPeekAtLastError()); }
 
+inline Geo make_geo(const fgb_spatial *sp) {
+  return Geo{sp->md.min[0], sp->md.min[1], sp->md.min[2], sp->md.radius, static_cast<int>(sp->md.grid_dim[0]),
+             static_cast<int>(sp->md.grid_dim[1]), static_cast<int>(sp->md.grid_dim[2]), sp->win_begin, sp->win_count};
+}
+
 // worklist entries needed for n items: bins with more than kFixSmall items
 inline size_t worklist_bytes(unsigned int n) { return (static_cast<size_t>(n) / (kFixSmall + 1) + 1) * sizeof(uint32_t); }
 
@@ -83,8 +88,7 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
   src.z = z;
   src.keys = nullptr;
   src.mask = 0;
-  src.g = Geo{sp->md.min[0], sp->md.min[1], sp->md.min[2], sp->md.radius, static_cast<int>(sp->md.grid_dim[0]),
-              static_cast<int>(sp->md.grid_dim[1]), static_cast<int>(sp->md.grid_dim[2])};
+  src.g = make_geo(sp);
   const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z)) && vars_in_aligned(vars, nvars);
   const unsigned int grid = bin_grid(n);
   const unsigned int B = sp->bin_count;
@@ -130,8 +134,7 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   src.x = x;
   src.y = y;
   src.z = z;
-  src.g = Geo{sp->md.min[0], sp->md.min[1], sp->md.min[2], sp->md.radius, static_cast<int>(sp->md.grid_dim[0]),
-              static_cast<int>(sp->md.grid_dim[1]), static_cast<int>(sp->md.grid_dim[2])};
+  src.g = make_geo(sp);
   const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
   const unsigned int grid = bin_grid(n);
   const unsigned int B = sp->bin_count;
@@ -211,6 +214,11 @@ unsigned long long fgb_launch_count(const fgb_ctx *ctx) { return ctx ? ctx->laun
 
 fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
                               fgb_spatial **out) {
+  return fgb_spatial_create_window(ctx, dims, env_min, env_max, radius, 0, -1, out);
+}
+
+fgb_status fgb_spatial_create_window(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
+                                     int plane_begin, int plane_count, fgb_spatial **out) {
   if (!ctx || !out || !env_min || !env_max || (dims != 2 && dims != 3) || !(radius > 0.f)) return FGB_ERR_INVALID_ARG;
   fgb_spatial *sp = new (std::nothrow) fgb_spatial();
   if (!sp) return FGB_ERR_ALLOC;
@@ -230,6 +238,22 @@ fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, cons
     md.grid_dim[a] = static_cast<unsigned int>(std::ceil(md.environment_width[a] / md.radius));
     bins *= md.grid_dim[a];
     md.wrap_compatible = md.wrap_compatible && approx_exactly_divisible(md.environment_width[a], md.radius);
+  }
+  {
+    // slab window on the slowest axis: the PBM covers planes [plane_begin, plane_begin + plane_count) only
+    const int slow = dims - 1;
+    const int gslow = static_cast<int>(md.grid_dim[slow]);
+    if (plane_count < 0) {
+      plane_begin = 0;
+      plane_count = gslow;
+    }
+    if (plane_begin < 0 || plane_count < 1 || plane_begin + plane_count > gslow) {
+      delete sp;
+      return FGB_ERR_INVALID_ARG;
+    }
+    sp->win_begin = plane_begin;
+    sp->win_count = plane_count;
+    bins = bins / static_cast<unsigned long long>(gslow) * static_cast<unsigned long long>(plane_count);
   }
   if (bins == 0 || bins >= 0x7FFFFFFFull) {
     delete sp;
@@ -277,6 +301,24 @@ fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata 
 }
 
 const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp) { return sp ? sp->d_md : nullptr; }
+
+fgb_status fgb_spatial_get_window(const fgb_spatial *sp, int *plane_begin, int *plane_count) {
+  if (!sp) return FGB_ERR_INVALID_ARG;
+  if (plane_begin) *plane_begin = sp->win_begin;
+  if (plane_count) *plane_count = sp->win_count;
+  return FGB_OK;
+}
+
+fgb_status fgb_plane_flags(fgb_ctx *ctx, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                           float radius, int grid_dim, int lo, int hi, unsigned int *flag_lo, unsigned int *flag_mid,
+                           unsigned int *flag_hi, void *stream) {
+  if (!ctx || (n && !pos)) return FGB_ERR_INVALID_ARG;
+  if (n == 0) return FGB_OK;
+  k_plane_flags<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(pos, n, d_n, env_min, radius, grid_dim, lo, hi,
+                                                                              flag_lo, flag_mid, flag_hi);
+  ctx->launches += 1;
+  return launch_ok();
+}
 
 fgb_status fgb_spatial_read_pbm(const fgb_spatial *sp, unsigned int *host_out, void *stream) {
   if (!sp || !host_out) return FGB_ERR_INVALID_ARG;
@@ -373,6 +415,14 @@ fgb_status fgb_compact(fgb_ctx *ctx, unsigned int stream_id, const unsigned int 
                        const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset,
                        const unsigned int *d_out_offset, const fgb_var *vars, unsigned int nvars,
                        unsigned int *d_out_count, unsigned int *d_out_total, void *stream) {
+  return fgb_compact_limited(ctx, stream_id, flags, invert, n, d_n, keep_front, out_offset, d_out_offset, 0xFFFFFFFFu, vars, nvars,
+                             d_out_count, d_out_total, stream);
+}
+
+fgb_status fgb_compact_limited(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *flags, int invert, unsigned int n,
+                               const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset,
+                               const unsigned int *d_out_offset, unsigned int out_limit, const fgb_var *vars, unsigned int nvars,
+                               unsigned int *d_out_count, unsigned int *d_out_total, void *stream) {
   if (!ctx || stream_id >= FGB_MAX_STREAMS || (n > keep_front && !flags)) return FGB_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VarTable vt;
@@ -396,10 +446,10 @@ fgb_status fgb_compact(fgb_ctx *ctx, unsigned int stream_id, const unsigned int 
   uint32_t *done = static_cast<uint32_t *>(s.ctrl.p) + 1;
   const bool vec = aligned16(flags) && vars_in_aligned(vars, nvars);
   if (vec)
-    k_compact<true><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, vt, state,
+    k_compact<true><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state,
                                                    done, d_out_count, d_out_total);
   else
-    k_compact<false><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, vt,
+    k_compact<false><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt,
                                                     state, done, d_out_count, d_out_total);
   ctx->launches += 1;
   return launch_ok();

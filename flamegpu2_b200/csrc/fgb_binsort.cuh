@@ -16,7 +16,8 @@ namespace fgb {
 
 struct Geo {
   float min0, min1, min2, radius;
-  int g0, g1, g2;
+  int g0, g1, g2;     // GLOBAL grid dimensions (the clamp of the reference's getGridPosition3D)
+  int z_off, z_cnt;   // slab window: planes [z_off, z_off + z_cnt) of the slowest axis are stored locally
 };
 
 #ifdef __CUDACC__
@@ -31,8 +32,12 @@ __device__ __forceinline__ uint32_t bin_key(const Geo &g, float x, float y, floa
   if (DIMS == 3) {
     int cz = static_cast<int>(floorf(__fdiv_rn(z - g.min2, g.radius)));
     cz = cz < 0 ? 0 : (cz >= g.g2 ? g.g2 - 1 : cz);
+    cz -= g.z_off;  // bin arithmetic stays the global one; only the plane index is rebased
+    cz = cz < 0 ? 0 : (cz >= g.z_cnt ? g.z_cnt - 1 : cz);
     return (static_cast<uint32_t>(cz) * g.g1 + cy) * g.g0 + cx;
   }
+  cy -= g.z_off;
+  cy = cy < 0 ? 0 : (cy >= g.z_cnt ? g.z_cnt - 1 : cy);
   return static_cast<uint32_t>(cy) * g.g0 + cx;
 }
 
@@ -248,6 +253,23 @@ __global__ void __launch_bounds__(1024) k_fix_big(const uint32_t *__restrict__ p
       block_bitonic(perm + s, n);
     }
   }
+}
+
+// ---- slab decomposition: classify items by the plane (slowest grid axis) of their position ----
+// plane = clamp(floorf((p - min)/radius), 0, dim-1) exactly as the bin arithmetic.
+// flag_lo[i] = plane < lo, flag_hi[i] = plane >= hi, flag_mid[i] = neither (any output may be NULL).
+__global__ void __launch_bounds__(256) k_plane_flags(const float *__restrict__ p, uint32_t n_max, const unsigned int *d_n,
+                                                     float mn, float radius, int dim, int lo, int hi, uint32_t *flag_lo,
+                                                     uint32_t *flag_mid, uint32_t *flag_hi) {
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  int c = static_cast<int>(floorf(__fdiv_rn(__ldg(p + i) - mn, radius)));
+  c = c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+  const bool l = c < lo, h = c >= hi;
+  if (flag_lo) flag_lo[i] = l ? 1u : 0u;
+  if (flag_hi) flag_hi[i] = h ? 1u : 0u;
+  if (flag_mid) flag_mid[i] = (!l && !h) ? 1u : 0u;
 }
 
 // ---- gather: out[j] = in[perm[j]] (scatter_position_generic, CUDAScatter.cu:89-104) ------

@@ -25,7 +25,7 @@ inline unsigned int compact_num_tiles(unsigned int n) { return (n + kCmpTile - 1
 template <bool VEC>
 __global__ void __launch_bounds__(kCmpThreads)
 k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const unsigned int *d_n, uint32_t keep_front,
-          uint32_t out_offset, const unsigned int *d_out_offset, const __grid_constant__ VarTable vt,
+          uint32_t out_offset, const unsigned int *d_out_offset, uint32_t out_limit, const __grid_constant__ VarTable vt,
           unsigned long long *state, uint32_t *done, uint32_t *d_out_count, uint32_t *d_out_total) {
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t s_excl;
@@ -81,8 +81,12 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
   }
 
   // ---- move the kept items of every variable; a thread's kept items are contiguous in the output
-  if (keep) {
-    const size_t pos0 = static_cast<size_t>(out_offset) + tile_excl + texcl;
+  // out_limit: only the first out_limit kept items are written (the counts still report all of them, so a
+  // caller with a fixed-capacity destination can detect the overflow instead of corrupting memory)
+  const uint32_t rank0 = tile_excl + texcl;
+  if (keep && rank0 < out_limit) {
+    const uint32_t room = out_limit - rank0;
+    const size_t pos0 = static_cast<size_t>(out_offset) + rank0;
     for (uint32_t v = 0; v < vt.n; ++v) {
       const uint32_t len = vt.len[v];
       if (VEC && len == 4 && i0 + kCmpItems <= n) {
@@ -90,20 +94,26 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
         const uint4 b = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]) + pos0;
-        if (keep == 0xFFu && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+        if (keep == 0xFFu && room >= 8u && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
           reinterpret_cast<uint4 *>(o)[0] = a;
           reinterpret_cast<uint4 *>(o)[1] = b;
         } else {
           uint32_t p = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (keep & (1u << j)) o[p++] = w[j];
+            if (keep & (1u << j)) {
+              if (p < room) o[p] = w[j];
+              ++p;
+            }
         }
       } else {
         uint32_t p = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (keep & (1u << j)) copy_item(vt, v, i0 + j, pos0 + p++);
+          if (keep & (1u << j)) {
+            if (p < room) copy_item(vt, v, i0 + j, pos0 + p);
+            ++p;
+          }
       }
     }
   }

@@ -78,6 +78,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
       p.radius = getf(kv, "radius", p.radius);
       p.repulse = getf(kv, "repulse", p.repulse);
       p.sort_period = getu(kv, "sort_period", p.sort_period);
+      p.env_max_z = getf(kv, "env_max_z", p.env_max_z);
       fgb_examples::define_circles(*s->model, p);
     } else if (name == "boids3d" || name == "boids2d") {
       fgb_examples::BoidsParams p;
@@ -107,6 +108,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     }
     s->sim = std::make_unique<flamegpu::CUDASimulation>(*s->model);
     s->sim->CUDAConfig().device_id = device;
+    if (kv.count("win_count")) s->sim->setMessageWindow("location", static_cast<int>(getu(kv, "win_begin", 0)), static_cast<int>(getu(kv, "win_count", 0)));
     s->sim->CUDAConfig().useCUDAGraphs = getu(kv, "graphs", 1) != 0;
     s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
     s->sim->CUDAConfig().trueSpatialSortKey = getu(kv, "true3d_sort", 0) != 0;
@@ -181,6 +183,38 @@ int fgbm_step_times(void *h, double *out, unsigned int cap, unsigned int *n) {
     *n = static_cast<unsigned int>(t.size());
     for (unsigned int i = 0; i < cap && i < t.size(); ++i) out[i] = t[i];
   });
+}
+
+// ---- multi-GPU slab driver hooks (flamegpu2_b200/slab.py) ------------------------------------------
+int fgbm_run_layers(void *h, unsigned int first, unsigned int last) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->runLayers(first, last); });
+}
+int fgbm_end_step(void *h) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->endStep(); });
+}
+int fgbm_refresh_bounds(void *h) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->refreshBounds(); });
+}
+// JSON [["name", bytes_per_item], ...] of a message list (is_message) or of an agent's state lists
+int fgbm_list_layout(void *h, int is_message, const char *name, char *buf, size_t cap) {
+  return guarded([&] {
+    auto lay = static_cast<Sim *>(h)->sim->listLayout(is_message != 0, name);
+    std::string js = "[";
+    for (size_t i = 0; i < lay.size(); ++i) js += (i ? ", [\"" : "[\"") + lay[i].first + "\", " + std::to_string(lay[i].second) + "]";
+    js += "]";
+    if (js.size() + 1 > cap) throw std::runtime_error("layout buffer too small");
+    std::memcpy(buf, js.c_str(), js.size() + 1);
+  });
+}
+int fgbm_slab_pack(void *h, int is_message, const char *name, const char *geometry_message, int lo, int hi, void *const *dst_lo,
+                   void *const *dst_hi, unsigned int capacity, int remove, unsigned int *d_counts) {
+  return guarded([&] {
+    static_cast<Sim *>(h)->sim->slabPack(is_message != 0, name, flamegpu::DEFAULT_STATE, geometry_message, lo, hi, dst_lo, dst_hi,
+                                         capacity, remove != 0, d_counts);
+  });
+}
+int fgbm_list_append(void *h, int is_message, const char *name, unsigned int n_max, const unsigned int *d_n, const void *const *src) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->listAppend(is_message != 0, name, flamegpu::DEFAULT_STATE, n_max, d_n, src); });
 }
 
 // Phase profile (model created with profile=1): JSON {"phase": [total_ms, calls], ...} into buf.

@@ -35,7 +35,9 @@ struct SpatialMeta {
   float max[3];
   float radius;
   float env_width[3];
-  int grid_dim[3];
+  int grid_dim[3];      // global grid (clamp of getGridPosition)
+  int win_begin;        // slab window on the slowest axis: first plane stored locally
+  int win_count;        // ... and how many (== grid_dim[slowest] on a single GPU)
   int wrap_compatible;
   const unsigned int *pbm;
 };

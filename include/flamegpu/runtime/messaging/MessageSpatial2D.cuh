@@ -55,7 +55,7 @@ class MessageSpatial2D {
           e = 0;
           if (s < 3) {
             const int y = cy + s - 1;
-            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1];
+            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.win_count;
             if (y >= 0 && y < gy) {
               const int row = y * gx;
               const int x0 = cx > 0 ? cx - 1 : 0;
@@ -123,7 +123,7 @@ class MessageSpatial2D {
       };
       __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y) : a(args) {
         cx = detail::grid_cell(args.in_meta, 0, x);
-        cy = detail::grid_cell(args.in_meta, 1, y);
+        cy = detail::grid_cell(args.in_meta, 1, y) - args.in_meta.win_begin;  // row index inside the slab window
       }
       __device__ __forceinline__ iterator begin() const { return iterator(a, cx, cy, true); }
       __device__ __forceinline__ iterator end() const { return iterator(a, cx, cy, false); }

@@ -61,7 +61,7 @@ class MessageSpatial3D {
           e = 0;
           if (s < 9) {
             const int y = cy + (s / 3) - 1, z = cz + (s % 3) - 1;
-            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1], gz = a.in_meta.grid_dim[2];
+            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1], gz = a.in_meta.win_count;
             if (y >= 0 && z >= 0 && y < gy && z < gz) {
               const int row = (z * gy + y) * gx;
               const int x0 = cx > 0 ? cx - 1 : 0;                 // getHash3D clamps x (reference :660-672)
@@ -133,7 +133,7 @@ class MessageSpatial3D {
       __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, float z) : a(args) {
         cx = detail::grid_cell(args.in_meta, 0, x);
         cy = detail::grid_cell(args.in_meta, 1, y);
-        cz = detail::grid_cell(args.in_meta, 2, z);
+        cz = detail::grid_cell(args.in_meta, 2, z) - args.in_meta.win_begin;  // plane index inside the slab window
       }
       __device__ __forceinline__ iterator begin() const { return iterator(a, cx, cy, cz, true); }
       __device__ __forceinline__ iterator end() const { return iterator(a, cx, cy, cz, false); }

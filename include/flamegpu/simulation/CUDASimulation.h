@@ -175,6 +175,7 @@ struct CUDAMessage {
   fgb_spatial_metadata md{};
   bool pbm_dirty = true;
   bool truncate = true;
+  int win_begin = 0, win_count = -1;  // slab window (planes of the slowest axis held by this process)
 };
 
 struct CUDAAgent {
@@ -304,6 +305,31 @@ class CUDASimulation {
   }
   unsigned int getAgentCount(const std::string &agent_name, const std::string &state = DEFAULT_STATE);
 
+  // ---- b200 multi-GPU extension: z-slab decomposition (no reference counterpart) -------
+  // Must be called before the first step / setPopulationData: this process stores only planes
+  // [plane_begin, plane_begin+plane_count) of the message list's slowest grid axis (own planes + ghosts).
+  void setMessageWindow(const std::string &message_name, int plane_begin, int plane_count) {
+    if (initialised) throw exception::InvalidArgument("setMessageWindow must be called before the simulation is initialised");
+    windows[message_name] = std::make_pair(plane_begin, plane_count);
+  }
+  // run layers [first, last) of the model eagerly (no end-of-step bookkeeping); endStep() finishes the step
+  void runLayers(unsigned int first, unsigned int last);
+  void endStep();
+  // Select the items of a list whose position along the slowest axis lies in planes < lo / >= hi
+  // (fgb_plane_flags + fgb_compact), packed into caller-provided device buffers (one per variable, list
+  // order); returns the two counts.  remove != 0 additionally drops them from the list (agent migration).
+  // Nothing returns to the host: the two counts go to the device words d_counts[0] (lo) and d_counts[1] (hi).
+  void slabPack(bool is_message, const std::string &name, const std::string &state, const std::string &geometry_message,
+                int lo, int hi, void *const *dst_lo, void *const *dst_hi, unsigned int capacity, bool remove,
+                unsigned int *d_counts);
+  // append up to n_max items (actual count in the device word d_n) from device buffers (one per variable,
+  // list order) to a list
+  void listAppend(bool is_message, const std::string &name, const std::string &state, unsigned int n_max,
+                  const unsigned int *d_n, const void *const *src);
+  // re-read every list count from the device (one sync) and tighten the host-side launch bounds
+  void refreshBounds() { initialise(); refresh_bounds(); }
+  std::vector<std::pair<std::string, size_t>> listLayout(bool is_message, const std::string &name);
+
   // ---- b200 extensions used by the parity harness / bench (no reference counterpart) -------------
   // Bulk SoA population exchange straight between caller buffers (ideally pinned) and the device
   // lists, asynchronous on the simulation stream: the AgentVector path above stages every variable
@@ -362,6 +388,8 @@ class CUDASimulation {
   void upload_environment();
   void plan_step();                         // reserve capacities for the coming step (may allocate)
   void record_step(cudaStream_t main);      // enqueue one whole step
+  void record_layers(cudaStream_t main, size_t first, size_t last);
+  void record_end_of_step(cudaStream_t main);
   void run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int stream_id);
   void refresh_bounds();                    // births only: read the counts back once per step
   int sort_geometry(const detail::FunctionRT &f, float mn[3], float width[3], unsigned int gd[3]) const;
@@ -385,6 +413,7 @@ class CUDASimulation {
   cudaEvent_t fork_event = nullptr;
   unsigned int *d_ctrl = nullptr;
   unsigned int next_slot = 1;
+  unsigned int slab_tmp_slot = 0;
   unsigned int *d_zero_slots = nullptr;
   unsigned int n_zero_slots = 0;
   char *d_env = nullptr;
@@ -394,6 +423,8 @@ class CUDASimulation {
   bool env_dirty = true;
   std::map<std::string, detail::CUDAAgent> agents;
   std::map<std::string, detail::CUDAMessage> messages;
+  std::map<std::string, std::pair<int, int>> windows;
+  detail::DevFlags slab_flags[3];
   std::vector<std::vector<detail::FunctionRT>> layers;  // [layer][function]
   bool model_has_births = false;
   bool model_has_host_layers = false;

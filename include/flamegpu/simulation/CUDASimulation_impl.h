@@ -29,6 +29,8 @@ inline void CUDASimulation::initialise() {
   FGB_CUDA_THROW(cudaMalloc(&d_ctrl, kCtrlWords * 4));
   FGB_CUDA_THROW(cudaMemset(d_ctrl, 0, kCtrlWords * 4));
   next_slot = 1;
+  slab_tmp_slot = alloc_slot();
+  alloc_slot();  // two consecutive words for slabPack's counts
 
   // agents whose functions touch spatial messages carry the auto-sort key variable
   // (reference src/flamegpu/model/AgentFunctionDescription.cpp:534-535)
@@ -52,7 +54,14 @@ inline void CUDASimulation::initialise() {
     if (!mp.second->persistent) zero_slots.push_back(m.list.count_slot);
     if (mp.second->dims() > 0) {
       if (!(mp.second->radius > 0.f)) throw exception::InvalidMessageType("spatial message '" + mp.first + "' has no radius");
-      FGB_ABI_THROW(fgb_spatial_create(ctx, mp.second->dims(), mp.second->min, mp.second->max, mp.second->radius, &m.spatial));
+      auto w = windows.find(mp.first);
+      if (w != windows.end()) {
+        m.win_begin = w->second.first;
+        m.win_count = w->second.second;
+      }
+      FGB_ABI_THROW(fgb_spatial_create_window(ctx, mp.second->dims(), mp.second->min, mp.second->max, mp.second->radius, m.win_begin,
+                                              m.win_count, &m.spatial));
+      FGB_ABI_THROW(fgb_spatial_get_window(m.spatial, &m.win_begin, &m.win_count));
       unsigned int bins = 0;
       FGB_ABI_THROW(fgb_spatial_get_metadata(m.spatial, &m.md, &bins));
     }
@@ -114,7 +123,8 @@ inline void CUDASimulation::initialise() {
           f.sortable = true;
           f.sort_dims = d;
           const MessageData &md = *f.msg_in->desc;
-          FGB_ABI_THROW(fgb_spatial_create(ctx, d, md.min, md.max, md.radius, &f.exec_binner));
+          FGB_ABI_THROW(fgb_spatial_create_window(ctx, d, md.min, md.max, md.radius, f.msg_in->win_begin, f.msg_in->win_count,
+                                                  &f.exec_binner));
         }
       }
     }
@@ -180,6 +190,7 @@ inline void CUDASimulation::destroy() {
     m.second.list.release();
     if (m.second.spatial) fgb_spatial_destroy(m.second.spatial);
   }
+  for (auto &f : slab_flags) f.release();
   if (d_env) cudaFree(d_env);
   if (d_zero_slots) cudaFree(d_zero_slots);
   if (d_ctrl) cudaFree(d_ctrl);
@@ -556,6 +567,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
         a.in_meta.env_width[k] = M.md.environment_width[k];
         a.in_meta.grid_dim[k] = static_cast<int>(M.md.grid_dim[k]);
       }
+      a.in_meta.win_begin = M.win_begin;
+      a.in_meta.win_count = M.win_count;
       a.in_meta.radius = M.md.radius;
       a.in_meta.wrap_compatible = M.md.wrap_compatible ? 1 : 0;
       a.in_meta.pbm = M.md.PBM;
@@ -686,9 +699,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   prof_end(st);
 }
 
-inline void CUDASimulation::record_step(cudaStream_t main) {
-  for (auto &m : messages) m.second.truncate = true;  // reference CUDASimulation.cu:599-601
-  for (size_t li = 0; li < layers.size(); ++li) {
+inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_t last) {
+  for (size_t li = first; li < last && li < layers.size(); ++li) {
     auto &layer = layers[li];
     const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty();
     if (fork) FGB_CUDA_THROW(cudaEventRecord(fork_event, main));
@@ -708,6 +720,9 @@ inline void CUDASimulation::record_step(cudaStream_t main) {
       if (env_dirty) upload_environment();
     }
   }
+}
+
+inline void CUDASimulation::record_end_of_step(cudaStream_t main) {
   // end of step on the device: ++step counter, non-persistent lists emptied (reference :619-625)
   detail::k_end_of_step<<<1, 32, 0, main>>>(d_ctrl, kStepSlot, d_zero_slots, n_zero_slots);
   ++own_launches;
@@ -716,6 +731,100 @@ inline void CUDASimulation::record_step(cudaStream_t main) {
       m.second.truncate = true;
       m.second.pbm_dirty = true;
     }
+}
+
+inline void CUDASimulation::record_step(cudaStream_t main) {
+  for (auto &m : messages) m.second.truncate = true;  // reference CUDASimulation.cu:599-601
+  record_layers(main, 0, layers.size());
+  record_end_of_step(main);
+}
+
+// ---- phase-wise execution for the multi-GPU slab driver (eager; exchanges happen between phases) ----
+inline void CUDASimulation::runLayers(unsigned int first, unsigned int last) {
+  initialise();
+  if (env_dirty) upload_environment();
+  if (first == 0) {
+    plan_step();
+    for (auto &m : messages) m.second.truncate = true;
+  }
+  record_layers(main_stream, first, last);
+}
+inline void CUDASimulation::endStep() {
+  record_end_of_step(main_stream);
+  ++step_count;
+  if (model_has_births) refresh_bounds();
+}
+
+inline std::vector<std::pair<std::string, size_t>> CUDASimulation::listLayout(bool is_message, const std::string &name) {
+  initialise();
+  detail::DevList &l = is_message ? messages.at(name).list : state_list(name, agent_rt(name).desc->initial_state);
+  std::vector<std::pair<std::string, size_t>> out;
+  for (size_t v = 0; v < l.names.size(); ++v) out.emplace_back(l.names[v], l.meta[v].bytes());
+  return out;
+}
+
+inline void CUDASimulation::slabPack(bool is_message, const std::string &name, const std::string &state,
+                                     const std::string &geometry_message, int lo, int hi, void *const *dst_lo, void *const *dst_hi,
+                                     unsigned int capacity, bool remove, unsigned int *d_counts) {
+  initialise();
+  detail::DevList &l = is_message ? messages.at(name).list : state_list(name, state);
+  const detail::CUDAMessage &G = messages.at(geometry_message);
+  const int slow = G.desc->dims() - 1;
+  const char *axis = slow == 2 ? "z" : "y";
+  const int ip = l.index_of(axis);
+  if (ip < 0) throw exception::InvalidAgentVar(std::string("list has no position variable '") + axis + "'");
+  const unsigned int n = l.bound;
+  FGB_CUDA_THROW(cudaMemsetAsync(d_counts, 0, 8, main_stream));
+  if (n == 0) return;
+  unsigned int *d_n = slot_ptr(l.count_slot);
+  for (auto &f : slab_flags) f.reserve(n);
+  FGB_ABI_THROW(fgb_ctx_reserve(ctx, 0, n, 0));
+  FGB_ABI_THROW(fgb_plane_flags(ctx, reinterpret_cast<const float *>(l.data[ip]), n, d_n, G.md.min[slow], G.md.radius,
+                                static_cast<int>(G.md.grid_dim[slow]), lo, hi, slab_flags[0].p, slab_flags[1].p, slab_flags[2].p,
+                                main_stream));
+  for (int side = 0; side < 2; ++side) {
+    void *const *dst = side == 0 ? dst_lo : dst_hi;
+    if (!dst) continue;
+    // the destination buffers hold `capacity` items: writes are clamped, the caller checks the count
+    std::vector<fgb_var> vars(l.names.size());
+    for (size_t v = 0; v < vars.size(); ++v) {
+      vars[v].type_len = l.meta[v].bytes();
+      vars[v].in = l.data[v];
+      vars[v].out = dst[v];
+    }
+    FGB_ABI_THROW(fgb_compact_limited(ctx, 0, slab_flags[side == 0 ? 0 : 2].p, 0, n, d_n, 0, 0, nullptr, capacity, vars.data(),
+                                      static_cast<unsigned int>(vars.size()), d_counts + side, nullptr, main_stream));
+  }
+  if (remove) {
+    std::vector<fgb_var> vars = l.vars(true);
+    FGB_ABI_THROW(fgb_compact(ctx, 0, slab_flags[1].p, 0, n, d_n, 0, 0, nullptr, vars.data(), static_cast<unsigned int>(vars.size()),
+                              nullptr, d_n, main_stream));
+    l.swap_buffers();
+  }
+}
+
+inline void CUDASimulation::listAppend(bool is_message, const std::string &name, const std::string &state, unsigned int n_max,
+                                       const unsigned int *d_n_src, const void *const *src) {
+  initialise();
+  if (n_max == 0) return;
+  detail::DevList &l = is_message ? messages.at(name).list : state_list(name, state);
+  unsigned int *d_n = slot_ptr(l.count_slot);
+  if (l.bound + n_max > l.capacity) {
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    l.reserve(l.bound + n_max, l.capacity);
+  }
+  std::vector<fgb_var> vars(l.names.size());
+  for (size_t v = 0; v < vars.size(); ++v) {
+    vars[v].type_len = l.meta[v].bytes();
+    vars[v].in = src[v];
+    vars[v].out = l.data[v];
+  }
+  // copy-all compaction: keep_front == n_max keeps every item below the device count; offset and the new
+  // size are the list's own device count word
+  FGB_ABI_THROW(fgb_compact(ctx, 0, nullptr, 0, n_max, d_n_src, n_max, 0, d_n, vars.data(), static_cast<unsigned int>(vars.size()),
+                            nullptr, d_n, main_stream));
+  l.bound += n_max;
+  if (is_message) messages.at(name).pbm_dirty = true;
 }
 
 inline void CUDASimulation::refresh_bounds() {

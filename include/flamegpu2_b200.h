@@ -92,6 +92,22 @@ int fgb_version(void);
  * MetaData.  Synchronous. */
 fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
                               fgb_spatial **out);
+/* Multi-GPU slab decomposition (no reference counterpart: a reference simulation never spans GPUs,
+ * SURVEY.md section 8e): same as fgb_spatial_create, but the handler stores only planes
+ * [plane_begin, plane_begin + plane_count) of the slowest grid axis (z in 3D, y in 2D).  Bin arithmetic
+ * is the GLOBAL one (identical to the single-GPU build); only the plane index is rebased, so the slab
+ * PBMs concatenate to the single-GPU PBM.  plane_count < 0 means the whole grid.  The metadata keeps
+ * the GLOBAL grid_dim; the window is queried with fgb_spatial_get_window. */
+fgb_status fgb_spatial_create_window(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
+                                     int plane_begin, int plane_count, fgb_spatial **out);
+fgb_status fgb_spatial_get_window(const fgb_spatial *sp, int *plane_begin, int *plane_count);
+/* Classifies n positions along one axis by grid plane, with the bin arithmetic of the PBM
+ * (plane = clamp(floorf((p - env_min) / radius), 0, grid_dim - 1)):
+ * flag_lo[i] = plane < lo, flag_hi[i] = plane >= hi, flag_mid[i] = neither.  Outputs may be NULL.
+ * Halo selection and agent migration of the slab decomposition are fgb_compact over these flags. */
+fgb_status fgb_plane_flags(fgb_ctx *ctx, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                           float radius, int grid_dim, int lo, int hi, unsigned int *flag_lo, unsigned int *flag_mid,
+                           unsigned int *flag_hi, void *stream);
 /* CUDAModelHandler::freeMetaDataDevicePtr (MessageSpatial3D.cu:92-111).  Synchronous. */
 fgb_status fgb_spatial_destroy(fgb_spatial *sp);
 /* Host copy of the metadata (PBM is the device pointer) and the bin count. */
@@ -154,6 +170,14 @@ fgb_status fgb_compact(fgb_ctx *ctx, unsigned int stream_id, const unsigned int 
                        const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset, const unsigned int *d_out_offset,
                        const fgb_var *vars, unsigned int nvars, unsigned int *d_out_count, unsigned int *d_out_total,
                        void *stream);
+
+/* fgb_compact with a bounded destination: only the first out_limit kept items are written, the counts
+ * still report every kept item (overflow is detectable, memory is never overrun).  Used for the
+ * fixed-capacity halo / migration staging buffers of the multi-GPU slab decomposition. */
+fgb_status fgb_compact_limited(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *flags, int invert, unsigned int n,
+                               const unsigned int *d_n, unsigned int keep_front, unsigned int out_offset,
+                               const unsigned int *d_out_offset, unsigned int out_limit, const fgb_var *vars, unsigned int nvars,
+                               unsigned int *d_out_count, unsigned int *d_out_total, void *stream);
 
 /* CUDAScatter::scatterAll / scatter_all_generic (CUDAScatter.cu:105-117,219-262):
  * out[out_offset + i] = in[i] for every variable (state transition append, message append). */
