@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda / e2e legs")
     ap.add_argument("--stable", type=int, default=0)
     ap.add_argument("--true3d-sort", type=int, default=0)
+    ap.add_argument("--iter-mode", type=int, default=0, help="0 reference visit order (default), 1 radius-first, 2 radius-only")
     ap.add_argument("--bin-order", type=int, default=1, help="run message-reading functions in bin order (b200 extension)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -205,7 +206,7 @@ def main():
     if world == 1:
         x, y, z = population(n, L, seed=rank)
         s = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
-                            true3d_sort=args.true3d_sort, bin_order=args.bin_order)
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
         s.set_population("Circle", {"x": x, "y": y, "z": z})
         stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
         slab_sim = None
@@ -225,7 +226,7 @@ def main():
         cap = int(max(65536, 6 * n // planes_per_rank))
         slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=cap,
                                        migrate_capacity=cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
-                                       stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order)
+                                       stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
         s = slab_sim.sim
         rng = np.random.default_rng(rank)
         z_lo, z_hi = slab_sim.z0 * RADIUS, slab_sim.z1 * RADIUS
@@ -279,7 +280,7 @@ def main():
         "config": {
             "workload": f"Circles-3D, {n} agents per GPU, [0,{L:g})^3, radius {RADIUS:g} ({bins} bins, ~8 agents/bin), "
                         f"whole CUDASimulation::step() (output_message, auto agent sort, PBM buildIndex, move)",
-            "agents_per_gpu": n, "bins": bins, "graphs": s.graphs, "bin_order_execution": bool(args.bin_order),
+            "agents_per_gpu": n, "bins": bins, "graphs": s.graphs, "bin_order_execution": bool(args.bin_order), "iterator_mode": args.iter_mode,
             "l2": "flushed between steps (256 MiB write outside the timed events)" if world == 1 else
                   "not flushed (exchange-synchronised steps; per-GPU working set ~80 MB)",
             "timing": "sum of per-step CUDA-event times on the simulation stream" if world == 1 else
@@ -297,7 +298,7 @@ def main():
         peak, peak_src = measured_peak()
         # -- per-phase device times from a profiled (eager, event-bracketed) pass of the same workload
         p = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, profile=1, stable=args.stable,
-                            true3d_sort=args.true3d_sort, bin_order=args.bin_order)
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
         p.set_population("Circle", {"x": x, "y": y, "z": z})
         pstream = torch.cuda.ExternalStream(p.stream, device=f"cuda:{local}")
         for i in range(args.warmup + 30):

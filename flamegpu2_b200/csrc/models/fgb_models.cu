@@ -115,6 +115,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
     s->sim->CUDAConfig().profile = getu(kv, "profile", 0) != 0;
     s->sim->CUDAConfig().binOrderExecution = getu(kv, "bin_order", 1) != 0;
+    s->sim->CUDAConfig().spatialIterationMode = static_cast<int>(getu(kv, "iter_mode", 0));
     *out = s.release();
   });
 }

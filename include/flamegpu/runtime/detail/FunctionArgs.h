@@ -39,6 +39,12 @@ struct SpatialMeta {
   int win_begin;        // slab window on the slowest axis: first plane stored locally
   int win_count;        // ... and how many (== grid_dim[slowest] on a single GPU)
   int wrap_compatible;
+  // b200 iterator modes (0 = reference order, every message of the Moore neighbourhood in strip order):
+  //  1 = radius-first: the same messages, each exactly once, but those within the radius of the search
+  //      origin first (in strip order), then the rest (in strip order);
+  //  2 = radius-only: only messages within the radius (a superset of what `sqrtf(d2) < radius` accepts).
+  int iter_mode;
+  float radius2_eps;   // radius^2 * (1 + 1e-5): conservative in-radius test of the iterator
   const unsigned int *pbm;
 };
 

@@ -47,9 +47,11 @@ class MessageSpatial2D {
       class Message {
         const detail::FunctionArgs &a;
         const detail::LocPtrs loc;
+        float ox, oy;
         int cx, cy;
         int strip;  // 0..2, 3 == end
         int idx, idx_end, nxt, nxt_end;
+        int phase;
         __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
           b = 0;
           e = 0;
@@ -73,20 +75,45 @@ class MessageSpatial2D {
             fetch(strip + 1, nxt, nxt_end);
           } while (idx >= idx_end && strip < 3);
         }
+        __device__ __forceinline__ void restart() {
+          strip = -1;
+          fetch(0, nxt, nxt_end);
+          next_strip();
+        }
+        __device__ __forceinline__ bool in_radius() const {
+          const float dx = __ldg(reinterpret_cast<const float *>(loc.x) + idx) - ox;
+          const float dy = __ldg(reinterpret_cast<const float *>(loc.y) + idx) - oy;
+          return dx * dx + dy * dy <= a.in_meta.radius2_eps;
+        }
+        __device__ __forceinline__ void settle() {
+          for (;;) {
+            if (strip >= 3) {
+              if (a.in_meta.iter_mode == 1 && phase == 0) {
+                phase = 1;
+                restart();
+                continue;
+              }
+              return;
+            }
+            if (in_radius() == (phase == 0)) return;
+            if (++idx >= idx_end) next_strip();
+          }
+        }
 
        public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, int _cx, int _cy, bool begin)
-            : a(args), loc(detail::make_loc(args)), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin)
+            : a(args), loc(detail::make_loc(args)), ox(x), oy(y), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0),
+              phase(0) {
           if (begin) {
-            strip = -1;
-            fetch(0, nxt, nxt_end);
-            next_strip();
+            restart();
+            if (a.in_meta.iter_mode != 0) settle();
           }
         }
         __device__ __forceinline__ bool operator!=(const Message &) const { return strip < 3; }
         __device__ __forceinline__ bool operator==(const Message &rhs) const { return strip == rhs.strip && idx == rhs.idx; }
         __device__ __forceinline__ Message &operator++() {
           if (++idx >= idx_end) next_strip();
+          if (a.in_meta.iter_mode != 0) settle();
           return *this;
         }
         template <typename T, unsigned int N>
@@ -110,8 +137,8 @@ class MessageSpatial2D {
         Message m;
 
        public:
-        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, int cx, int cy, bool begin)
-            : m(args, cx, cy, begin) {}
+        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, int cx, int cy, bool begin)
+            : m(args, x, y, cx, cy, begin) {}
         __device__ __forceinline__ iterator &operator++() {
           ++m;
           return *this;
@@ -121,15 +148,16 @@ class MessageSpatial2D {
         __device__ __forceinline__ Message &operator*() { return m; }
         __device__ __forceinline__ Message *operator->() { return &m; }
       };
-      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y) : a(args) {
+      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y) : a(args), lx(x), ly(y) {
         cx = detail::grid_cell(args.in_meta, 0, x);
         cy = detail::grid_cell(args.in_meta, 1, y) - args.in_meta.win_begin;  // row index inside the slab window
       }
-      __device__ __forceinline__ iterator begin() const { return iterator(a, cx, cy, true); }
-      __device__ __forceinline__ iterator end() const { return iterator(a, cx, cy, false); }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, cx, cy, true); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, cx, cy, false); }
 
      private:
       const detail::FunctionArgs &a;
+      float lx, ly;
       int cx, cy;
     };
 

@@ -50,10 +50,12 @@ class MessageSpatial3D {
       class Message {
         const detail::FunctionArgs &a;
         const detail::LocPtrs loc;
+        float ox, oy, oz;   // search origin (used by the radius modes only)
         int cx, cy, cz;
         int strip;          // 0..8 current strip, 9 == end
         int idx, idx_end;   // current message, one past the last message of the strip
         int nxt, nxt_end;   // prefetched bounds of strip+1
+        int phase;          // radius-first mode: 0 = in-radius pass, 1 = the rest
 
         // [PBM[hash(cx-1,y,z)], PBM[hash(cx+1,y,z)+1]) of strip s; empty if outside the grid
         __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
@@ -79,14 +81,42 @@ class MessageSpatial3D {
             fetch(strip + 1, nxt, nxt_end);
           } while (idx >= idx_end && strip < 9);
         }
+        __device__ __forceinline__ void restart() {
+          strip = -1;
+          fetch(0, nxt, nxt_end);
+          next_strip();
+        }
+        // conservative superset of the user's usual `sqrtf(dx*dx+dy*dy+dz*dz) < radius`
+        __device__ __forceinline__ bool in_radius() const {
+          const float dx = __ldg(reinterpret_cast<const float *>(loc.x) + idx) - ox;
+          const float dy = __ldg(reinterpret_cast<const float *>(loc.y) + idx) - oy;
+          const float dz = __ldg(reinterpret_cast<const float *>(loc.z) + idx) - oz;
+          return dx * dx + dy * dy + dz * dz <= a.in_meta.radius2_eps;
+        }
+        // radius modes: move on until the current message belongs to the current pass
+        __device__ __forceinline__ void settle() {
+          for (;;) {
+            if (strip >= 9) {
+              if (a.in_meta.iter_mode == 1 && phase == 0) {
+                phase = 1;
+                restart();
+                continue;
+              }
+              return;
+            }
+            if (in_radius() == (phase == 0)) return;
+            if (++idx >= idx_end) next_strip();
+          }
+        }
 
        public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, int _cx, int _cy, int _cz, bool begin)
-            : a(args), loc(detail::make_loc(args)), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0), nxt(0), nxt_end(0) {
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, float z, int _cx, int _cy, int _cz,
+                                           bool begin)
+            : a(args), loc(detail::make_loc(args)), ox(x), oy(y), oz(z), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0),
+              nxt(0), nxt_end(0), phase(0) {
           if (begin) {
-            strip = -1;
-            fetch(0, nxt, nxt_end);
-            next_strip();
+            restart();
+            if (a.in_meta.iter_mode != 0) settle();
           }
         }
         __device__ __forceinline__ bool operator!=(const Message &) const { return strip < 9; }
@@ -95,6 +125,7 @@ class MessageSpatial3D {
         }
         __device__ __forceinline__ Message &operator++() {
           if (++idx >= idx_end) next_strip();
+          if (a.in_meta.iter_mode != 0) settle();
           return *this;
         }
         template <typename T, unsigned int N>
@@ -119,8 +150,9 @@ class MessageSpatial3D {
         Message m;
 
        public:
-        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, int cx, int cy, int cz, bool begin)
-            : m(args, cx, cy, cz, begin) {}
+        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, float z, int cx, int cy, int cz,
+                                            bool begin)
+            : m(args, x, y, z, cx, cy, cz, begin) {}
         __device__ __forceinline__ iterator &operator++() {
           ++m;
           return *this;
@@ -130,16 +162,18 @@ class MessageSpatial3D {
         __device__ __forceinline__ Message &operator*() { return m; }
         __device__ __forceinline__ Message *operator->() { return &m; }
       };
-      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, float z) : a(args) {
+      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, float z)
+          : a(args), lx(x), ly(y), lz(z) {
         cx = detail::grid_cell(args.in_meta, 0, x);
         cy = detail::grid_cell(args.in_meta, 1, y);
         cz = detail::grid_cell(args.in_meta, 2, z) - args.in_meta.win_begin;  // plane index inside the slab window
       }
-      __device__ __forceinline__ iterator begin() const { return iterator(a, cx, cy, cz, true); }
-      __device__ __forceinline__ iterator end() const { return iterator(a, cx, cy, cz, false); }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, lz, cx, cy, cz, true); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, lz, cx, cy, cz, false); }
 
      private:
       const detail::FunctionArgs &a;
+      float lx, ly, lz;
       int cx, cy, cz;
     };
 

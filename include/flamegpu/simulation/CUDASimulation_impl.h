@@ -407,7 +407,7 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
     }
   k.push_back(sort_bits);
   k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull) |
-              (cuda_config.binOrderExecution ? 4ull : 0ull));
+              (cuda_config.binOrderExecution ? 4ull : 0ull) | (static_cast<unsigned long long>(cuda_config.spatialIterationMode) << 8));
   return k;
 }
 
@@ -570,6 +570,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       a.in_meta.win_begin = M.win_begin;
       a.in_meta.win_count = M.win_count;
       a.in_meta.radius = M.md.radius;
+      a.in_meta.iter_mode = cuda_config.spatialIterationMode;
+      a.in_meta.radius2_eps = M.md.radius * M.md.radius * 1.00001f;
       a.in_meta.wrap_compatible = M.md.wrap_compatible ? 1 : 0;
       a.in_meta.pbm = M.md.PBM;
     }
