@@ -90,7 +90,7 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
   src.mask = 0;
   src.g = make_geo(sp);
   const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z)) && vars_in_aligned(vars, nvars);
-  const unsigned int grid = bin_grid(n);
+  const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
   const bool stable = (flags & FGB_BUILD_STABLE) != 0;
   if (stable) {
@@ -136,7 +136,7 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   src.z = z;
   src.g = make_geo(sp);
   const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
-  const unsigned int grid = bin_grid(n);
+  const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
   VarTable none{};
   none.n = 0;

@@ -82,25 +82,30 @@ struct KeySrc {
   }
 };
 
-// Runs of equal keys among a thread's (up to) four consecutive items.
-struct Runs {
-  bool head1, head2, head3;  // item j starts a new run (item 0 always does)
-  uint32_t len0, len1, len2; // run length if the run starts at item 0/1/2 (a run at 3 has length 1)
-};
-__device__ __forceinline__ Runs make_runs(const uint32_t k[4], int cnt) {
-  const bool v1 = cnt > 1, v2 = cnt > 2, v3 = cnt > 3;
-  const bool s1 = v1 && k[1] == k[0], s2 = v2 && k[2] == k[1], s3 = v3 && k[3] == k[2];
-  Runs r;
-  r.head1 = v1 && !s1;
-  r.head2 = v2 && !s2;
-  r.head3 = v3 && !s3;
-  const uint32_t t3 = s3 ? 1u : 0u;
-  r.len2 = 1u + t3;
-  const uint32_t t2 = s2 ? r.len2 : 0u;
-  r.len1 = 1u + t2;
-  const uint32_t t1 = s1 ? r.len1 : 0u;
-  r.len0 = 1u + t1;
-  return r;
+// ---- block-local aggregation table ---------------------------------------------------------
+// Every block first aggregates the keys of its tile in a shared-memory open-addressing table
+// (shared-memory atomics), then touches global memory once per DISTINCT key of the tile.  Lists
+// arrive grouped (agents are sorted every step), so a 2048-item tile holds a few hundred distinct
+// bins: ~8x fewer L2 atomics than one per item, and none of them on the per-item critical path.
+constexpr int kTileItems = 8;                               // items per thread
+constexpr int kTile = kBinThreads * kTileItems;             // 2048 items per block
+constexpr int kTabBits = 12;
+constexpr int kTabSlots = 1 << kTabBits;                    // 4096 slots (load factor <= 0.5)
+constexpr uint32_t kTabEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t tab_insert(uint32_t *s_key, uint32_t key) {
+  uint32_t slot = (key * 2654435761u) >> (32 - kTabBits);
+  while (true) {
+    const uint32_t prev = atomicCAS(s_key + slot, kTabEmpty, key);
+    if (prev == kTabEmpty || prev == key) return slot;
+    slot = (slot + 1) & (kTabSlots - 1);
+  }
+}
+
+template <int DIMS, bool VEC>
+__device__ __forceinline__ void load_tile_keys(const KeySrc<DIMS> &src, uint32_t i0, uint32_t n, uint32_t k[kTileItems]) {
+  src.template load4<VEC>(i0, n, k);
+  src.template load4<VEC>(i0 + 4, n, k + 4);
 }
 
 // ---- phase 1: histogram ------------------------------------------------------------------
@@ -110,23 +115,42 @@ template <int DIMS, bool VEC>
 __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                           uint32_t *hist, unsigned long long *state,
                                                           uint32_t n_state, uint32_t *ctrl) {
+  __shared__ uint32_t s_key[kTabSlots];
+  __shared__ uint32_t s_cnt[kTabSlots];
   const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
   const uint32_t total = gridDim.x * kBinThreads;
   for (uint32_t s = gtid; s < n_state; s += total) state[s] = 0ull;
   if (gtid == 0 && ctrl) ctrl[0] = 0u;
+  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+    s_key[s] = kTabEmpty;
+    s_cnt[s] = 0u;
+  }
+  __syncthreads();
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t i0 = gtid * kBinItems;
-  if (i0 >= n) return;
-  uint32_t k[4];
-  src.template load4<VEC>(i0, n, k);
-  // run-length aggregate the thread's consecutive items: lists arrive nearly bin-sorted (agents
-  // are bin-sorted every step), so most threads issue one RED instead of four.
-  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
-  const Runs r = make_runs(k, cnt);
-  atomicAdd(hist + k[0], r.len0);
-  if (r.head1) atomicAdd(hist + k[1], r.len1);
-  if (r.head2) atomicAdd(hist + k[2], r.len2);
-  if (r.head3) atomicAdd(hist + k[3], 1u);
+  const uint32_t i0 = gtid * kTileItems;
+  if (i0 < n) {
+    uint32_t k[kTileItems];
+    load_tile_keys<DIMS, VEC>(src, i0, n, k);
+    const int cnt = (n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems;
+    // run-length aggregate the thread's consecutive items, one shared-memory atomic per run
+    int j = 0;
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      if (r == j && j < cnt) {
+        int e = j + 1;
+#pragma unroll
+        for (int t = 1; t < kTileItems; ++t)
+          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+        atomicAdd(s_cnt + tab_insert(s_key, k[r]), static_cast<uint32_t>(e - j));
+        j = e;
+      }
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+    const uint32_t key = s_key[s];
+    if (key != kTabEmpty) atomicAdd(hist + key, s_cnt[s]);
+  }
 }
 
 // ---- phase 3: scatter --------------------------------------------------------------------
@@ -135,43 +159,71 @@ template <int DIMS, bool VEC, bool IDX_ONLY>
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                              uint32_t *cursor, const __grid_constant__ VarTable vt,
                                                              uint32_t *perm) {
+  __shared__ uint32_t s_key[kTabSlots];
+  __shared__ uint32_t s_cnt[kTabSlots];  // count of the key in this tile, then its global base
+  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+    s_key[s] = kTabEmpty;
+    s_cnt[s] = 0u;
+  }
+  __syncthreads();
   const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t i0 = gtid * kBinItems;
-  if (i0 >= n) return;
-  uint32_t k[4], dst[4];
-  src.template load4<VEC>(i0, n, k);
-  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
-  // claim one contiguous slot range per run of equal keys (independent atomics, all in flight)
-  const Runs r = make_runs(k, cnt);
-  const uint32_t b0 = atomicAdd(cursor + k[0] + 1, r.len0);
-  const uint32_t b1 = r.head1 ? atomicAdd(cursor + k[1] + 1, r.len1) : 0u;
-  const uint32_t b2 = r.head2 ? atomicAdd(cursor + k[2] + 1, r.len2) : 0u;
-  const uint32_t b3 = r.head3 ? atomicAdd(cursor + k[3] + 1, 1u) : 0u;
-  dst[0] = b0;
-  dst[1] = r.head1 ? b1 : dst[0] + 1;
-  dst[2] = r.head2 ? b2 : dst[1] + 1;
-  dst[3] = r.head3 ? b3 : dst[2] + 1;
-  if constexpr (IDX_ONLY) {
+  const uint32_t i0 = gtid * kTileItems;
+  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  uint32_t k[kTileItems], slot[kTileItems], rank[kTileItems];
+  if (cnt) {
+    load_tile_keys<DIMS, VEC>(src, i0, n, k);
+    // rank of each item among the tile's items of the same key (runs of a thread claim a range at once)
+    int j = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (t < cnt) perm[dst[t]] = i0 + t;
-  } else {
-  for (uint32_t v = 0; v < vt.n; ++v) {
-    const uint32_t len = vt.len[v];
-    if (VEC && len == 4 && cnt == 4) {
-      const uint4 q = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
-      uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
-      o[dst[0]] = q.x;
-      o[dst[1]] = q.y;
-      o[dst[2]] = q.z;
-      o[dst[3]] = q.w;
-    } else {
+    for (int r = 0; r < kTileItems; ++r) {
+      if (r == j && j < cnt) {
+        int e = j + 1;
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+        for (int t = 1; t < kTileItems; ++t)
+          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+        const uint32_t sl = tab_insert(s_key, k[r]);
+        const uint32_t b = atomicAdd(s_cnt + sl, static_cast<uint32_t>(e - j));
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (r + t < e && t < kTileItems - r) {
+            slot[r + t] = sl;
+            rank[r + t] = b + t;
+          }
+        j = e;
+      }
     }
   }
+  __syncthreads();
+  // one global atomic per distinct key of the tile: claim the contiguous slot range
+  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+    const uint32_t key = s_key[s];
+    if (key != kTabEmpty) s_cnt[s] = atomicAdd(cursor + key + 1, s_cnt[s]);
+  }
+  __syncthreads();
+  if (!cnt) return;
+  uint32_t dst[kTileItems];
+#pragma unroll
+  for (int t = 0; t < kTileItems; ++t) dst[t] = t < cnt ? s_cnt[slot[t]] + rank[t] : 0u;
+  if constexpr (IDX_ONLY) {
+#pragma unroll
+    for (int t = 0; t < kTileItems; ++t)
+      if (t < cnt) perm[dst[t]] = i0 + t;
+  } else {
+    for (uint32_t v = 0; v < vt.n; ++v) {
+      const uint32_t len = vt.len[v];
+      if (VEC && len == 4 && cnt == kTileItems) {
+        const uint4 q0 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+        const uint4 q1 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
+        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+        o[dst[0]] = q0.x; o[dst[1]] = q0.y; o[dst[2]] = q0.z; o[dst[3]] = q0.w;
+        o[dst[4]] = q1.x; o[dst[5]] = q1.y; o[dst[6]] = q1.z; o[dst[7]] = q1.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+      }
+    }
   }
 }
 
@@ -308,9 +360,11 @@ __global__ void __launch_bounds__(kBinThreads) k_gather(const uint32_t *__restri
 
 #endif  // __CUDACC__
 
+// blocks for the 4-items-per-thread kernels (gather) and for the tile kernels (histogram, scatter)
 inline unsigned int bin_grid(unsigned int n) {
   const unsigned int per_block = kBinThreads * kBinItems;
   return (n + per_block - 1) / per_block;
 }
+inline unsigned int tile_grid(unsigned int n) { return (n + kTile - 1) / kTile; }
 
 }  // namespace fgb
