@@ -94,7 +94,10 @@ constexpr int kTabSlots = 1 << kTabBits;                    // 4096 slots (load 
 constexpr uint32_t kTabEmpty = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t tab_insert(uint32_t *s_key, uint32_t key) {
-  uint32_t slot = (key * 2654435761u) >> (32 - kTabBits);
+  // low key bits keep x-adjacent bins in adjacent slots (coalesced write-out of the staged tile); the high
+  // bits are mixed in additively so that keys that differ by a multiple of the table size (the same column
+  // in another z plane of a power-of-two grid) do not pile up on one probe chain
+  uint32_t slot = (key + (key >> kTabBits) * 0x9E3779B1u) & (kTabSlots - 1);
   while (true) {
     const uint32_t prev = atomicCAS(s_key + slot, kTabEmpty, key);
     if (prev == kTabEmpty || prev == key) return slot;
@@ -155,25 +158,33 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
 
 // ---- phase 3: scatter --------------------------------------------------------------------
 // cursor[k+1] holds the next free slot of bin k.  IDX_ONLY: perm[dst] = source index.
+//
+// Tile-staged: the block (1) ranks its items per key in the shared-memory table, (2) claims one
+// contiguous output range per distinct key with a single global atomic, (3) lays the tile out in
+// TABLE order in shared memory (the table is indexed by the low key bits, so x-adjacent bins -- which
+// are adjacent in the output -- sit in adjacent slots), and (4) writes it out with consecutive lanes
+// on consecutive staged items: stores hit whole 32-byte sectors instead of one sector per 4 bytes.
 template <int DIMS, bool VEC, bool IDX_ONLY>
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                              uint32_t *cursor, const __grid_constant__ VarTable vt,
                                                              uint32_t *perm) {
-  __shared__ uint32_t s_key[kTabSlots];
-  __shared__ uint32_t s_cnt[kTabSlots];  // count of the key in this tile, then its global base
+  __shared__ uint32_t s_key[kTabSlots];   // key of the slot, later the slot's offset in the staged tile
+  __shared__ uint32_t s_cnt[kTabSlots];   // count of the key in this tile, later its global base
+  __shared__ uint32_t s_dst[kTile];       // staged tile: destination index ...
+  __shared__ uint16_t s_src[kTile];       // ... and source item (offset inside the tile)
+  __shared__ uint32_t s_scan[33];
   for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
     s_key[s] = kTabEmpty;
     s_cnt[s] = 0u;
   }
   __syncthreads();
-  const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t i0 = gtid * kTileItems;
+  const uint32_t tile0 = blockIdx.x * kTile;
+  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
   const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
   uint32_t k[kTileItems], slot[kTileItems], rank[kTileItems];
   if (cnt) {
     load_tile_keys<DIMS, VEC>(src, i0, n, k);
-    // rank of each item among the tile's items of the same key (runs of a thread claim a range at once)
     int j = 0;
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
@@ -195,33 +206,47 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, u
     }
   }
   __syncthreads();
-  // one global atomic per distinct key of the tile: claim the contiguous slot range
-  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
-    const uint32_t key = s_key[s];
-    if (key != kTabEmpty) s_cnt[s] = atomicAdd(cursor + key + 1, s_cnt[s]);
+  // per slot: claim the global range (one atomic per distinct key) and compute the staging offset
+  {
+    constexpr int kPer = kTabSlots / kBinThreads;  // 16 consecutive slots per thread
+    uint32_t c[kPer], sum = 0;
+    const int s0 = threadIdx.x * kPer;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const uint32_t key = s_key[s0 + q];
+      c[q] = key != kTabEmpty ? s_cnt[s0 + q] : 0u;
+      if (c[q]) s_cnt[s0 + q] = atomicAdd(cursor + key + 1, c[q]);
+      sum += c[q];
+    }
+    uint32_t tile_total;
+    uint32_t off = block_exclusive_scan(sum, s_scan, &tile_total);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      s_key[s0 + q] = off;
+      off += c[q];
+    }
   }
   __syncthreads();
-  if (!cnt) return;
-  uint32_t dst[kTileItems];
 #pragma unroll
-  for (int t = 0; t < kTileItems; ++t) dst[t] = t < cnt ? s_cnt[slot[t]] + rank[t] : 0u;
+  for (int t = 0; t < kTileItems; ++t)
+    if (t < cnt) {
+      const uint32_t e = s_key[slot[t]] + rank[t];
+      s_dst[e] = s_cnt[slot[t]] + rank[t];
+      s_src[e] = static_cast<uint16_t>(threadIdx.x * kTileItems + t);
+    }
+  __syncthreads();
+  const uint32_t tile_n = tile0 < n ? ((n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile) : 0u;
   if constexpr (IDX_ONLY) {
-#pragma unroll
-    for (int t = 0; t < kTileItems; ++t)
-      if (t < cnt) perm[dst[t]] = i0 + t;
+    for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) perm[s_dst[e]] = tile0 + s_src[e];
   } else {
     for (uint32_t v = 0; v < vt.n; ++v) {
-      const uint32_t len = vt.len[v];
-      if (VEC && len == 4 && cnt == kTileItems) {
-        const uint4 q0 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
-        const uint4 q1 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
+      if (vt.len[v] == 4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]) + tile0;
         uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
-        o[dst[0]] = q0.x; o[dst[1]] = q0.y; o[dst[2]] = q0.z; o[dst[3]] = q0.w;
-        o[dst[4]] = q1.x; o[dst[5]] = q1.y; o[dst[6]] = q1.z; o[dst[7]] = q1.w;
+#pragma unroll 4
+        for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) o[s_dst[e]] = __ldg(in + s_src[e]);
       } else {
-#pragma unroll
-        for (int t = 0; t < kTileItems; ++t)
-          if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+        for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) copy_item(vt, v, tile0 + s_src[e], s_dst[e]);
       }
     }
   }
