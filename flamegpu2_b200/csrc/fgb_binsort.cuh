@@ -111,44 +111,68 @@ __device__ __forceinline__ void load_tile_keys(const KeySrc<DIMS> &src, uint32_t
   src.template load4<VEC>(i0 + 4, n, k + 4);
 }
 
+// Number of runs of equal keys among a thread's consecutive items, summed over the block.  A tile
+// of a bin-sorted list has few runs (neighbouring items share a bin, and output positions of
+// consecutive items are consecutive); a tile of a list in some other order has one run per item.
+__device__ __forceinline__ uint32_t block_run_count(const uint32_t k[kTileItems], int cnt, uint32_t *s_counter) {
+  uint32_t runs = cnt > 0 ? 1u : 0u;
+#pragma unroll
+  for (int t = 1; t < kTileItems; ++t)
+    if (t < cnt && k[t] != k[t - 1]) ++runs;
+  if (threadIdx.x == 0) *s_counter = 0u;
+  __syncthreads();
+  const uint32_t w = __reduce_add_sync(0xffffffffu, runs);
+  if ((threadIdx.x & 31) == 0) atomicAdd(s_counter, w);
+  __syncthreads();
+  return *s_counter;
+}
+
 // ---- phase 1: histogram ------------------------------------------------------------------
 // Also zeroes the look-back words of the scan that follows and the big-bin counter.
 // hist[] must be all-zero on entry; the scan re-zeroes it.
+// Per tile: grouped input -> one RED per run straight to global memory; ungrouped input -> aggregate in
+// the shared-memory table first, one RED per distinct key.
 template <int DIMS, bool VEC>
 __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                           uint32_t *hist, unsigned long long *state,
                                                           uint32_t n_state, uint32_t *ctrl) {
   __shared__ uint32_t s_key[kTabSlots];
   __shared__ uint32_t s_cnt[kTabSlots];
+  __shared__ uint32_t s_runs;
   const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
   const uint32_t total = gridDim.x * kBinThreads;
   for (uint32_t s = gtid; s < n_state; s += total) state[s] = 0ull;
   if (gtid == 0 && ctrl) ctrl[0] = 0u;
-  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
-    s_key[s] = kTabEmpty;
-    s_cnt[s] = 0u;
-  }
-  __syncthreads();
   const uint32_t n = load_count(d_n, n_max);
+  const uint32_t tile0 = blockIdx.x * kTile;
+  if (tile0 >= n) return;
   const uint32_t i0 = gtid * kTileItems;
-  if (i0 < n) {
-    uint32_t k[kTileItems];
-    load_tile_keys<DIMS, VEC>(src, i0, n, k);
-    const int cnt = (n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems;
-    // run-length aggregate the thread's consecutive items, one shared-memory atomic per run
-    int j = 0;
+  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  uint32_t k[kTileItems];
+  if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
+  if (!grouped) {
+    for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+      s_key[s] = kTabEmpty;
+      s_cnt[s] = 0u;
+    }
+    __syncthreads();
+  }
+  int j = 0;
 #pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
-      if (r == j && j < cnt) {
-        int e = j + 1;
+  for (int r = 0; r < kTileItems; ++r) {
+    if (r == j && j < cnt) {
+      int e = j + 1;
 #pragma unroll
-        for (int t = 1; t < kTileItems; ++t)
-          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
-        atomicAdd(s_cnt + tab_insert(s_key, k[r]), static_cast<uint32_t>(e - j));
-        j = e;
-      }
+      for (int t = 1; t < kTileItems; ++t)
+        if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+      if (grouped) atomicAdd(hist + k[r], static_cast<uint32_t>(e - j));
+      else atomicAdd(s_cnt + tab_insert(s_key, k[r]), static_cast<uint32_t>(e - j));
+      j = e;
     }
   }
+  if (grouped) return;
   __syncthreads();
   for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
     const uint32_t key = s_key[s];
@@ -159,11 +183,13 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
 // ---- phase 3: scatter --------------------------------------------------------------------
 // cursor[k+1] holds the next free slot of bin k.  IDX_ONLY: perm[dst] = source index.
 //
-// Tile-staged: the block (1) ranks its items per key in the shared-memory table, (2) claims one
-// contiguous output range per distinct key with a single global atomic, (3) lays the tile out in
-// TABLE order in shared memory (the table is indexed by the low key bits, so x-adjacent bins -- which
-// are adjacent in the output -- sit in adjacent slots), and (4) writes it out with consecutive lanes
-// on consecutive staged items: stores hit whole 32-byte sectors instead of one sector per 4 bytes.
+// Grouped tile (the steady state of a bin-sorted list): one global atomic per run, items of a run
+// and of neighbouring threads land on consecutive addresses, payload streamed with 128-bit loads.
+// Ungrouped tile: (1) rank the items per key in the shared-memory table, (2) claim one contiguous
+// output range per distinct key with a single global atomic, (3) lay the tile out in TABLE order in
+// shared memory (the table is indexed by the low key bits, so x-adjacent bins -- adjacent in the
+// output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
+// items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
 template <int DIMS, bool VEC, bool IDX_ONLY>
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                              uint32_t *cursor, const __grid_constant__ VarTable vt,
@@ -173,18 +199,64 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, u
   __shared__ uint32_t s_dst[kTile];       // staged tile: destination index ...
   __shared__ uint16_t s_src[kTile];       // ... and source item (offset inside the tile)
   __shared__ uint32_t s_scan[33];
+  __shared__ uint32_t s_runs;
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t tile0 = blockIdx.x * kTile;
+  if (tile0 >= n) return;
+  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
+  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+  uint32_t k[kTileItems];
+  if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
+
+  if (grouped) {
+    if (!cnt) return;
+    uint32_t dst[kTileItems];
+    int j = 0;
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      if (r == j && j < cnt) {
+        int e = j + 1;
+#pragma unroll
+        for (int t = 1; t < kTileItems; ++t)
+          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+        const uint32_t b = atomicAdd(cursor + k[r] + 1, static_cast<uint32_t>(e - j));
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (r + t < e && t < kTileItems - r) dst[r + t] = b + t;
+        j = e;
+      }
+    }
+    if constexpr (IDX_ONLY) {
+#pragma unroll
+      for (int t = 0; t < kTileItems; ++t)
+        if (t < cnt) perm[dst[t]] = i0 + t;
+    } else {
+      for (uint32_t v = 0; v < vt.n; ++v) {
+        if (VEC && vt.len[v] == 4 && cnt == kTileItems) {
+          const uint4 q0 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+          const uint4 q1 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
+          uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+          o[dst[0]] = q0.x; o[dst[1]] = q0.y; o[dst[2]] = q0.z; o[dst[3]] = q0.w;
+          o[dst[4]] = q1.x; o[dst[5]] = q1.y; o[dst[6]] = q1.z; o[dst[7]] = q1.w;
+        } else {
+#pragma unroll
+          for (int t = 0; t < kTileItems; ++t)
+            if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+        }
+      }
+    }
+    return;
+  }
+
   for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
     s_key[s] = kTabEmpty;
     s_cnt[s] = 0u;
   }
   __syncthreads();
-  const uint32_t n = load_count(d_n, n_max);
-  const uint32_t tile0 = blockIdx.x * kTile;
-  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
-  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
-  uint32_t k[kTileItems], slot[kTileItems], rank[kTileItems];
-  if (cnt) {
-    load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  uint32_t slot[kTileItems], rank[kTileItems];
+  {
     int j = 0;
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
@@ -235,7 +307,6 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, u
       s_src[e] = static_cast<uint16_t>(threadIdx.x * kTileItems + t);
     }
   __syncthreads();
-  const uint32_t tile_n = tile0 < n ? ((n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile) : 0u;
   if constexpr (IDX_ONLY) {
     for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) perm[s_dst[e]] = tile0 + s_src[e];
   } else {
