@@ -99,26 +99,35 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
     r = sp->worklist.reserve(worklist_bytes(n));
     if (r) return r;
   }
-  if (vec)
-    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
-  else
-    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
-  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-  ctx->launches += 2;
+  r = sp->tile_mode.reserve((static_cast<size_t>(grid) + 1) * 4);
+  if (r) return r;
+  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
   uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
+  const unsigned int dgrid = bin_grid(n);
+  if (vec)
+    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
+  else
+    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
+  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
   if (!stable) {
-    if (vec)
-      k_bin_scatter<DIMS, true, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr);
-    else
-      k_bin_scatter<DIMS, false, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr);
-    ctx->launches += 1;
+    if (vec) {
+      k_bin_scatter_direct<DIMS, true, false><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
+      k_bin_scatter_staged<DIMS, true, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
+    } else {
+      k_bin_scatter_direct<DIMS, false, false><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
+      k_bin_scatter_staged<DIMS, false, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
+    }
+    ctx->launches += 4;
     return launch_ok();
   }
-  if (vec)
-    k_bin_scatter<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm);
-  else
-    k_bin_scatter<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm);
-  ctx->launches += 1;
+  if (vec) {
+    k_bin_scatter_direct<DIMS, true, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
+    k_bin_scatter_staged<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
+  } else {
+    k_bin_scatter_direct<DIMS, false, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
+    k_bin_scatter_staged<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
+  }
+  ctx->launches += 4;
   return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars,
                      st);
 }
@@ -144,15 +153,22 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
     int r = sp->worklist.reserve(worklist_bytes(n));
     if (r) return r;
   }
+  int r2 = sp->tile_mode.reserve((static_cast<size_t>(grid) + 1) * 4);
+  if (r2) return r2;
+  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
+  const unsigned int dgrid = bin_grid(n);
   if (vec) {
-    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
     k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-    k_bin_scatter<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm);
+    k_bin_scatter_direct<DIMS, true, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
+    k_bin_scatter_staged<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
   } else {
-    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
     k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-    k_bin_scatter<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm);
+    k_bin_scatter_direct<DIMS, false, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
+    k_bin_scatter_staged<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
   }
+  ctx->launches += 1;
   ctx->launches += 3;
   if (flags & FGB_BUILD_STABLE)
     return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
@@ -289,6 +305,7 @@ fgb_status fgb_spatial_destroy(fgb_spatial *sp) {
   if (sp->d_ctrl) cudaFree(sp->d_ctrl);
   sp->perm.release();
   sp->worklist.release();
+  sp->tile_mode.release();
   delete sp;
   return FGB_OK;
 }
@@ -331,7 +348,9 @@ fgb_status fgb_spatial_read_pbm(const fgb_spatial *sp, unsigned int *host_out, v
 
 fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max) {
   if (!sp) return FGB_ERR_INVALID_ARG;
-  int r = sp->perm.reserve(static_cast<size_t>(n_max) * 4);
+  int r = sp->tile_mode.reserve((static_cast<size_t>(tile_grid(n_max)) + 1) * 4);
+  if (r) return r;
+  r = sp->perm.reserve(static_cast<size_t>(n_max) * 4);
   if (r) return r;
   return sp->worklist.reserve(worklist_bytes(n_max));
 }

@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t block_run_count(const uint32_t k[kTileItems]
 template <int DIMS, bool VEC>
 __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
                                                           uint32_t *hist, unsigned long long *state,
-                                                          uint32_t n_state, uint32_t *ctrl) {
+                                                          uint32_t n_state, uint32_t *ctrl, uint32_t *tile_mode) {
   __shared__ uint32_t s_key[kTabSlots];
   __shared__ uint32_t s_cnt[kTabSlots];
   __shared__ uint32_t s_runs;
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
   if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
   const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
   const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
+  if (threadIdx.x == 0) tile_mode[blockIdx.x] = grouped ? 1u : 0u;  // the scatter kernels follow this choice
   if (!grouped) {
     for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
       s_key[s] = kTabEmpty;
@@ -190,65 +191,74 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
 // shared memory (the table is indexed by the low key bits, so x-adjacent bins -- adjacent in the
 // output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
 // items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
+// Grouped tiles: 4 items per thread, no shared memory, full occupancy (two blocks per 2048-item tile).
 template <int DIMS, bool VEC, bool IDX_ONLY>
-__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
-                                                             uint32_t *cursor, const __grid_constant__ VarTable vt,
-                                                             uint32_t *perm) {
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_direct(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                                    uint32_t *cursor, const __grid_constant__ VarTable vt,
+                                                                    uint32_t *perm, const uint32_t *__restrict__ tile_mode) {
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i0 = (blockIdx.x * kBinThreads + threadIdx.x) * kBinItems;
+  if (i0 >= n) return;
+  if (tile_mode[(blockIdx.x * kBinThreads * kBinItems) / kTile] == 0u) return;  // handled by the staged kernel
+  uint32_t k[4], dst[4];
+  src.template load4<VEC>(i0, n, k);
+  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
+  // claim one contiguous slot range per run of equal keys (independent atomics, all in flight)
+  const bool v1 = cnt > 1, v2 = cnt > 2, v3 = cnt > 3;
+  const bool s1 = v1 && k[1] == k[0], s2 = v2 && k[2] == k[1], s3 = v3 && k[3] == k[2];
+  const bool h1 = v1 && !s1, h2 = v2 && !s2, h3 = v3 && !s3;
+  const uint32_t len2 = 1u + (s3 ? 1u : 0u);
+  const uint32_t len1 = 1u + (s2 ? len2 : 0u);
+  const uint32_t len0 = 1u + (s1 ? len1 : 0u);
+  const uint32_t b0 = atomicAdd(cursor + k[0] + 1, len0);
+  const uint32_t b1 = h1 ? atomicAdd(cursor + k[1] + 1, len1) : 0u;
+  const uint32_t b2 = h2 ? atomicAdd(cursor + k[2] + 1, len2) : 0u;
+  const uint32_t b3 = h3 ? atomicAdd(cursor + k[3] + 1, 1u) : 0u;
+  dst[0] = b0;
+  dst[1] = h1 ? b1 : dst[0] + 1;
+  dst[2] = h2 ? b2 : dst[1] + 1;
+  dst[3] = h3 ? b3 : dst[2] + 1;
+  if constexpr (IDX_ONLY) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < cnt) perm[dst[t]] = i0 + t;
+  } else {
+    for (uint32_t v = 0; v < vt.n; ++v) {
+      if (VEC && vt.len[v] == 4 && cnt == 4) {
+        const uint4 q = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+        o[dst[0]] = q.x;
+        o[dst[1]] = q.y;
+        o[dst[2]] = q.z;
+        o[dst[3]] = q.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+      }
+    }
+  }
+}
+
+// Ungrouped tiles: shared-memory table + staged, coalesced write-out.
+template <int DIMS, bool VEC, bool IDX_ONLY>
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                                    uint32_t *cursor, const __grid_constant__ VarTable vt,
+                                                                    uint32_t *perm, const uint32_t *__restrict__ tile_mode) {
   __shared__ uint32_t s_key[kTabSlots];   // key of the slot, later the slot's offset in the staged tile
   __shared__ uint32_t s_cnt[kTabSlots];   // count of the key in this tile, later its global base
   __shared__ uint32_t s_dst[kTile];       // staged tile: destination index ...
   __shared__ uint16_t s_src[kTile];       // ... and source item (offset inside the tile)
   __shared__ uint32_t s_scan[33];
-  __shared__ uint32_t s_runs;
   const uint32_t n = load_count(d_n, n_max);
   const uint32_t tile0 = blockIdx.x * kTile;
   if (tile0 >= n) return;
+  if (tile_mode[blockIdx.x] != 0u) return;  // handled by the direct kernel
   const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
   const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
   const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
   uint32_t k[kTileItems];
   if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
-  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
-
-  if (grouped) {
-    if (!cnt) return;
-    uint32_t dst[kTileItems];
-    int j = 0;
-#pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
-      if (r == j && j < cnt) {
-        int e = j + 1;
-#pragma unroll
-        for (int t = 1; t < kTileItems; ++t)
-          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
-        const uint32_t b = atomicAdd(cursor + k[r] + 1, static_cast<uint32_t>(e - j));
-#pragma unroll
-        for (int t = 0; t < kTileItems; ++t)
-          if (r + t < e && t < kTileItems - r) dst[r + t] = b + t;
-        j = e;
-      }
-    }
-    if constexpr (IDX_ONLY) {
-#pragma unroll
-      for (int t = 0; t < kTileItems; ++t)
-        if (t < cnt) perm[dst[t]] = i0 + t;
-    } else {
-      for (uint32_t v = 0; v < vt.n; ++v) {
-        if (VEC && vt.len[v] == 4 && cnt == kTileItems) {
-          const uint4 q0 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
-          const uint4 q1 = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
-          uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
-          o[dst[0]] = q0.x; o[dst[1]] = q0.y; o[dst[2]] = q0.z; o[dst[3]] = q0.w;
-          o[dst[4]] = q1.x; o[dst[5]] = q1.y; o[dst[6]] = q1.z; o[dst[7]] = q1.w;
-        } else {
-#pragma unroll
-          for (int t = 0; t < kTileItems; ++t)
-            if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
-        }
-      }
-    }
-    return;
-  }
 
   for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
     s_key[s] = kTabEmpty;

@@ -234,4 +234,5 @@ struct fgb_spatial {
   fgb::DevBuf perm;      // stable mode: permutation
   fgb::DevBuf worklist;  // stable mode: big bins
   unsigned int *d_ctrl = nullptr;  // [0] = big-bin count
+  fgb::DevBuf tile_mode;           // per 2048-item tile: 1 = grouped (direct scatter), 0 = ungrouped (staged scatter)
 };
