@@ -171,6 +171,33 @@ FLAMEGPU_AGENT_FUNCTION(t_birth_optional_death, flamegpu::MessageNone, flamegpu:
   return flamegpu::ALIVE;
 }
 
+// ---- test_agent_function_conditions.cu:24-47 ---------------------------------------------------
+FLAMEGPU_AGENT_FUNCTION(t_cond_fn1, flamegpu::MessageNone, flamegpu::MessageNone) {
+  FLAMEGPU->setVariable<int>("x", FLAMEGPU->getVariable<int>("x") + 1);
+  FLAMEGPU->setVariable<int, 4>("y", 0, 3);
+  FLAMEGPU->setVariable<int, 4>("y", 1, 4);
+  FLAMEGPU->setVariable<int, 4>("y", 2, 5);
+  FLAMEGPU->setVariable<int, 4>("y", 3, 6);
+  return flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION(t_cond_fn2, flamegpu::MessageNone, flamegpu::MessageNone) {
+  FLAMEGPU->setVariable<int>("x", FLAMEGPU->getVariable<int>("x") - 1);
+  FLAMEGPU->setVariable<int, 4>("y", 0, 23);
+  FLAMEGPU->setVariable<int, 4>("y", 1, 24);
+  FLAMEGPU->setVariable<int, 4>("y", 2, 25);
+  FLAMEGPU->setVariable<int, 4>("y", 3, 26);
+  return flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION_CONDITION(t_cond_is1) { return FLAMEGPU->getVariable<int>("x") == 1; }
+FLAMEGPU_AGENT_FUNCTION_CONDITION(t_cond_not1) { return FLAMEGPU->getVariable<int>("x") != 1; }
+// same-state condition + death: only agents with x % 3 == 0 run; of those, even x die
+FLAMEGPU_AGENT_FUNCTION(t_cond_death_fn, flamegpu::MessageNone, flamegpu::MessageNone) {
+  const int x = FLAMEGPU->getVariable<int>("x");
+  FLAMEGPU->setVariable<int>("x", x + 1000);
+  return (x % 2 == 0) ? flamegpu::DEAD : flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION_CONDITION(t_cond_mod3) { return FLAMEGPU->getVariable<int>("x") % 3 == 0; }
+
 enum TestModel {
   TM_COUNT3D = 0,        // Spatial3DMessageTest.Mandatory
   TM_OPTIONAL3D = 1,     // Spatial3DMessageTest.Optional
@@ -181,7 +208,9 @@ enum TestModel {
   TM_BIRTH_MANDATORY = 6,       // DeviceAgentCreationTest.Mandatory_Output_SameState
   TM_BIRTH_OPTIONAL = 7,        // DeviceAgentCreationTest.Optional_Output_SameState
   TM_BIRTH_OPTIONAL_DEATH = 8,  // DeviceAgentCreationTest.Optional_Output_SameState_WithDeath
-  TM_BIRTH_OTHER_AGENT = 9      // DeviceAgentCreationTest.Mandatory_Output_DifferentAgent
+  TM_BIRTH_OTHER_AGENT = 9,     // DeviceAgentCreationTest.Mandatory_Output_DifferentAgent
+  TM_CONDITION_SPLIT = 10,      // TestAgentFunctionConditions.SplitAgents
+  TM_CONDITION_DEATH = 11       // condition + death in the same state (order: disabled front, then survivors)
 };
 
 struct TestParams {
@@ -294,6 +323,32 @@ inline void define_test_model(flamegpu::ModelDescription &model, const TestParam
       flamegpu::AgentFunctionDescription f = agent.newFunction("output", t_birth_mandatory);
       f.setAgentOutput(agent2);
       model.newLayer().addAgentFunction(f);
+      break;
+    }
+    case TM_CONDITION_SPLIT: {
+      agent.newVariable<int>("x");
+      agent.newVariable<int, 4>("y");
+      agent.newState("Start");
+      agent.newState("End");
+      agent.newState("End2");
+      flamegpu::AgentFunctionDescription af1 = agent.newFunction("Function1", t_cond_fn1);
+      af1.setInitialState("Start");
+      af1.setEndState("End");
+      af1.setFunctionCondition(t_cond_is1);
+      flamegpu::AgentFunctionDescription af2 = agent.newFunction("Function2", t_cond_fn2);
+      af2.setInitialState("Start");
+      af2.setEndState("End2");
+      af2.setFunctionCondition(t_cond_not1);
+      model.newLayer().addAgentFunction(af1);
+      model.newLayer().addAgentFunction(af2);
+      break;
+    }
+    case TM_CONDITION_DEATH: {
+      agent.newVariable<int>("x");
+      flamegpu::AgentFunctionDescription af = agent.newFunction("Function1", t_cond_death_fn);
+      af.setFunctionCondition(t_cond_mod3);
+      af.setAllowAgentDeath(true);
+      model.newLayer().addAgentFunction(af);
       break;
     }
     default:

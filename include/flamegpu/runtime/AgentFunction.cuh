@@ -29,18 +29,22 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
     const unsigned int c = __ldg(args.d_count);
     n = c < n ? c : n;
   }
-  if (index >= n) return;
+  // function condition: the agents that failed it sit at the front of the list and do not execute
+  // (reference CUDAFatAgent::processFunctionCondition, CUDAFatAgent.cu:186-236)
+  const unsigned int offset = args.d_agent_offset ? __ldg(args.d_agent_offset) : 0u;
+  if (index + offset >= n) return;
   // Run agents in the bin order of the input list when the scheduler provides it: lanes of a warp then
   // walk the same message strips (coalesced / broadcast loads).  Every per-agent slot (variables, scan
   // flags, message and new-agent slots) is addressed by the AGENT index, so results do not change.
-  const unsigned int agent = args.exec_perm ? __ldg(args.exec_perm + index) : index;
-  DeviceAPI<MessageIn, MessageOut> api(args, agent);
+  const unsigned int agent = args.exec_perm ? __ldg(args.exec_perm + index) : offset + index;
+  const unsigned int slot = agent - offset;  // message / new-agent slot: index among the executing agents
+  DeviceAPI<MessageIn, MessageOut> api(args, agent, slot);
   const AGENT_STATUS status = AgentFunction()(&api);
   // one flag store per thread, no memset beforehand (reference AgentFunction.cuh:111-119 +
   // CUDAScanCompaction::zero_async)
   if (args.death_flag) args.death_flag[agent] = static_cast<unsigned int>(status);
   if (MessageOut::HAS_OUTPUT) {
-    if (args.msg_out_flag) args.msg_out_flag[agent] = api.message_out.written() ? 1u : 0u;
+    if (args.msg_out_flag) args.msg_out_flag[slot] = api.message_out.written() ? 1u : 0u;
   }
   api.agent_out.finalise();
 }

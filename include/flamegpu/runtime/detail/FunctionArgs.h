@@ -59,6 +59,7 @@ struct DevEnv {
 struct FunctionArgs {
   const unsigned int *d_count;  // device-resident agent count (<= bound)
   const unsigned int *exec_perm; // thread t runs agent exec_perm[t] (bin order); NULL: agent t
+  const unsigned int *d_agent_offset;  // function condition: agents [0, *d_agent_offset) are disabled (NULL: 0)
   unsigned int bound;           // launch bound
   DevVars agent;                // variables of the executing agent's state list
   DevVars msg_in;               // input message list (bin-sorted for spatial messages)

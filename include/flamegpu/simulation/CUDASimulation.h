@@ -63,6 +63,19 @@ __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const 
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
+// function condition helpers: words[active] = words[count] - words[failed]; death flags of the
+// disabled front are forced to "alive"; move flags select the executing survivors for a state change
+__global__ void k_sub_word(unsigned int *dst, const unsigned int *a, const unsigned int *b) { *dst = *a - *b; }
+__global__ void k_fill_front(unsigned int *flags, const unsigned int *d_front, unsigned int bound, unsigned int value) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < bound && i < *d_front) flags[i] = value;
+}
+__global__ void k_move_flags(unsigned int *move, const unsigned int *death, const unsigned int *d_front, const unsigned int *d_n,
+                             unsigned int bound) {
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bound || i >= *d_n) return;
+  move[i] = (i >= *d_front && (!death || death[i] == 1u)) ? 1u : 0u;
+}
 __global__ void k_iota(unsigned int *dst, unsigned int n, unsigned int first) {
   const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = first + i;
@@ -193,7 +206,8 @@ struct FunctionRT {
   DevList scratch_new;  // new-agent slots, one per parent thread
   char *d_defaults = nullptr;
   std::vector<size_t> default_offsets;
-  DevFlags death_flag, msg_flag, birth_flag;
+  DevFlags death_flag, msg_flag, birth_flag, cond_flag, move_flag;
+  unsigned int failed_slot = 0, active_slot = 0;  // function condition: device words
   bool sortable = false;
   int sort_dims = 0;
   fgb_spatial *exec_binner = nullptr;  // bins the executing agents on the input list's grid

@@ -97,6 +97,8 @@ inline void CUDASimulation::initialise() {
       if (!fp->message_input.empty()) f.msg_in = &messages.at(fp->message_input);
       if (!fp->message_output.empty()) f.msg_out = &messages.at(fp->message_output);
       f.tmp_slot = alloc_slot();
+      f.failed_slot = alloc_slot();
+      f.active_slot = alloc_slot();
       if (!fp->agent_output.empty()) {
         model_has_births = true;
         f.out_agent = &agent_rt(fp->agent_output);
@@ -180,6 +182,8 @@ inline void CUDASimulation::destroy() {
       f.death_flag.release();
       f.msg_flag.release();
       f.birth_flag.release();
+      f.cond_flag.release();
+      f.move_flag.release();
       if (f.d_defaults) cudaFree(f.d_defaults);
       f.exec_perm.release();
       if (f.exec_binner) fgb_spatial_destroy(f.exec_binner);
@@ -451,6 +455,10 @@ inline void CUDASimulation::plan_step() {
       const unsigned int n = bound_of(L);
       if (n == 0) continue;
       if (f.fn->has_agent_death || f.fn->condition) f.death_flag.reserve(n);
+      if (f.fn->condition) {
+        f.cond_flag.reserve(n);
+        f.move_flag.reserve(n);
+      }
       if (f.exec_binner) {
         f.exec_perm.reserve(n);
         FGB_ABI_THROW(fgb_spatial_reserve(f.exec_binner, n));
@@ -479,7 +487,9 @@ inline void CUDASimulation::plan_step() {
         else tb += n;
         T.reserve(tb, T.capacity);
       }
-      if (f.fn->initial_state != f.fn->end_state && !(f.out_agent && &f.out_agent->states.at(f.fn->agent_output_state) == &L)) bound_of(L) = 0;
+      if (f.fn->initial_state != f.fn->end_state && !f.fn->condition &&
+          !(f.out_agent && &f.out_agent->states.at(f.fn->agent_output_state) == &L))
+        bound_of(L) = 0;
       if (f.sortable) {
         float mn[3], width[3];
         unsigned int gd[3];
@@ -518,6 +528,37 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     prof_end(st);
   }
 
+  // 1b. function condition (reference CUDASimulation.cu:686-837, CUDAFatAgent.cu:186-236): evaluate it for every
+  // agent, then partition the list stably into [failed | passed]; only the passed part executes
+  const bool conditional = fn.condition != nullptr;
+  unsigned int *d_failed = slot_ptr(f.failed_slot);
+  unsigned int *d_active = slot_ptr(f.active_slot);
+  if (conditional) {
+    prof_begin("condition:" + fn.name, st);
+    f.cond_flag.reserve(n);
+    f.move_flag.reserve(n);
+    f.death_flag.reserve(n);
+    detail::FunctionArgs c;
+    std::memset(&c, 0, sizeof(c));
+    c.d_count = d_n;
+    c.bound = n;
+    L.fill_table(c.agent);
+    c.death_flag = f.cond_flag.p;
+    c.d_step = slot_ptr(kStepSlot);
+    c.env = env_table;
+    void *cargs[] = {&c};
+    FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(fn.condition), dim3((n + 127) / 128), dim3(128), cargs, 0, st));
+    ++own_launches;
+    std::vector<fgb_var> vars = L.vars(true);
+    const unsigned int nv = static_cast<unsigned int>(vars.size());
+    FGB_ABI_THROW(fgb_compact(ctx, sid, f.cond_flag.p, /*invert=*/1, n, d_n, 0, 0, nullptr, vars.data(), nv, d_failed, nullptr, st));
+    FGB_ABI_THROW(fgb_compact(ctx, sid, f.cond_flag.p, /*invert=*/0, n, d_n, 0, 0, d_failed, vars.data(), nv, nullptr, nullptr, st));
+    L.swap_buffers();
+    detail::k_sub_word<<<1, 1, 0, st>>>(d_active, d_n, d_failed);
+    ++own_launches;
+    prof_end(st);
+  }
+
   // 2. index of the input list, built lazily before its first reader (reference :864)
   if (f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty) {
     detail::CUDAMessage &M = *f.msg_in;
@@ -537,7 +578,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   }
 
   // 2b. execution order: bin the executing agents on the input list's grid (b200 extension)
-  const bool bin_order = f.exec_binner && cuda_config.binOrderExecution;
+  const bool bin_order = f.exec_binner && cuda_config.binOrderExecution && !conditional;
   if (bin_order) {
     prof_begin("exec_order", st);
     f.exec_perm.reserve(n);
@@ -554,6 +595,9 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   std::memset(&a, 0, sizeof(a));
   a.d_count = d_n;
   a.exec_perm = bin_order ? f.exec_perm.p : nullptr;
+  a.d_agent_offset = conditional ? d_failed : nullptr;
+  // the executing agents: all of them, or the part of the list that passed the condition
+  unsigned int *d_exec = conditional ? d_active : d_n;
   a.bound = n;
   L.fill_table(a.agent);
   if (f.msg_in) {
@@ -622,17 +666,17 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     unsigned int *d_mc = slot_ptr(O.list.count_slot);
     if (fn.message_output_optional) {
       std::vector<fgb_var> vars = O.list.vars(/*from_data=*/false);  // swap (written) -> data (read list)
-      FGB_ABI_THROW(fgb_compact(ctx, sid, f.msg_flag.p, 0, n, d_n, 0, 0, O.truncate ? nullptr : d_mc, vars.data(),
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.msg_flag.p, 0, n, d_exec, 0, 0, O.truncate ? nullptr : d_mc, vars.data(),
                                 static_cast<unsigned int>(vars.size()), nullptr, d_mc, st));
       O.list.bound = (O.truncate ? 0u : O.list.bound) + n;
     } else if (O.truncate) {
       O.list.swap_buffers();
-      detail::k_copy_word<<<1, 1, 0, st>>>(d_mc, d_n);
+      detail::k_copy_word<<<1, 1, 0, st>>>(d_mc, d_exec);
       ++own_launches;
       O.list.bound = n;
     } else {
       std::vector<fgb_var> vars = O.list.vars(false);
-      FGB_ABI_THROW(fgb_compact(ctx, sid, nullptr, 0, n, d_n, n, 0, d_mc, vars.data(), static_cast<unsigned int>(vars.size()), nullptr,
+      FGB_ABI_THROW(fgb_compact(ctx, sid, nullptr, 0, n, d_exec, n, 0, d_mc, vars.data(), static_cast<unsigned int>(vars.size()), nullptr,
                                 d_mc, st));
       O.list.bound += n;
     }
@@ -644,6 +688,11 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   unsigned int *d_tmp = slot_ptr(f.tmp_slot);
   const bool births = f.out_agent != nullptr;
   detail::DevList *T = births ? &f.out_agent->states.at(fn.agent_output_state) : nullptr;
+  if (conditional && fn.has_agent_death) {
+    // disabled agents at the front are kept unconditionally (reference scatter_all_count, CUDAScatter.cu:82-83)
+    detail::k_fill_front<<<(n + 255) / 256, 256, 0, st>>>(f.death_flag.p, d_failed, n, 1u);
+    ++own_launches;
+  }
   if (same_state) {
     if (fn.has_agent_death) {
       std::vector<fgb_var> vars = L.vars(true);
@@ -661,8 +710,16 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       vars[v].out = E.data[v];
     }
     unsigned int *d_ec = slot_ptr(E.count_slot);
-    FGB_ABI_THROW(fgb_compact(ctx, sid, fn.has_agent_death ? f.death_flag.p : nullptr, 0, n, d_n, fn.has_agent_death ? 0u : n, 0, d_ec,
-                              vars.data(), static_cast<unsigned int>(vars.size()), nullptr, d_ec, st));
+    if (conditional) {
+      // only the executing survivors change state; the disabled front stays in the initial state
+      detail::k_move_flags<<<(n + 255) / 256, 256, 0, st>>>(f.move_flag.p, fn.has_agent_death ? f.death_flag.p : nullptr, d_failed, d_n, n);
+      ++own_launches;
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.move_flag.p, 0, n, d_n, 0, 0, d_ec, vars.data(), static_cast<unsigned int>(vars.size()),
+                                nullptr, d_ec, st));
+    } else {
+      FGB_ABI_THROW(fgb_compact(ctx, sid, fn.has_agent_death ? f.death_flag.p : nullptr, 0, n, d_n, fn.has_agent_death ? 0u : n, 0, d_ec,
+                                vars.data(), static_cast<unsigned int>(vars.size()), nullptr, d_ec, st));
+    }
     E.bound += n;
   }
 
@@ -679,14 +736,14 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     const unsigned int nv = static_cast<unsigned int>(vars.size());
     unsigned int *d_tc = slot_ptr(T->count_slot);
     if (T == &L && same_state) {
-      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, fn.has_agent_death ? d_tmp : d_n, vars.data(), nv, nullptr, d_n, st));
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, fn.has_agent_death ? d_tmp : d_n, vars.data(), nv, nullptr, d_n, st));
       L.bound += n;
     } else if (T == &L) {  // the initial state was vacated by the transition: children start at 0
-      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
       births_into_vacated = true;
       L.bound = n;
     } else {
-      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_n, 0, 0, d_tc, vars.data(), nv, nullptr, d_tc, st));
+      FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, d_tc, vars.data(), nv, nullptr, d_tc, st));
       T->bound += n;
       if (same_state && fn.has_agent_death) {
         detail::k_copy_word<<<1, 1, 0, st>>>(d_n, d_tmp);
@@ -695,8 +752,13 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     }
   }
   if (!same_state && !births_into_vacated) {
-    FGB_CUDA_THROW(cudaMemsetAsync(d_n, 0, 4, st));
-    L.bound = 0;
+    if (conditional) {
+      detail::k_copy_word<<<1, 1, 0, st>>>(d_n, d_failed);  // the agents that failed the condition stay
+      ++own_launches;
+    } else {
+      FGB_CUDA_THROW(cudaMemsetAsync(d_n, 0, 4, st));
+      L.bound = 0;
+    }
   }
   prof_end(st);
 }

@@ -120,6 +120,23 @@ def test_death_and_birth_vs_reference(tmp_path):
         s.close()
 
 
+def test_function_conditions_vs_reference(tmp_path):
+    # condition + death in one state: list order [disabled | executing survivors] must match the reference's
+    n = 5000
+    rng = np.random.default_rng(6)
+    x = rng.integers(0, 1000, n).astype(np.int32)
+    inp = str(tmp_path / "c.bin")
+    fgbs.write_state(inp, {"x": x})
+    fgbs.run_ref("test", {"which": 11}, inp, str(tmp_path / "refc"))
+    ref = fgbs.read_state(str(tmp_path / "refc.agent.bin"))
+    s = _sim("test", which=11)
+    s.set_population("agent", {"x": x})
+    s.step(1)
+    assert np.array_equal(s.get("agent", "_id", np.uint32), ref["_id"])
+    assert np.array_equal(s.get("agent", "x", np.int32).view(np.uint32), ref["x"])
+    s.close()
+
+
 def test_stress_step_vs_reference(tmp_path):
     n, L = 60000, 39.0
     rng = np.random.default_rng(77)

@@ -396,3 +396,43 @@ def test_iterator_radius_modes_match_reference_order_results(mode, golden_dir):
     c2 = s.get("agent", "count", np.uint32)
     assert np.array_equal(c2, e2) if mode == 1 else np.all(c2 <= e2)
     s.close()
+
+
+def test_reference_function_condition_split():
+    # TestAgentFunctionConditions.SplitAgents (test_agent_function_conditions.cu:48-105)
+    n = 1000
+    x = (np.arange(2 * n) % 2).astype(np.int32)
+    y = np.tile(np.array([13, 14, 15, 16], np.int32), (2 * n, 1))
+    s = _sim("test", which=10)
+    s.set_population("agent", {"x": x, "y": y}, state="Start")
+    s.step(1)
+    assert s.count("agent", "Start") == 0 and s.count("agent", "End") == n and s.count("agent", "End2") == n
+    assert np.all(s.get("agent", "x", np.int32, state="End") == 2)
+    assert np.all(s.get("agent", "y", np.int32, 4, state="End") == [3, 4, 5, 6])
+    assert np.all(s.get("agent", "x", np.int32, state="End2") == -1)
+    assert np.all(s.get("agent", "y", np.int32, 4, state="End2") == [23, 24, 25, 26])
+    # ids keep the original relative order inside each destination state
+    ids = np.arange(1, 2 * n + 1, dtype=np.uint32)
+    assert np.array_equal(s.get("agent", "_id", np.uint32, state="End"), ids[x == 1])
+    assert np.array_equal(s.get("agent", "_id", np.uint32, state="End2"), ids[x != 1])
+    s.close()
+
+
+def test_function_condition_with_death_same_state():
+    n = 5000
+    rng = np.random.default_rng(6)
+    x = rng.integers(0, 1000, n).astype(np.int32)
+    s = _sim("test", which=11)
+    s.set_population("agent", {"x": x})
+    s.step(1)
+    ids = np.arange(1, n + 1, dtype=np.uint32)
+    passed = x % 3 == 0
+    keep = passed & (x % 2 != 0)
+    exp_ids = np.concatenate([ids[~passed], ids[keep]])       # disabled agents first, then the executing survivors
+    exp_x = np.concatenate([x[~passed], x[keep] + 1000])
+    assert np.array_equal(s.get("agent", "_id", np.uint32), exp_ids)
+    assert np.array_equal(s.get("agent", "x", np.int32), exp_x)
+    # AllDisabled (:107-140): a second step where nothing passes must leave the list intact
+    s.step(1)
+    assert s.count("agent") > 0
+    s.close()
