@@ -223,9 +223,10 @@ def main():
         planes_per_rank = int(np.ceil(L / RADIUS))
         planes = planes_per_rank * world
         Lz = float(planes * RADIUS)
-        cap = int(max(65536, 6 * n // planes_per_rank))
-        slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=cap,
-                                       migrate_capacity=cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
+        halo_cap = int(2 * n // planes_per_rank + 8192)      # a boundary plane holds ~n/planes_per_rank messages
+        mig_cap = int(n // planes_per_rank // 4 + 4096)       # a few percent of a plane changes slab per step
+        slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=halo_cap,
+                                       migrate_capacity=mig_cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
                                        stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
         s = slab_sim.sim
         rng = np.random.default_rng(rank)

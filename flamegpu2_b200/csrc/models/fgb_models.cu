@@ -193,6 +193,9 @@ int fgbm_run_layers(void *h, unsigned int first, unsigned int last) {
 int fgbm_end_step(void *h) {
   return guarded([&] { static_cast<Sim *>(h)->sim->endStep(); });
 }
+int fgbm_end_step_pipelined(void *h) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->endStepPipelined(); });
+}
 int fgbm_refresh_bounds(void *h) {
   return guarded([&] { static_cast<Sim *>(h)->sim->refreshBounds(); });
 }

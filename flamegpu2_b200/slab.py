@@ -12,7 +12,8 @@ One process per GPU (torch.distributed, NCCL over NVLink).  Rank r owns the bin 
                                                   identical to the single-GPU build)
   migration: agents whose new plane left [z0, z1) are packed, removed, sent to the neighbour and appended
 
-Nothing returns to the host inside a step except one count refresh at its end.
+Nothing returns to the host inside a step; the launch bounds are tightened from the counts of the previous
+step, read back asynchronously (CUDASimulation::endStepPipelined).
 """
 from __future__ import annotations
 
@@ -117,6 +118,7 @@ class SlabSimulation:
         L.fgbm_run_layers.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
         L.fgbm_end_step.argtypes = [C.c_void_p]
         L.fgbm_refresh_bounds.argtypes = [C.c_void_p]
+        L.fgbm_end_step_pipelined.argtypes = [C.c_void_p]
         L.fgbm_list_layout.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
         L.fgbm_slab_pack.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_uint, C.c_int, C.c_void_p]
@@ -156,8 +158,9 @@ class SlabSimulation:
         self._check(self.lib.fgbm_run_layers(s.h, *self.read_layers), "fgbm_run_layers")
         # migration: agents now below z0 go down, at or above z1 go up
         self._exchange(False, self.agent, self.agent_buf, self.z0, self.z1, remove=True)
-        self._check(self.lib.fgbm_end_step(s.h), "fgbm_end_step")
-        self._check(self.lib.fgbm_refresh_bounds(s.h), "fgbm_refresh_bounds")  # the one host sync of the step
+        # end of step + pipelined count refresh: the host consumes the counts of the PREVIOUS step while the
+        # device runs this one, so it never drains the GPU
+        self._check(self.lib.fgbm_end_step_pipelined(s.h), "fgbm_end_step_pipelined")
 
     def check_overflow(self):
         """Counts that exceeded the staging capacity mean lost items: fail loudly."""

@@ -90,6 +90,7 @@ struct DevList {
   unsigned int capacity = 0;
   unsigned int bound = 0;       // host-known upper bound of the device count
   unsigned int count_slot = 0;  // control-block slot of the device count
+  unsigned int appended_this_step = 0;  // upper bound of what listAppend added since the last endStep
   bool double_buffered = true;
 
   void init(const VariableMap &vars, bool dbl) {
@@ -343,6 +344,9 @@ class CUDASimulation {
                   const unsigned int *d_n, const void *const *src);
   // re-read every list count from the device (one sync) and tighten the host-side launch bounds
   void refreshBounds() { initialise(); refresh_bounds(); }
+  // Pipelined variant for the slab driver: the counts of step t are copied to pinned memory asynchronously and
+  // consumed one step later, while the GPU is already running step t+1, so the host never drains the device.
+  void endStepPipelined();
   std::vector<std::pair<std::string, size_t>> listLayout(bool is_message, const std::string &name);
 
   // ---- b200 extensions used by the parity harness / bench (no reference counterpart) -------------
@@ -440,6 +444,9 @@ class CUDASimulation {
   std::map<std::string, detail::CUDAMessage> messages;
   std::map<std::string, std::pair<int, int>> windows;
   detail::DevFlags slab_flags[3];
+  unsigned int *h_ctrl_pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ctrl_events[2] = {nullptr, nullptr};
+  unsigned long long pipelined_steps = 0;
   std::vector<std::vector<detail::FunctionRT>> layers;  // [layer][function]
   bool model_has_births = false;
   bool model_has_host_layers = false;

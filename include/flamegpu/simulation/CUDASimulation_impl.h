@@ -195,6 +195,10 @@ inline void CUDASimulation::destroy() {
     if (m.second.spatial) fgb_spatial_destroy(m.second.spatial);
   }
   for (auto &f : slab_flags) f.release();
+  for (int i = 0; i < 2; ++i) {
+    if (h_ctrl_pinned[i]) cudaFreeHost(h_ctrl_pinned[i]);
+    if (ctrl_events[i]) cudaEventDestroy(ctrl_events[i]);
+  }
   if (d_env) cudaFree(d_env);
   if (d_zero_slots) cudaFree(d_zero_slots);
   if (d_ctrl) cudaFree(d_ctrl);
@@ -819,6 +823,36 @@ inline void CUDASimulation::endStep() {
   if (model_has_births) refresh_bounds();
 }
 
+inline void CUDASimulation::endStepPipelined() {
+  record_end_of_step(main_stream);
+  ++step_count;
+  if (!h_ctrl_pinned[0]) {
+    for (int i = 0; i < 2; ++i) {
+      FGB_CUDA_THROW(cudaMallocHost(&h_ctrl_pinned[i], kCtrlWords * 4));
+      FGB_CUDA_THROW(cudaEventCreateWithFlags(&ctrl_events[i], cudaEventDisableTiming));
+    }
+  }
+  const int cur = static_cast<int>(pipelined_steps & 1ull), prev = cur ^ 1;
+  FGB_CUDA_THROW(cudaMemcpyAsync(h_ctrl_pinned[cur], d_ctrl, next_slot * 4, cudaMemcpyDeviceToHost, main_stream));
+  FGB_CUDA_THROW(cudaEventRecord(ctrl_events[cur], main_stream));
+  if (pipelined_steps > 0) {
+    // counts as of the end of the PREVIOUS step (complete long ago: the device is busy with this step)
+    FGB_CUDA_THROW(cudaEventSynchronize(ctrl_events[prev]));
+    const unsigned int *h = h_ctrl_pinned[prev];
+    for (auto &a : agents)
+      for (auto &s : a.second.states) {
+        detail::DevList &l = s.second;
+        // everything appended since that snapshot is covered by appended_this_step (this step's appends)
+        l.bound = std::min(l.capacity, h[l.count_slot] + l.appended_this_step);
+        l.bound = std::max(l.bound, 1u);
+      }
+  }
+  for (auto &a : agents)
+    for (auto &s : a.second.states) s.second.appended_this_step = 0;
+  for (auto &m : messages) m.second.list.appended_this_step = 0;
+  ++pipelined_steps;
+}
+
 inline std::vector<std::pair<std::string, size_t>> CUDASimulation::listLayout(bool is_message, const std::string &name) {
   initialise();
   detail::DevList &l = is_message ? messages.at(name).list : state_list(name, agent_rt(name).desc->initial_state);
@@ -888,6 +922,7 @@ inline void CUDASimulation::listAppend(bool is_message, const std::string &name,
   FGB_ABI_THROW(fgb_compact(ctx, 0, nullptr, 0, n_max, d_n_src, n_max, 0, d_n, vars.data(), static_cast<unsigned int>(vars.size()),
                             nullptr, d_n, main_stream));
   l.bound += n_max;
+  l.appended_this_step += n_max;
   if (is_message) messages.at(name).pbm_dirty = true;
 }
 
