@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda / e2e legs")
     ap.add_argument("--stable", type=int, default=0)
     ap.add_argument("--true3d-sort", type=int, default=0)
-    ap.add_argument("--iter-mode", type=int, default=0, help="0 reference visit order (default), 1 radius-first, 2 radius-only")
+    ap.add_argument("--iter-mode", type=int, default=0, help="0 reference visit order (default), 1 radius-filtered lock-step walk (opt-in)")
     ap.add_argument("--bin-order", type=int, default=1, help="run message-reading functions in bin order (b200 extension)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

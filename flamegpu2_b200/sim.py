@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfgb_models.so")
+LIB_PATH = os.environ.get("FGB_MODELS_LIB") or os.path.join(_HERE, "lib", "libfgb_models.so")  # override: A/B builds
 
 _lib = None
 

@@ -101,6 +101,7 @@ struct MessageData {
 struct AgentFunctionData {
   std::string name;
   AgentFunctionWrapper *func = nullptr;
+  AgentFunctionWrapper *func_filtered = nullptr;  // b200: radius-filtered iterator variant (== func for non-spatial input)
   AgentFunctionConditionWrapper *condition = nullptr;
   std::type_index in_type = std::type_index(typeid(void));
   std::type_index out_type = std::type_index(typeid(void));
@@ -335,6 +336,7 @@ class AgentDescription {
     auto f = std::make_shared<AgentFunctionData>();
     f->name = function_name;
     f->func = AgentFunction::fnPtr();
+    f->func_filtered = AgentFunction::fnPtrFiltered();
     f->in_type = AgentFunction::inType();
     f->out_type = AgentFunction::outType();
     f->initial_state = agent->initial_state;

@@ -21,7 +21,9 @@ typedef void(AgentFunctionWrapper)(const detail::FunctionArgs);
 typedef void(AgentFunctionConditionWrapper)(const detail::FunctionArgs);
 
 #if defined(__CUDACC__)
-template <typename AgentFunction, typename MessageIn, typename MessageOut>
+// ITER_MODE: spatial iterator variant compiled into this instance (0 reference visit order, 1 radius-filtered
+// lock-step walk); it reaches the iterator as a constant, so each instance contains one variant only
+template <typename AgentFunction, typename MessageIn, typename MessageOut, int ITER_MODE = 0>
 __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionArgs args) {
   const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int n = args.bound;
@@ -38,7 +40,7 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
   // flags, message and new-agent slots) is addressed by the AGENT index, so results do not change.
   const unsigned int agent = args.exec_perm ? __ldg(args.exec_perm + index) : offset + index;
   const unsigned int slot = agent - offset;  // message / new-agent slot: index among the executing agents
-  DeviceAPI<MessageIn, MessageOut> api(args, agent, slot);
+  DeviceAPI<MessageIn, MessageOut> api(args, agent, slot, ITER_MODE);
   const AGENT_STATUS status = AgentFunction()(&api);
   // one flag store per thread, no memset beforehand (reference AgentFunction.cuh:111-119 +
   // CUDAScanCompaction::zero_async)
@@ -72,6 +74,9 @@ __global__ void agent_function_condition_wrapper(const __grid_constant__ detail:
         flamegpu::DeviceAPI<message_in, message_out> *FLAMEGPU) const;                                                  \
     static constexpr flamegpu::AgentFunctionWrapper *fnPtr() {                                                          \
       return &flamegpu::agent_function_wrapper<funcName##_impl, message_in, message_out>;                               \
+    }                                                                                                                   \
+    static constexpr flamegpu::AgentFunctionWrapper *fnPtrFiltered() {                                                  \
+      return &flamegpu::agent_function_wrapper<funcName##_impl, message_in, message_out, message_in::SPATIAL ? 1 : 0>;  \
     }                                                                                                                   \
     static std::type_index inType() { return std::type_index(typeid(message_in)); }                                     \
     static std::type_index outType() { return std::type_index(typeid(message_out)); }                                   \

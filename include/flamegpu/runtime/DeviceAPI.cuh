@@ -115,8 +115,8 @@ class DeviceAPI {
     mutable id_t id;
   };
 
-  __device__ __forceinline__ DeviceAPI(const detail::FunctionArgs &args, unsigned int idx, unsigned int slot)
-      : message_in(args), message_out(args, slot), agent_out(args, slot), environment(args), a(args), index(idx) {}
+  __device__ __forceinline__ DeviceAPI(const detail::FunctionArgs &args, unsigned int idx, unsigned int slot, int iter_mode = 0)
+      : message_in(args, iter_mode), message_out(args, slot), agent_out(args, slot), environment(args), a(args), index(idx) {}
 
   template <typename T, unsigned int N>
   __device__ __forceinline__ T getVariable(const char (&name)[N]) const {

@@ -8,6 +8,8 @@
 #define FGB_INCLUDE_FLAMEGPU_RUNTIME_DETAIL_FUNCTIONARGS_H_
 
 #include <cstdint>
+#include <limits>
+#include <type_traits>
 
 #include "flamegpu/defines.h"
 #include "flamegpu/detail/hash.h"
@@ -39,10 +41,10 @@ struct SpatialMeta {
   int win_begin;        // slab window on the slowest axis: first plane stored locally
   int win_count;        // ... and how many (== grid_dim[slowest] on a single GPU)
   int wrap_compatible;
-  // b200 iterator modes (0 = reference order, every message of the Moore neighbourhood in strip order):
-  //  1 = radius-first: the same messages, each exactly once, but those within the radius of the search
-  //      origin first (in strip order), then the rest (in strip order);
-  //  2 = radius-only: only messages within the radius (a superset of what `sqrtf(d2) < radius` accepts).
+  // b200 iterator modes: 0 = reference order, every message of the Moore neighbourhood in strip order;
+  //  1 = radius-filtered: only messages within the radius of the search origin (a superset of what
+  //      `sqrtf(d2) < radius` accepts), in the same relative order; the lanes of a warp walk in lock-step
+  //      and queue their accepted messages in shared memory (MessageSpatial3D.cuh advance_filtered).
   int iter_mode;
   float radius2_eps;   // radius^2 * (1 + 1e-5): conservative in-radius test of the iterator
   const unsigned int *pbm;
@@ -115,8 +117,97 @@ FGB_HD LocPtrs make_loc(const FunctionArgs &a) {
   l.x = a.msg_in.ptr[(kHashX * a.msg_in.salt) >> (32 - kSlotBits)];
   l.y = a.msg_in.ptr[(kHashY * a.msg_in.salt) >> (32 - kSlotBits)];
   l.z = a.msg_in.ptr[(kHashZ * a.msg_in.salt) >> (32 - kSlotBits)];  // 2D lists: an empty slot, never read
+#if defined(__CUDA_ARCH__)
+  // keep the three pointers in registers: without this the compiler re-derives them (hash * salt, shift, indexed
+  // constant load) inside the message loop, ~10 instructions per message
+  asm("" : "+l"(l.x), "+l"(l.y), "+l"(l.z));
+#endif
   return l;
 }
+
+// Radius-filtered iterator (MessageSpatial2D/3D::In::Filter, ITER_MODE 1).  Each lane walks its strips in chunks
+// of up to 32 consecutive messages and keeps, per chunk with at least one message within the radius, the pair
+// {first message index, accepted bit mask} in dynamic shared memory: word w of thread t at [w * blockDim.x + t]
+// (conflict free).  The scheduler launches with kFilterQueueWords * blockDim.x words.
+constexpr unsigned int kFilterChunks = 16;                    // queued chunks per lane (up to 512 accepted messages)
+constexpr unsigned int kFilterQueueWords = 2 * kFilterChunks;
+// location of the padding message a lane is shown while other lanes of its warp still have accepted messages:
+// far outside any environment, finite so that distance arithmetic on it stays on the fast paths
+template <typename T>
+FGB_HD T pad_location() {
+  if constexpr (std::is_floating_point<T>::value) {
+    return static_cast<T>(1.0e18f);
+  } else {
+    return T{};
+  }
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t *filter_queue() {
+  extern __shared__ uint32_t fgb_filter_queue_smem[];
+  return fgb_filter_queue_smem;
+}
+// packed fp32x2 arithmetic of sm_100 (two messages per instruction)
+__device__ __forceinline__ unsigned long long f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// bit k of the result: message i0+k (k < n <= 32) lies within sqrt(r2) of (ox,oy,oz).  The location arrays are
+// 8-byte aligned at even indices (one cudaMalloc per variable), so pairs of messages are fetched with one 64-bit load.
+template <int DIMS>
+__device__ __forceinline__ uint32_t radius_mask(const float *__restrict__ x, const float *__restrict__ y,
+                                                const float *__restrict__ z, int i0, int n, float ox, float oy, float oz,
+                                                float r2) {
+  auto one = [&](int j) {
+    const float dx = __ldg(x + j) - ox, dy = __ldg(y + j) - oy;
+    float d2 = dx * dx + dy * dy;
+    if (DIMS == 3) {
+      const float dz = __ldg(z + j) - oz;
+      d2 += dz * dz;
+    }
+    return d2 <= r2;
+  };
+  if (n <= 0) return 0u;
+  uint32_t m = 0;  // filled from the top: after c messages they occupy bits [32-c, 32)
+  int i = 0;
+  if (i0 & 1) {
+    m = one(i0) ? 0x80000000u : 0u;
+    i = 1;
+  }
+  const unsigned long long OX = f32x2(ox, ox), OY = f32x2(oy, oy), OZ = f32x2(oz, oz);
+#pragma unroll 2
+  for (; i + 2 <= n; i += 2) {
+    const unsigned long long X = __ldg(reinterpret_cast<const unsigned long long *>(x + i0 + i));
+    const unsigned long long Y = __ldg(reinterpret_cast<const unsigned long long *>(y + i0 + i));
+    const unsigned long long dx = f32x2_sub(X, OX), dy = f32x2_sub(Y, OY);
+    unsigned long long d = f32x2_fma(dy, dy, f32x2_mul(dx, dx));
+    if (DIMS == 3) {
+      const unsigned long long Z = __ldg(reinterpret_cast<const unsigned long long *>(z + i0 + i));
+      const unsigned long long dz = f32x2_sub(Z, OZ);
+      d = f32x2_fma(dz, dz, d);
+    }
+    const float d0 = __uint_as_float(static_cast<uint32_t>(d)), d1 = __uint_as_float(static_cast<uint32_t>(d >> 32));
+    m = (m >> 2) | (d0 <= r2 ? 0x40000000u : 0u) | (d1 <= r2 ? 0x80000000u : 0u);
+  }
+  if (i < n) m = (m >> 1) | (one(i0 + i) ? 0x80000000u : 0u);
+  return m >> (32 - n);
+}
+#endif
 
 // host: choose a salt that makes the table collision free and fill hash[]; returns false if none found
 template <typename Table>

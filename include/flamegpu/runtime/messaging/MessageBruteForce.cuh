@@ -44,7 +44,7 @@ class MessageBruteForce {
         return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
       }
     };
-    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args) : a(args) {}
+    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args, int = 0) : a(args) {}
     __device__ __forceinline__ unsigned int size() const { return a.d_msg_in_count ? __ldg(a.d_msg_in_count) : 0u; }
     __device__ __forceinline__ Message begin() const { return Message(a, 0); }
     __device__ __forceinline__ Message end() const { return Message(a, size()); }

@@ -15,7 +15,7 @@ class MessageNone {
 #if defined(__CUDACC__)
   class In {
    public:
-    __device__ __forceinline__ explicit In(const detail::FunctionArgs &) {}
+    __device__ __forceinline__ explicit In(const detail::FunctionArgs &, int = 0) {}
   };
   class Out {
    public:

@@ -49,9 +49,14 @@ class MessageSpatial2D {
         const detail::LocPtrs loc;
         float ox, oy;
         int cx, cy;
-        int strip;  // 0..2, 3 == end
+        int strip;  // 0..2, 3 == all strips walked, 4 == end (radius-filtered mode)
         int idx, idx_end, nxt, nxt_end;
-        int phase;
+        int sidx;   // radius-filtered mode, see MessageSpatial3D.cuh
+        int cbase;          // chunk being handed out: first message index, remaining accepted bits
+        unsigned int cmask;
+        unsigned int qpos, qcount, lanes;
+        const int mode;  // compile-time constant after inlining (agent_function_wrapper<..., ITER_MODE>)
+        bool pad;   // this lane is waiting for the others: its current message is a padding message at infinity
         __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
           b = 0;
           e = 0;
@@ -75,60 +80,101 @@ class MessageSpatial2D {
             fetch(strip + 1, nxt, nxt_end);
           } while (idx >= idx_end && strip < 3);
         }
-        __device__ __forceinline__ void restart() {
-          strip = -1;
-          fetch(0, nxt, nxt_end);
-          next_strip();
-        }
-        __device__ __forceinline__ bool in_radius() const {
-          const float dx = __ldg(reinterpret_cast<const float *>(loc.x) + idx) - ox;
-          const float dy = __ldg(reinterpret_cast<const float *>(loc.y) + idx) - oy;
-          return dx * dx + dy * dy <= a.in_meta.radius2_eps;
-        }
-        __device__ __forceinline__ void settle() {
+        // lock-step walk + per-lane queue, same scheme as MessageSpatial3D::In::Filter::Message::advance_filtered
+        __device__ __forceinline__ void advance_filtered() {
+          uint32_t *q = detail::filter_queue() + threadIdx.x;
+          const unsigned int stride = blockDim.x;
           for (;;) {
-            if (strip >= 3) {
-              if (a.in_meta.iter_mode == 1 && phase == 0) {
-                phase = 1;
-                restart();
-                continue;
+            // Every lane takes the same path through this function (all decisions are warp votes), so the warp
+            // stays converged.  While any lane still has accepted messages, every lane returns to the agent
+            // function: lanes that have none left are given a padding message far outside the environment.
+            if (cmask == 0u && qpos < qcount) {
+              cbase = static_cast<int>(q[(2u * qpos) * stride]);
+              cmask = q[(2u * qpos + 1u) * stride];
+              ++qpos;
+            }
+            if (__any_sync(lanes, cmask != 0u)) {
+              pad = cmask == 0u;
+              if (!pad) {
+                idx = cbase + (__ffs(static_cast<int>(cmask)) - 1);
+                cmask &= cmask - 1u;
               }
               return;
             }
-            if (in_radius() == (phase == 0)) return;
-            if (++idx >= idx_end) next_strip();
+            qpos = 0;
+            qcount = 0;
+            if (__all_sync(lanes, strip >= 3)) {
+              strip = 4;
+              return;
+            }
+            // walk: one chunk of the current strip per round, until a queue is full or every lane has walked all strips
+            for (;;) {
+              const bool walked = strip >= 3;
+              const unsigned int full = __ballot_sync(lanes, !walked && qcount >= detail::kFilterChunks);
+              const unsigned int done = __ballot_sync(lanes, walked);
+              if (full != 0u || done == lanes) break;
+              if (!walked) {
+                const int n = idx_end - sidx < 32 ? idx_end - sidx : 32;
+                const uint32_t m = detail::radius_mask<2>(reinterpret_cast<const float *>(loc.x), reinterpret_cast<const float *>(loc.y),
+                                                          nullptr, sidx, n, ox, oy, 0.f, a.in_meta.radius2_eps);
+                if (m) {
+                  q[(2u * qcount) * stride] = static_cast<uint32_t>(sidx);
+                  q[(2u * qcount + 1u) * stride] = m;
+                  ++qcount;
+                }
+                sidx += n;
+                if (sidx >= idx_end) {
+                  next_strip();
+                  sidx = idx;
+                }
+              }
+            }
           }
+        }
+        template <typename T>
+        __device__ __forceinline__ T location(const char *base) const {
+          const T v = __ldg(reinterpret_cast<const T *>(base) + idx);
+          return pad ? detail::pad_location<T>() : v;
         }
 
        public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin)
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin, int _mode = 0)
             : a(args), loc(detail::make_loc(args)), ox(x), oy(y), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0),
-              phase(0) {
+              sidx(0), cbase(0), cmask(0), qpos(0), qcount(0), lanes(0), pad(false), mode(_mode) {
           if (begin) {
-            restart();
-            if (a.in_meta.iter_mode != 0) settle();
+            strip = -1;
+            fetch(0, nxt, nxt_end);
+            next_strip();
+            if (mode != 0) {
+              lanes = __activemask();
+              sidx = idx;
+              advance_filtered();
+            }
           }
         }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return strip < 3; }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return strip < (mode != 0 ? 4 : 3); }
         __device__ __forceinline__ bool operator==(const Message &rhs) const { return strip == rhs.strip && idx == rhs.idx; }
         __device__ __forceinline__ Message &operator++() {
-          if (++idx >= idx_end) next_strip();
-          if (a.in_meta.iter_mode != 0) settle();
+          if (mode != 0) {
+            advance_filtered();
+          } else if (++idx >= idx_end) {
+            next_strip();
+          }
           return *this;
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
           const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
-          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
-          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          if (h == detail::kHashX) return location<T>(loc.x);
+          if (h == detail::kHashY) return location<T>(loc.y);
           const int s = detail::find_slot(a.msg_in, h);
-          if (s < 0) return T{};
+          if (s < 0 || pad) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }
         template <typename T, flamegpu::size_type N, unsigned int M>
         __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
           const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
-          if (s < 0 || index >= N) return T{};
+          if (s < 0 || index >= N || pad) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
         }
         __device__ __forceinline__ unsigned int getIndex() const { return static_cast<unsigned int>(idx); }
@@ -137,8 +183,8 @@ class MessageSpatial2D {
         Message m;
 
        public:
-        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, int cx, int cy, bool begin)
-            : m(args, x, y, cx, cy, begin) {}
+        __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, int cx, int cy, bool begin, int mode)
+            : m(args, x, y, cx, cy, begin, mode) {}
         __device__ __forceinline__ iterator &operator++() {
           ++m;
           return *this;
@@ -148,17 +194,18 @@ class MessageSpatial2D {
         __device__ __forceinline__ Message &operator*() { return m; }
         __device__ __forceinline__ Message *operator->() { return &m; }
       };
-      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y) : a(args), lx(x), ly(y) {
+      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, int _mode) : a(args), lx(x), ly(y), mode(_mode) {
         cx = detail::grid_cell(args.in_meta, 0, x);
         cy = detail::grid_cell(args.in_meta, 1, y) - args.in_meta.win_begin;  // row index inside the slab window
       }
-      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, cx, cy, true); }
-      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, cx, cy, false); }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, cx, cy, true, mode); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, cx, cy, false, mode); }
 
      private:
       const detail::FunctionArgs &a;
       float lx, ly;
       int cx, cy;
+      int mode;
     };
 
     class WrapFilter {
@@ -259,13 +306,14 @@ class MessageSpatial2D {
       int cx, cy;
     };
 
-    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args) : a(args) {}
-    __device__ __forceinline__ Filter operator()(float x, float y) const { return Filter(a, x, y); }
+    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args, int _mode = 0) : a(args), mode(_mode) {}
+    __device__ __forceinline__ Filter operator()(float x, float y) const { return Filter(a, x, y, mode); }
     __device__ __forceinline__ WrapFilter wrap(float x, float y) const { return WrapFilter(a, x, y); }
     __device__ __forceinline__ float radius() const { return a.in_meta.radius; }
 
    private:
     const detail::FunctionArgs &a;
+    const int mode;
   };
 
   class Out : public MessageBruteForce::Out {

@@ -50,12 +50,18 @@ class MessageSpatial3D {
       class Message {
         const detail::FunctionArgs &a;
         const detail::LocPtrs loc;
-        float ox, oy, oz;   // search origin (used by the radius modes only)
+        float ox, oy, oz;   // search origin (radius-filtered mode only)
         int cx, cy, cz;
-        int strip;          // 0..8 current strip, 9 == end
-        int idx, idx_end;   // current message, one past the last message of the strip
+        int strip;          // 0..8 current strip, 9 == all strips walked, 10 == end (radius-filtered mode)
+        int idx, idx_end;   // message presented to the agent function, one past the last message of the strip
         int nxt, nxt_end;   // prefetched bounds of strip+1
-        int phase;          // radius-first mode: 0 = in-radius pass, 1 = the rest
+        // radius-filtered mode: scan cursor, this lane's queue of accepted messages, lanes that walk together
+        int sidx;
+        int cbase;          // chunk being handed out: first message index, remaining accepted bits
+        unsigned int cmask;
+        unsigned int qpos, qcount, lanes;
+        const int mode;  // compile-time constant after inlining (agent_function_wrapper<..., ITER_MODE>)
+        bool pad;   // this lane is waiting for the others: its current message is a padding message at infinity
 
         // [PBM[hash(cx-1,y,z)], PBM[hash(cx+1,y,z)+1]) of strip s; empty if outside the grid
         __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
@@ -81,67 +87,110 @@ class MessageSpatial3D {
             fetch(strip + 1, nxt, nxt_end);
           } while (idx >= idx_end && strip < 9);
         }
-        __device__ __forceinline__ void restart() {
-          strip = -1;
-          fetch(0, nxt, nxt_end);
-          next_strip();
-        }
-        // conservative superset of the user's usual `sqrtf(dx*dx+dy*dy+dz*dz) < radius`
-        __device__ __forceinline__ bool in_radius() const {
-          const float dx = __ldg(reinterpret_cast<const float *>(loc.x) + idx) - ox;
-          const float dy = __ldg(reinterpret_cast<const float *>(loc.y) + idx) - oy;
-          const float dz = __ldg(reinterpret_cast<const float *>(loc.z) + idx) - oz;
-          return dx * dx + dy * dy + dz * dz <= a.in_meta.radius2_eps;
-        }
-        // radius modes: move on until the current message belongs to the current pass
-        __device__ __forceinline__ void settle() {
+        // Radius-filtered mode: the lanes of a warp walk their strips TOGETHER, each testing
+        // its own messages against the radius and queueing the accepted ones in shared memory; only when a
+        // queue is full (or every lane has walked all strips) do the lanes return to the agent function, once
+        // per queued message.  The expensive in-radius branch of the user code then runs max-over-lanes(#accepted)
+        // times per warp instead of once per message of the neighbourhood.
+        __device__ __forceinline__ void advance_filtered() {
+          uint32_t *q = detail::filter_queue() + threadIdx.x;
+          const unsigned int stride = blockDim.x;
           for (;;) {
-            if (strip >= 9) {
-              if (a.in_meta.iter_mode == 1 && phase == 0) {
-                phase = 1;
-                restart();
-                continue;
+            // Every lane takes the same path through this function (all decisions are warp votes), so the warp
+            // stays converged.  While any lane still has accepted messages, every lane returns to the agent
+            // function: lanes that have none left are given a padding message far outside the environment.
+            if (cmask == 0u && qpos < qcount) {
+              cbase = static_cast<int>(q[(2u * qpos) * stride]);
+              cmask = q[(2u * qpos + 1u) * stride];
+              ++qpos;
+            }
+            if (__any_sync(lanes, cmask != 0u)) {
+              pad = cmask == 0u;
+              if (!pad) {
+                idx = cbase + (__ffs(static_cast<int>(cmask)) - 1);
+                cmask &= cmask - 1u;
               }
               return;
             }
-            if (in_radius() == (phase == 0)) return;
-            if (++idx >= idx_end) next_strip();
+            qpos = 0;
+            qcount = 0;
+            if (__all_sync(lanes, strip >= 9)) {
+              strip = 10;
+              return;
+            }
+            // walk: one chunk of the current strip per round, until a queue is full or every lane has walked all strips
+            for (;;) {
+              const bool walked = strip >= 9;
+              const unsigned int full = __ballot_sync(lanes, !walked && qcount >= detail::kFilterChunks);
+              const unsigned int done = __ballot_sync(lanes, walked);
+              if (full != 0u || done == lanes) break;
+              if (!walked) {
+                const int n = idx_end - sidx < 32 ? idx_end - sidx : 32;
+                const uint32_t m = detail::radius_mask<3>(reinterpret_cast<const float *>(loc.x), reinterpret_cast<const float *>(loc.y),
+                                                          reinterpret_cast<const float *>(loc.z), sidx, n, ox, oy, oz, a.in_meta.radius2_eps);
+                if (m) {
+                  q[(2u * qcount) * stride] = static_cast<uint32_t>(sidx);
+                  q[(2u * qcount + 1u) * stride] = m;
+                  ++qcount;
+                }
+                sidx += n;
+                if (sidx >= idx_end) {
+                  next_strip();
+                  sidx = idx;
+                }
+              }
+            }
           }
+        }
+        template <typename T>
+        __device__ __forceinline__ T location(const char *base) const {
+          const T v = __ldg(reinterpret_cast<const T *>(base) + idx);
+          return pad ? detail::pad_location<T>() : v;
         }
 
        public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, float z, int _cx, int _cy, int _cz,
-                                           bool begin)
+        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, float z, int _cx, int _cy, int _cz, bool begin, int _mode = 0)
             : a(args), loc(detail::make_loc(args)), ox(x), oy(y), oz(z), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0),
-              nxt(0), nxt_end(0), phase(0) {
+              nxt(0), nxt_end(0), sidx(0), cbase(0), cmask(0), qpos(0), qcount(0), lanes(0), pad(false), mode(_mode) {
           if (begin) {
-            restart();
-            if (a.in_meta.iter_mode != 0) settle();
+            strip = -1;
+            fetch(0, nxt, nxt_end);
+            next_strip();
+            if (mode != 0) {
+              lanes = __activemask();
+              sidx = idx;
+              advance_filtered();
+            }
           }
         }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return strip < 9; }
+        __device__ __forceinline__ bool operator!=(const Message &) const {
+          return strip < (mode != 0 ? 10 : 9);
+        }
         __device__ __forceinline__ bool operator==(const Message &rhs) const {
           return strip == rhs.strip && idx == rhs.idx;
         }
         __device__ __forceinline__ Message &operator++() {
-          if (++idx >= idx_end) next_strip();
-          if (a.in_meta.iter_mode != 0) settle();
+          if (mode != 0) {
+            advance_filtered();
+          } else if (++idx >= idx_end) {
+            next_strip();
+          }
           return *this;
         }
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
           const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
-          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
-          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
-          if (h == detail::kHashZ) return __ldg(reinterpret_cast<const T *>(loc.z) + idx);
+          if (h == detail::kHashX) return location<T>(loc.x);
+          if (h == detail::kHashY) return location<T>(loc.y);
+          if (h == detail::kHashZ) return location<T>(loc.z);
           const int s = detail::find_slot(a.msg_in, h);
-          if (s < 0) return T{};
+          if (s < 0 || pad) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
         }
         template <typename T, flamegpu::size_type N, unsigned int M>
         __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
           const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
-          if (s < 0 || index >= N) return T{};
+          if (s < 0 || index >= N || pad) return T{};
           return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
         }
         __device__ __forceinline__ unsigned int getIndex() const { return static_cast<unsigned int>(idx); }
@@ -151,8 +200,8 @@ class MessageSpatial3D {
 
        public:
         __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, float z, int cx, int cy, int cz,
-                                            bool begin)
-            : m(args, x, y, z, cx, cy, cz, begin) {}
+                                            bool begin, int mode)
+            : m(args, x, y, z, cx, cy, cz, begin, mode) {}
         __device__ __forceinline__ iterator &operator++() {
           ++m;
           return *this;
@@ -162,19 +211,20 @@ class MessageSpatial3D {
         __device__ __forceinline__ Message &operator*() { return m; }
         __device__ __forceinline__ Message *operator->() { return &m; }
       };
-      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, float z)
-          : a(args), lx(x), ly(y), lz(z) {
+      __device__ __forceinline__ Filter(const detail::FunctionArgs &args, float x, float y, float z, int _mode)
+          : a(args), lx(x), ly(y), lz(z), mode(_mode) {
         cx = detail::grid_cell(args.in_meta, 0, x);
         cy = detail::grid_cell(args.in_meta, 1, y);
         cz = detail::grid_cell(args.in_meta, 2, z) - args.in_meta.win_begin;  // plane index inside the slab window
       }
-      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, lz, cx, cy, cz, true); }
-      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, lz, cx, cy, cz, false); }
+      __device__ __forceinline__ iterator begin() const { return iterator(a, lx, ly, lz, cx, cy, cz, true, mode); }
+      __device__ __forceinline__ iterator end() const { return iterator(a, lx, ly, lz, cx, cy, cz, false, mode); }
 
      private:
       const detail::FunctionArgs &a;
       float lx, ly, lz;
       int cx, cy, cz;
+      int mode;
     };
 
     // 27 single bins, x slowest, z fastest, toroidal wrap (reference nextCell :264-276, :727-749)
@@ -285,8 +335,9 @@ class MessageSpatial3D {
       int cx, cy, cz;
     };
 
-    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args) : a(args) {}
-    __device__ __forceinline__ Filter operator()(float x, float y, float z) const { return Filter(a, x, y, z); }
+    // mode: 0 reference visit order, 1 radius-filtered; a compile-time constant of the kernel instance
+    __device__ __forceinline__ explicit In(const detail::FunctionArgs &args, int _mode = 0) : a(args), mode(_mode) {}
+    __device__ __forceinline__ Filter operator()(float x, float y, float z) const { return Filter(a, x, y, z, mode); }
     // The reference checks bounds / wrapCompatible only with FLAMEGPU_SEATBELTS (:527-551); this build
     // is the seatbelts-off configuration.
     __device__ __forceinline__ WrapFilter wrap(float x, float y, float z) const { return WrapFilter(a, x, y, z); }
@@ -294,6 +345,7 @@ class MessageSpatial3D {
 
    private:
     const detail::FunctionArgs &a;
+    const int mode;
   };
 
   class Out : public MessageSpatial2D::Out {

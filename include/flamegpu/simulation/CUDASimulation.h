@@ -280,7 +280,7 @@ class CUDASimulation {
     bool inLayerConcurrency = true;
     bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
-    int spatialIterationMode = 0;     // b200: 0 reference order, 1 radius-first, 2 radius-only (FunctionArgs.h)
+    int spatialIterationMode = 0;     // b200: 0 reference order, 1 radius-filtered lock-step walk (FunctionArgs.h)
     bool binOrderExecution = true;    // b200: run functions that read spatial messages in bin order
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's

@@ -658,7 +658,10 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     void *kargs[] = {&a};
     const unsigned int bs = static_cast<unsigned int>(f.block_size);
     prof_begin("function:" + fn.name, st);
-    FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, 0, st));
+    // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
+    const bool filtered = f.msg_in && f.msg_in->spatial && cuda_config.spatialIterationMode != 0 && fn.func_filtered;
+    const size_t smem = filtered ? sizeof(uint32_t) * detail::kFilterQueueWords * bs : 0;
+    FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(filtered ? fn.func_filtered : fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, smem, st));
     prof_end(st);
     ++own_launches;
   }

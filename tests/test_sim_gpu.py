@@ -360,32 +360,45 @@ def test_host_buffer_step_matches_population_path():
     b.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-def test_iterator_radius_modes_match_reference_order_results(mode, golden_dir):
-    # b200 iterator modes: 1 = radius-first (every message still presented once), 2 = radius-only.
-    # Circles filters by radius itself, so both must give the bit-identical step (same in-radius
-    # messages in the same relative order); mode 1 must also keep the Moore-neighbourhood counts.
-    n, L = 60000, 39.0
+@pytest.mark.parametrize("bin_order", [1, 0])
+def test_iterator_radius_filtered_mode(bin_order, golden_dir):
+    # b200 iterator mode 1: the messages within the radius are presented (lock-step walk, per-lane queue).
+    # Circles filters by radius itself, so the step must be bit-identical (same in-radius messages in the same
+    # relative order), with and without bin-order execution (lanes of a warp in different bins).
+    mode = 1
+    n, L = 60001, 39.0  # not a multiple of the warp size: partial last warp
     pos = _circles_pop(n, L, seed=91)
     res = []
     for m in (0, mode):
-        s = _sim("circles", env_max=L, radius=2.0, stable=1, iter_mode=m)
+        s = _sim("circles", env_max=L, radius=2.0, stable=1, iter_mode=m, bin_order=bin_order)
         s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
         s.step(3)
         res.append([s.get("Circle", v, np.float32) for v in ("x", "y", "z", "drift")] + [s.get("Circle", "_id", np.uint32)])
         s.close()
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+    # dense case: more accepted messages than one queue holds (forces intermediate drains)
+    n2, L2 = 20000, 8.0
+    pos2 = _circles_pop(n2, L2, seed=17)
+    res = []
+    for m in (0, mode):
+        s = _sim("circles", env_max=L2, radius=2.0, stable=1, iter_mode=m, bin_order=bin_order)
+        s.set_population("Circle", {"x": pos2[0], "y": pos2[1], "z": pos2[2]})
+        s.step(2)
+        res.append([s.get("Circle", v, np.float32) for v in ("x", "y", "z", "drift")])
+        s.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
     p3 = np.fromfile(os.path.join(golden_dir, "mandatory3d_pos.f32"), dtype=np.float32).reshape(3, -1)
     expect = np.fromfile(os.path.join(golden_dir, "mandatory3d_expect.u32"), dtype=np.uint32)
-    s = _sim("test", which=0, max_x=5, max_y=5, max_z=5, radius=1, sort_period=0, iter_mode=mode)
+    s = _sim("test", which=0, max_x=5, max_y=5, max_z=5, radius=1, sort_period=0, iter_mode=mode, bin_order=bin_order)
     s.set_population("agent", {"x": p3[0], "y": p3[1], "z": p3[2]})
     s.step(1)
     cnt = s.get("agent", "count", np.uint32)
-    if mode == 1:
-        assert np.array_equal(cnt, expect), "radius-first still visits the whole Moore neighbourhood exactly once"
-    else:
-        assert np.all(cnt <= expect) and cnt.sum() < expect.sum()
+    d = np.sqrt(((p3[:, :, None].astype(np.float64) - p3[:, None, :]) ** 2).sum(axis=0))
+    # this model counts every message it is shown: all messages within the radius, plus the padding messages (at
+    # infinity) a lane receives while other lanes of its warp still have accepted messages queued
+    assert np.all(cnt >= (d < 0.9999).sum(axis=1)) and cnt.sum() < expect.sum()
     s.close()
     # 2D twin
     p2 = np.fromfile(os.path.join(golden_dir, "mandatory2d_pos.f32"), dtype=np.float32).reshape(2, -1)
@@ -394,7 +407,7 @@ def test_iterator_radius_modes_match_reference_order_results(mode, golden_dir):
     s.set_population("agent", {"x": p2[0], "y": p2[1]})
     s.step(1)
     c2 = s.get("agent", "count", np.uint32)
-    assert np.array_equal(c2, e2) if mode == 1 else np.all(c2 <= e2)
+    assert c2.sum() > 0 and c2.sum() < e2.sum()
     s.close()
 
 
