@@ -348,6 +348,26 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{ksteps} steps of the same {n}-agent Circles workload"}
             line["reference_cuda"] = reference_cuda(n, L)
+            if args.iter_mode == 0:
+                # -- opt-in, not the headline: the radius-filtered iterator (CUDAConfig().spatialIterationMode = 1),
+                #    bit-identical Circles results (tests/test_sim_gpu.py), same workload and timing method
+                f = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
+                                    true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=1)
+                f.set_population("Circle", {"x": x, "y": y, "z": z})
+                fstream = torch.cuda.ExternalStream(f.stream, device=f"cuda:{local}")
+                k_f = min(args.steps, 100)
+                for i in range(args.warmup + k_f):
+                    with torch.cuda.stream(fstream):
+                        flush.add_(1)
+                    f.step(1)
+                    if i == args.warmup - 1:
+                        f.sync()
+                        f.step_times()
+                f.sync()
+                ft = float(f.step_times().sum())
+                f.close()
+                line["opt_in"] = {"radius_filtered_iterator": {"value": n * k_f / ft, "unit": "agent-steps/s",
+                                                               "ms_per_step": ft / k_f * 1e3, "steps": k_f}}
         print(json.dumps(line), flush=True)
     s.close()
     if dist is not None:
