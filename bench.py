@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / reference_cuda / e2e legs")
     ap.add_argument("--stable", type=int, default=0)
     ap.add_argument("--true3d-sort", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=1, help="1: build the PBM on a second stream while the agents are sorted")
+    ap.add_argument("--tile-order", type=int, default=1, help="1: tile-local execution order after the auto sort")
     ap.add_argument("--iter-mode", type=int, default=0, help="0 reference visit order (default), 1 radius-filtered lock-step walk (opt-in)")
     ap.add_argument("--bin-order", type=int, default=1, help="run message-reading functions in bin order (b200 extension)")
     args = ap.parse_args()
@@ -206,7 +208,7 @@ def main():
     if world == 1:
         x, y, z = population(n, L, seed=rank)
         s = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, timing=1, stable=args.stable,
-                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode, overlap=args.overlap, tile_order=args.tile_order)
         s.set_population("Circle", {"x": x, "y": y, "z": z})
         stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
         slab_sim = None
@@ -227,7 +229,7 @@ def main():
         mig_cap = int(n // planes_per_rank // 4 + 4096)       # a few percent of a plane changes slab per step
         slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=halo_cap,
                                        migrate_capacity=mig_cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
-                                       stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
+                                       stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode, overlap=args.overlap, tile_order=args.tile_order)
         s = slab_sim.sim
         rng = np.random.default_rng(rank)
         z_lo, z_hi = slab_sim.z0 * RADIUS, slab_sim.z1 * RADIUS
@@ -282,6 +284,7 @@ def main():
             "workload": f"Circles-3D, {n} agents per GPU, [0,{L:g})^3, radius {RADIUS:g} ({bins} bins, ~8 agents/bin), "
                         f"whole CUDASimulation::step() (output_message, auto agent sort, PBM buildIndex, move)",
             "agents_per_gpu": n, "bins": bins, "graphs": s.graphs, "bin_order_execution": bool(args.bin_order), "iterator_mode": args.iter_mode,
+            "overlap_index_build": bool(args.overlap), "tile_local_exec_order": bool(args.tile_order),
             "l2": "flushed between steps (256 MiB write outside the timed events)" if world == 1 else
                   "not flushed (exchange-synchronised steps; per-GPU working set ~80 MB)",
             "timing": "sum of per-step CUDA-event times on the simulation stream" if world == 1 else
@@ -299,7 +302,7 @@ def main():
         peak, peak_src = measured_peak()
         # -- per-phase device times from a profiled (eager, event-bracketed) pass of the same workload
         p = fsim.Simulation("circles", device=local, env_max=L, radius=RADIUS, repulse=REPULSE, profile=1, stable=args.stable,
-                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode)
+                            true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode, overlap=args.overlap, tile_order=args.tile_order)
         p.set_population("Circle", {"x": x, "y": y, "z": z})
         pstream = torch.cuda.ExternalStream(p.stream, device=f"cuda:{local}")
         for i in range(args.warmup + 30):

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libflamegpu2_b200.so")
 FGB_MAX_VARS = 32
 FGB_BUILD_DEFAULT = 0
 FGB_BUILD_STABLE = 1
+FGB_BUILD_TILE_LOCAL = 2
 FGB_ERR_NO_DEVICE = -3
 
 

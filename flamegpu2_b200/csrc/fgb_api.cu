@@ -147,6 +147,14 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
   const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
+  if (flags & FGB_BUILD_TILE_LOCAL) {
+    if (vec)
+      k_group_tile<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, perm);
+    else
+      k_group_tile<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, perm);
+    ctx->launches += 1;
+    return launch_ok();
+  }
   VarTable none{};
   none.n = 0;
   if (flags & FGB_BUILD_STABLE) {

@@ -333,6 +333,78 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(KeySrc<DIMS>
   }
 }
 
+// Tile-local grouping (FGB_BUILD_TILE_LOCAL): perm[tile0 + e] = index of the item at grouped position e of its
+// 2048-item tile, equal bins adjacent (table order).  One pass, no global atomics, no histogram: enough to give
+// the lanes of a warp common message strips when the list is already coarsely ordered (the reference's auto sort
+// leaves agents in (x,y)-column order), at a quarter of the cost of the global permutation.
+template <int DIMS, bool VEC>
+__global__ void __launch_bounds__(kBinThreads) k_group_tile(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                            uint32_t *__restrict__ perm) {
+  __shared__ uint32_t s_key[kTabSlots];   // key of the slot, later the slot's offset in the tile
+  __shared__ uint32_t s_cnt[kTabSlots];
+  __shared__ uint16_t s_src[kTile];
+  __shared__ uint32_t s_scan[33];
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t tile0 = blockIdx.x * kTile;
+  if (tile0 >= n) return;
+  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
+  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+  uint32_t k[kTileItems];
+  if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
+    s_key[s] = kTabEmpty;
+    s_cnt[s] = 0u;
+  }
+  __syncthreads();
+  uint32_t slot[kTileItems], rank[kTileItems];
+  {
+    int j = 0;
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      if (r == j && j < cnt) {
+        int e = j + 1;
+#pragma unroll
+        for (int t = 1; t < kTileItems; ++t)
+          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+        const uint32_t sl = tab_insert(s_key, k[r]);
+        const uint32_t b = atomicAdd(s_cnt + sl, static_cast<uint32_t>(e - j));
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (r + t < e && t < kTileItems - r) {
+            slot[r + t] = sl;
+            rank[r + t] = b + t;
+          }
+        j = e;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int kPer = kTabSlots / kBinThreads;
+    uint32_t c[kPer], sum = 0;
+    const int s0 = threadIdx.x * kPer;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      c[q] = s_key[s0 + q] != kTabEmpty ? s_cnt[s0 + q] : 0u;
+      sum += c[q];
+    }
+    uint32_t tile_total;
+    uint32_t off = block_exclusive_scan(sum, s_scan, &tile_total);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      s_key[s0 + q] = off;
+      off += c[q];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < kTileItems; ++t)
+    if (t < cnt) s_src[s_key[slot[t]] + rank[t]] = static_cast<uint16_t>(threadIdx.x * kTileItems + t);
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) perm[tile0 + e] = tile0 + s_src[e];
+}
+
 // ---- stable order: per-bin fix-up --------------------------------------------------------
 constexpr int kFixSmall = 32;
 

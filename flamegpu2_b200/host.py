@@ -169,8 +169,10 @@ class Spatial:
                "fgb_spatial_read_pbm")
         return out
 
-    def bin_permutation(self, x, y, z, perm_out, n: int, *, stable=False, d_n=None):
+    def bin_permutation(self, x, y, z, perm_out, n: int, *, stable=False, tile_local=False, d_n=None):
         flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT
+        if tile_local:
+            flags |= _capi.FGB_BUILD_TILE_LOCAL
         _check(lib().fgb_bin_permutation(self.h, n, _ptr(d_n), _ptr(x), _ptr(y), _ptr(z), _ptr(perm_out), flags, _stream_ptr()),
                "fgb_bin_permutation")
 

@@ -282,6 +282,8 @@ class CUDASimulation {
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
     int spatialIterationMode = 0;     // b200: 0 reference order, 1 radius-filtered lock-step walk (FunctionArgs.h)
     bool binOrderExecution = true;    // b200: run functions that read spatial messages in bin order
+    bool tileLocalExecOrder = true;   // b200: bin-order execution groups inside 2048-agent tiles when the list was just sorted
+    bool overlapIndexBuild = true;    // b200: build the input list's PBM on a second stream while the agents are sorted
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
                                       // key collapses z, CUDASimulation.cu:487; see sort_geometry())
@@ -410,6 +412,7 @@ class CUDASimulation {
   void record_layers(cudaStream_t main, size_t first, size_t last);
   void record_end_of_step(cudaStream_t main);
   void run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int stream_id);
+  void build_input_index(detail::CUDAMessage &M, cudaStream_t st);
   void refresh_bounds();                    // births only: read the counts back once per step
   int sort_geometry(const detail::FunctionRT &f, float mn[3], float width[3], unsigned int gd[3]) const;
   std::vector<unsigned long long> graph_key() const;
@@ -430,6 +433,9 @@ class CUDASimulation {
   std::vector<cudaStream_t> side_streams;
   std::vector<cudaEvent_t> join_events;
   cudaEvent_t fork_event = nullptr;
+  cudaStream_t index_stream = nullptr;   // PBM builds of a layer's input lists (overlapIndexBuild)
+  cudaEvent_t index_fork = nullptr, index_done = nullptr;
+  bool index_pending = false;
   unsigned int *d_ctrl = nullptr;
   unsigned int next_slot = 1;
   unsigned int slab_tmp_slot = 0;

@@ -26,6 +26,9 @@ inline void CUDASimulation::initialise() {
   FGB_ABI_THROW(fgb_ctx_create(cuda_config.device_id, &ctx));
   FGB_CUDA_THROW(cudaStreamCreateWithFlags(&main_stream, cudaStreamNonBlocking));
   FGB_CUDA_THROW(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+  FGB_CUDA_THROW(cudaEventCreateWithFlags(&index_fork, cudaEventDisableTiming));
+  FGB_CUDA_THROW(cudaEventCreateWithFlags(&index_done, cudaEventDisableTiming));
+  FGB_CUDA_THROW(cudaStreamCreateWithFlags(&index_stream, cudaStreamNonBlocking));
   FGB_CUDA_THROW(cudaMalloc(&d_ctrl, kCtrlWords * 4));
   FGB_CUDA_THROW(cudaMemset(d_ctrl, 0, kCtrlWords * 4));
   next_slot = 1;
@@ -205,6 +208,11 @@ inline void CUDASimulation::destroy() {
   for (auto s : side_streams) cudaStreamDestroy(s);
   for (auto e : join_events) cudaEventDestroy(e);
   if (fork_event) cudaEventDestroy(fork_event);
+  if (index_fork) cudaEventDestroy(index_fork);
+  if (index_done) cudaEventDestroy(index_done);
+  if (index_stream) cudaStreamDestroy(index_stream);
+  fork_event = index_fork = index_done = nullptr;
+  index_stream = nullptr;
   if (main_stream) cudaStreamDestroy(main_stream);
   if (ctx) fgb_ctx_destroy(ctx);
   ctx = nullptr;
@@ -415,7 +423,8 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
     }
   k.push_back(sort_bits);
   k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull) |
-              (cuda_config.binOrderExecution ? 4ull : 0ull) | (static_cast<unsigned long long>(cuda_config.spatialIterationMode) << 8));
+              (cuda_config.binOrderExecution ? 4ull : 0ull) | (cuda_config.overlapIndexBuild ? 8ull : 0ull) |
+              (cuda_config.tileLocalExecOrder ? 16ull : 0ull) | (static_cast<unsigned long long>(cuda_config.spatialIterationMode) << 8));
   return k;
 }
 
@@ -516,6 +525,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
 
   // 1. automatic spatial sort of the executing agents (reference CUDASimulation.cu:463-573)
   const unsigned int period = f.agent->desc->sort_period;
+  // after the auto sort the list is in the sort key's order: grouping inside tiles is enough for step 2b
+  const bool sorted_now = f.sortable && period != 0 && step_count % period == 0 && cuda_config.tileLocalExecOrder;
   if (f.sortable && period != 0 && step_count % period == 0) {
     float mn[3], width[3];
     unsigned int gd[3];
@@ -563,23 +574,9 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     prof_end(st);
   }
 
-  // 2. index of the input list, built lazily before its first reader (reference :864)
-  if (f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty) {
-    detail::CUDAMessage &M = *f.msg_in;
-    if (M.list.bound > 0) {
-      prof_begin("build_index", st);
-      std::vector<fgb_var> vars = M.list.vars(true);
-      const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
-      FGB_ABI_THROW(fgb_build_index(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
-                                    reinterpret_cast<const float *>(M.list.data[iy]),
-                                    iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
-                                    static_cast<unsigned int>(vars.size()),
-                                    cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
-      M.list.swap_buffers();
-      prof_end(st);
-    }
-    M.pbm_dirty = false;
-  }
+  // 2. index of the input list, built lazily before its first reader (reference :864); record_layers has
+  // normally issued it already (on the index stream, overlapping the sort above)
+  if (f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty) build_input_index(*f.msg_in, st);
 
   // 2b. execution order: bin the executing agents on the input list's grid (b200 extension)
   const bool bin_order = f.exec_binner && cuda_config.binOrderExecution && !conditional;
@@ -590,7 +587,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     FGB_ABI_THROW(fgb_bin_permutation(f.exec_binner, n, d_n, reinterpret_cast<const float *>(L.data[ix]),
                                       reinterpret_cast<const float *>(L.data[iy]),
                                       iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, f.exec_perm.p,
-                                      cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+                                      sorted_now ? FGB_BUILD_TILE_LOCAL : FGB_BUILD_DEFAULT, st));
     prof_end(st);
   }
 
@@ -657,6 +654,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   {
     void *kargs[] = {&a};
     const unsigned int bs = static_cast<unsigned int>(f.block_size);
+    if (index_pending && f.msg_in && f.msg_in->spatial) FGB_CUDA_THROW(cudaStreamWaitEvent(st, index_done, 0));
     prof_begin("function:" + fn.name, st);
     // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
     const bool filtered = f.msg_in && f.msg_in->spatial && cuda_config.spatialIterationMode != 0 && fn.func_filtered;
@@ -770,9 +768,40 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   prof_end(st);
 }
 
+inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream_t st) {
+  if (M.list.bound > 0) {
+    prof_begin("build_index", st);
+    std::vector<fgb_var> vars = M.list.vars(true);
+    const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
+    FGB_ABI_THROW(fgb_build_index(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
+                                  reinterpret_cast<const float *>(M.list.data[iy]),
+                                  iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
+                                  static_cast<unsigned int>(vars.size()),
+                                  cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+    M.list.swap_buffers();
+    prof_end(st);
+  }
+  M.pbm_dirty = false;
+}
+
 inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_t last) {
   for (size_t li = first; li < last && li < layers.size(); ++li) {
     auto &layer = layers[li];
+    // The PBMs this layer reads do not depend on the layer's own agent lists: build them on the index stream
+    // while the functions' streams sort / partition their agents; each reader waits for index_done before its
+    // kernel.  (Also orders the build before EVERY reader when several functions of a layer share a list.)
+    index_pending = false;
+    for (auto &f : layer) {
+      if (!(f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty)) continue;
+      const bool overlap = cuda_config.overlapIndexBuild && !cuda_config.profile;
+      if (overlap && !index_pending) {
+        FGB_CUDA_THROW(cudaEventRecord(index_fork, main));
+        FGB_CUDA_THROW(cudaStreamWaitEvent(index_stream, index_fork, 0));
+        index_pending = true;
+      }
+      build_input_index(*f.msg_in, overlap ? index_stream : main);
+    }
+    if (index_pending) FGB_CUDA_THROW(cudaEventRecord(index_done, index_stream));
     const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty();
     if (fork) FGB_CUDA_THROW(cudaEventRecord(fork_event, main));
     for (size_t i = 0; i < layer.size(); ++i) {

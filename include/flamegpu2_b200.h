@@ -125,7 +125,10 @@ enum fgb_build_flags {
   FGB_BUILD_DEFAULT = 0,
   /* within-bin order = source order (deterministic).  Default order is arrival order of the
    * scatter, like the reference's atomicInc sub-index (MessageSpatial3D.cu:70). */
-  FGB_BUILD_STABLE = 1
+  FGB_BUILD_STABLE = 1,
+  /* fgb_bin_permutation only: group equal bins inside tiles of 2048 consecutive points instead of globally
+   * (one pass, the PBM is not written).  For lists that are already coarsely ordered. */
+  FGB_BUILD_TILE_LOCAL = 2
 };
 
 /* MessageSpatial3D::CUDAModelHandler::buildIndex (MessageSpatial3D.cu:113-146) and

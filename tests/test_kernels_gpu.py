@@ -155,6 +155,42 @@ def test_build_index_repeatable_many_calls(ctx):
     sp.close()
 
 
+@pytest.mark.parametrize("dims", [3, 2])
+@pytest.mark.parametrize("n", [1, 2047, 2048, 6000, 300007])
+def test_bin_permutation_global_and_tile_local(ctx, n, dims):
+    # fgb_bin_permutation (b200 extension): the execution order of an agent function that reads a spatial list
+    from flamegpu2_b200 import host
+
+    mn, mx, radius = [0.0] * dims, [30.0, 22.0, 17.0][:dims], 1.5
+    pos = _positions(n, mn, mx, seed=n + dims, dims=dims)
+    g = orc.Grid(dims, mn, mx, radius)
+    keys = g.bin_keys(pos[0], pos[1], pos[2] if dims == 3 else None)
+    sp = host.Spatial(ctx, dims, mn, mx, radius)
+    dp = [t(p) for p in pos]
+    perm = torch.zeros(n, dtype=torch.int32, device=DEV)
+    # global: sorted by bin, PBM = offsets
+    sp.bin_permutation(dp[0], dp[1], dp[2] if dims == 3 else None, perm, n)
+    torch.cuda.synchronize()
+    pm = as_u32(perm)
+    assert np.array_equal(np.sort(pm), np.arange(n, dtype=np.uint32))
+    assert np.all(np.diff(keys[pm].astype(np.int64)) >= 0)
+    pbm_ref, _ = g.build_index(pos[0], pos[1], pos[2] if dims == 3 else None)
+    assert np.array_equal(sp.pbm(), pbm_ref)
+    # tile local: a permutation inside every 2048-item tile, equal bins contiguous inside the tile
+    perm.zero_()
+    sp.bin_permutation(dp[0], dp[1], dp[2] if dims == 3 else None, perm, n, tile_local=True)
+    torch.cuda.synchronize()
+    pm = as_u32(perm)
+    assert np.array_equal(np.sort(pm), np.arange(n, dtype=np.uint32))
+    for t0 in range(0, n, 2048):
+        seg = pm[t0:t0 + 2048]
+        assert seg.min() >= t0 and seg.max() < min(t0 + 2048, n)
+        k = keys[seg]
+        runs = 1 + int(np.count_nonzero(np.diff(k.astype(np.int64))))
+        assert runs == len(np.unique(k)), "every bin of the tile forms one contiguous run"
+    sp.close()
+
+
 @pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 125001, 3000000])
 def test_exclusive_scan(ctx, n):
     rng = np.random.default_rng(n)
