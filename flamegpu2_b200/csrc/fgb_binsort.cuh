@@ -98,10 +98,14 @@ __device__ __forceinline__ uint32_t tab_insert(uint32_t *s_key, uint32_t key) {
   // bits are mixed in additively so that keys that differ by a multiple of the table size (the same column
   // in another z plane of a power-of-two grid) do not pile up on one probe chain
   uint32_t slot = (key + (key >> kTabBits) * 0x9E3779B1u) & (kTabSlots - 1);
+  // Double hashing with a long odd stride.  Because adjacent keys sit in adjacent slots, the keys of a tile form
+  // runs of hundreds of occupied slots; with linear probing two overlapping runs (2D lists: neighbouring rows
+  // of the grid) cost ~250 probes per insert (measured: 20x slower builds).  A long stride leaves the run at once.
+  const uint32_t step = ((key * 0x85EBCA6Bu) >> (32 - kTabBits)) | 0x401u;
   while (true) {
     const uint32_t prev = atomicCAS(s_key + slot, kTabEmpty, key);
     if (prev == kTabEmpty || prev == key) return slot;
-    slot = (slot + 1) & (kTabSlots - 1);
+    slot = (slot + step) & (kTabSlots - 1);
   }
 }
 

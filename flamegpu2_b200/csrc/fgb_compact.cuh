@@ -22,43 +22,50 @@ inline unsigned int compact_num_tiles(unsigned int n) { return (n + kCmpTile - 1
 // state[]: one look-back word per tile, all-zero on entry; done: zero on entry.  The last block
 // to finish its look-back re-zeroes both, so consecutive launches (and CUDA-graph replays) need
 // no memset in between.
+//
+// Layout: a tile is 8 warps x 256 items; in round r (0..7) lane l of warp w handles item
+// tile0 + w*256 + r*32 + l.  Every load is a fully coalesced 128-byte warp access and, because the
+// kept items of one round are ranked with a ballot, every store instruction writes one contiguous
+// run of the output: no shared-memory staging and no alignment cases.  (The first version gave each
+// thread 8 consecutive items: vector loads, but eight strided 4-byte stores per variable.)
 template <bool VEC>
 __global__ void __launch_bounds__(kCmpThreads)
 k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const unsigned int *d_n, uint32_t keep_front,
           uint32_t out_offset, const unsigned int *d_out_offset, uint32_t out_limit, const __grid_constant__ VarTable vt,
           unsigned long long *state, uint32_t *done, uint32_t *d_out_count, uint32_t *d_out_total) {
-  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t s_warp[kCmpThreads / 32];
   __shared__ uint32_t s_excl;
   __shared__ uint32_t s_last;
   const uint32_t n = load_count(d_n, n_max);
   const int tile = blockIdx.x;
   const bool last_tile = tile == static_cast<int>(gridDim.x) - 1;
-  const uint32_t i0 = static_cast<uint32_t>(tile) * kCmpTile + threadIdx.x * kCmpItems;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t w0 = static_cast<uint32_t>(tile) * kCmpTile + warp * (32u * kCmpItems);
   if (d_out_offset) out_offset = __ldg(d_out_offset);
 
-  // ---- keep mask of this thread's 8 consecutive items
-  uint32_t keep = 0;
-  if (i0 < n) {
-    if (VEC && keep_front == 0 && i0 + kCmpItems <= n) {
-      const uint4 a = ld_stream_u4(flags + i0), b = ld_stream_u4(flags + i0 + 4);
-      const uint32_t f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  // ---- keep ballots of the warp's 8 rounds
+  uint32_t bal[kCmpItems];
+  uint32_t wcount = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) keep |= (((f[j] == 1u) != (invert != 0)) ? 1u : 0u) << j;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t i = i0 + j;
-        if (i < n) {
-          bool k = i < keep_front;
-          if (!k) k = (ld_stream_u32(flags + (i - keep_front)) == 1u) != (invert != 0);
-          keep |= (k ? 1u : 0u) << j;
-        }
-      }
+  for (int r = 0; r < kCmpItems; ++r) {
+    const uint32_t i = w0 + r * 32u + lane;
+    bool k = false;
+    if (i < n) {
+      k = i < keep_front;
+      if (!k) k = (ld_stream_u32(flags + (i - keep_front)) == 1u) != (invert != 0);
     }
+    bal[r] = __ballot_sync(0xFFFFFFFFu, k);
+    wcount += __popc(bal[r]);
   }
-  const uint32_t tcount = __popc(keep);
-  uint32_t agg;
-  const uint32_t texcl = block_exclusive_scan(tcount, warp_sums, &agg);
+  if (lane == 0) s_warp[warp] = wcount;
+  __syncthreads();
+  uint32_t wexcl = 0, agg = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < kCmpThreads / 32; ++w) {
+    const uint32_t c = s_warp[w];
+    if (w < warp) wexcl += c;
+    agg += c;
+  }
 
   // ---- publish the tile aggregate, resolve the exclusive prefix
   if (threadIdx.x == 0) {
@@ -80,40 +87,36 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
     if (d_out_total) *d_out_total = out_offset + tile_excl + agg;
   }
 
-  // ---- move the kept items of every variable; a thread's kept items are contiguous in the output
+  // ---- move the kept items of every variable
   // out_limit: only the first out_limit kept items are written (the counts still report all of them, so a
   // caller with a fixed-capacity destination can detect the overflow instead of corrupting memory)
-  const uint32_t rank0 = tile_excl + texcl;
-  if (keep && rank0 < out_limit) {
-    const uint32_t room = out_limit - rank0;
-    const size_t pos0 = static_cast<size_t>(out_offset) + rank0;
+  if (wcount) {
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t rank[kCmpItems];
+    uint32_t run = tile_excl + wexcl;
+    uint32_t mine = 0;  // bit r: this lane's item of round r is kept and fits under out_limit
+#pragma unroll
+    for (int r = 0; r < kCmpItems; ++r) {
+      rank[r] = run + __popc(bal[r] & lt);
+      if (((bal[r] >> lane) & 1u) && rank[r] < out_limit) mine |= 1u << r;
+      run += __popc(bal[r]);
+    }
     for (uint32_t v = 0; v < vt.n; ++v) {
       const uint32_t len = vt.len[v];
-      if (VEC && len == 4 && i0 + kCmpItems <= n) {
-        const uint4 a = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
-        const uint4 b = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4 + 16);
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]) + pos0;
-        if (keep == 0xFFu && room >= 8u && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
-          reinterpret_cast<uint4 *>(o)[0] = a;
-          reinterpret_cast<uint4 *>(o)[1] = b;
-        } else {
-          uint32_t p = 0;
+      if (len == 4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]);
+        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]) + out_offset;
+        uint32_t val[kCmpItems];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (keep & (1u << j)) {
-              if (p < room) o[p] = w[j];
-              ++p;
-            }
-        }
+        for (int r = 0; r < kCmpItems; ++r)
+          if (mine & (1u << r)) val[r] = ld_stream_u32(in + w0 + r * 32u + lane);
+#pragma unroll
+        for (int r = 0; r < kCmpItems; ++r)
+          if (mine & (1u << r)) o[rank[r]] = val[r];
       } else {
-        uint32_t p = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (keep & (1u << j)) {
-            if (p < room) copy_item(vt, v, i0 + j, pos0 + p);
-            ++p;
-          }
+        for (int r = 0; r < kCmpItems; ++r)
+          if (mine & (1u << r)) copy_item(vt, v, w0 + r * 32u + lane, static_cast<size_t>(out_offset) + rank[r]);
       }
     }
   }

@@ -48,10 +48,42 @@ def circles_positions(n, L, sorted_like, seed=0):
     return pos.contiguous()
 
 
+def boids2d_case(ctx, n, reps, flush, peak, jitter_bins):
+    """2D list of the Boids-2D shape: bin-sorted a step ago, every point then moved by up to jitter_bins bins."""
+    r = 0.0007
+    sp = host.Spatial(ctx, 2, (-0.5, -0.5), (0.5, 0.5), r)
+    sp.reserve(n)
+    g = torch.Generator(device=DEV)
+    g.manual_seed(5)
+    pos = torch.rand((2, n), generator=g, device=DEV) - 0.5
+    gd = sp.grid_dim[0]
+    cell = torch.floor((pos + 0.5) / r).to(torch.int64).clamp_(0, gd - 1)
+    order = torch.argsort(cell[1] * gd + cell[0], stable=True)
+    pos = pos[:, order].contiguous()
+    pos = (pos + (torch.rand((2, n), generator=g, device=DEV) - 0.5) * 2 * jitter_bins * r).clamp_(-0.5, 0.4999999).contiguous()
+    ids = torch.arange(n, dtype=torch.int32, device=DEV)
+    fx = torch.rand(n, generator=g, device=DEV)
+    ins = [fx, fx.clone(), ids, pos[0].contiguous(), pos[1].contiguous()]
+    outs = [torch.empty_like(a) for a in ins]
+    alg = n * 2 * 20 + 4 * (sp.bin_count + 1)
+    med, best = timed(lambda: sp.build_index(ins[3], ins[4], None, ins, outs, n), reps=reps, flush=flush)
+    print(json.dumps({"op": "build_index_2d", "n": n, "bins": sp.bin_count, "jitter_bins": jitter_bins, "us_median": med,
+                      "us_best": best, "alg_bytes": alg, "GBps": alg / med / 1e3, "frac_of_measured_peak": alg / med / 1e3 / peak}),
+          flush=True)
+    perm = torch.empty(n, dtype=torch.int32, device=DEV)
+    for tl in (False, True):
+        med, best = timed(lambda: sp.bin_permutation(ins[3], ins[4], None, perm, n, tile_local=tl), reps=reps, flush=flush)
+        print(json.dumps({"op": "bin_permutation_2d", "n": n, "tile_local": tl, "jitter_bins": jitter_bins, "us_median": med,
+                          "us_best": best}), flush=True)
+    sp.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="1000000,16777216")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--boids2d", action="store_true", help="only the 2D (Boids) build / permutation cases")
+    ap.add_argument("--jitter", type=float, default=None, help="--boids2d: displacement in bins since the list was sorted")
     args = ap.parse_args()
     peaks = {}
     try:
@@ -61,6 +93,10 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ctx = host.Context(0)
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=DEV)  # 256 MB > 126 MB L2
+    if args.boids2d:
+        for jit in ([args.jitter] if args.jitter is not None else [0.05, 0.7]):
+            boids2d_case(ctx, 16_000_000, args.reps, flush, peak, jit)
+        return
     for n in [int(s) for s in args.sizes.split(",")]:
         L = float(round((n) ** (1.0 / 3.0)))
         sp = host.Spatial(ctx, 3, (0, 0, 0), (L, L, L), 2.0)
