@@ -57,6 +57,19 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
     bal[r] = __ballot_sync(0xFFFFFFFFu, k);
     wcount += __popc(bal[r]);
   }
+  // the loads of the payload do not depend on the output rank: fetch the first variable now, so that the
+  // tile-aggregate exchange and the look-back below overlap with memory latency instead of adding to it
+  uint32_t keptbits = 0;  // bit r: this lane's item of round r is kept
+#pragma unroll
+  for (int r = 0; r < kCmpItems; ++r) keptbits |= ((bal[r] >> lane) & 1u) << r;
+  const bool first4 = vt.n > 0 && vt.len[0] == 4;
+  uint32_t val0[kCmpItems];
+  if (first4) {
+    const uint32_t *in0 = reinterpret_cast<const uint32_t *>(vt.in[0]);
+#pragma unroll
+    for (int r = 0; r < kCmpItems; ++r)
+      if (keptbits & (1u << r)) val0[r] = ld_stream_u32(in0 + w0 + r * 32u + lane);
+  }
   if (lane == 0) s_warp[warp] = wcount;
   __syncthreads();
   uint32_t wexcl = 0, agg = 0;
@@ -101,23 +114,33 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
       if (((bal[r] >> lane) & 1u) && rank[r] < out_limit) mine |= 1u << r;
       run += __popc(bal[r]);
     }
+    // software pipeline over the variables: the loads of variable v+1 are in flight while v is stored
+    uint32_t cur[kCmpItems];
+#pragma unroll
+    for (int r = 0; r < kCmpItems; ++r) cur[r] = val0[r];
+    bool cur4 = first4;
     for (uint32_t v = 0; v < vt.n; ++v) {
-      const uint32_t len = vt.len[v];
-      if (len == 4) {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]);
+      const bool next4 = v + 1 < vt.n && vt.len[v + 1] == 4;
+      uint32_t nxt[kCmpItems];
+      if (next4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 1]);
+#pragma unroll
+        for (int r = 0; r < kCmpItems; ++r)
+          if (mine & (1u << r)) nxt[r] = ld_stream_u32(in + w0 + r * 32u + lane);
+      }
+      if (cur4) {
         uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]) + out_offset;
-        uint32_t val[kCmpItems];
 #pragma unroll
         for (int r = 0; r < kCmpItems; ++r)
-          if (mine & (1u << r)) val[r] = ld_stream_u32(in + w0 + r * 32u + lane);
-#pragma unroll
-        for (int r = 0; r < kCmpItems; ++r)
-          if (mine & (1u << r)) o[rank[r]] = val[r];
+          if (mine & (1u << r)) o[rank[r]] = cur[r];
       } else {
 #pragma unroll
         for (int r = 0; r < kCmpItems; ++r)
           if (mine & (1u << r)) copy_item(vt, v, w0 + r * 32u + lane, static_cast<size_t>(out_offset) + rank[r]);
       }
+#pragma unroll
+      for (int r = 0; r < kCmpItems; ++r) cur[r] = nxt[r];
+      cur4 = next4;
     }
   }
 
