@@ -59,6 +59,17 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
                : "l"(p));
   return r;
 }
+// 256-bit read-only load (sm_100: LDG.E.ENL2.256); p must be 32-byte aligned
+__device__ __forceinline__ void ld_nc_f8(const float *p, float v[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_nc_u8(const uint32_t *p, uint32_t v[8]) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
   uint32_t r;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));

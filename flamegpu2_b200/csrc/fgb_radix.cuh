@@ -54,9 +54,18 @@ __global__ void __launch_bounds__(kRsThreads) k_radix_hist(const uint32_t *__res
   __syncthreads();
   const uint32_t n = load_count(d_n, n_max);
   const uint32_t stride = gridDim.x * kRsThreads;
-  for (uint32_t i = blockIdx.x * kRsThreads + threadIdx.x; i < n; i += stride) {
-    const uint32_t k = ld_stream_u32(keys + i);
-    for (int p = 0; p < plan.passes; ++p) atomicAdd(&sh[p][(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
+  // warp-aggregated: lists arrive nearly sorted (agents were sorted a step ago), so the lanes of a warp mostly hold
+  // the same digit; one shared-memory atomic per distinct digit of the warp instead of 32 on the same address
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * kRsThreads; base < n; base += stride) {  // block-uniform trip count
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t k = valid ? ld_stream_u32(keys + i) : 0u;
+    for (int p = 0; p < plan.passes; ++p) {
+      const uint32_t d = (k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
+      if (valid && lane == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&sh[p][d], static_cast<uint32_t>(__popc(peers)));
+    }
   }
   __syncthreads();
   for (int p = 0; p < plan.passes; ++p)
