@@ -266,7 +266,10 @@ def main():
     if dist is not None:
         dist.barrier()
     if world == 1:
-        dev_total = float(s.step_times().sum())  # per-step events: the L2 flush between steps is excluded
+        st_ = s.step_times()
+        if os.environ.get("FGB_BENCH_DEBUG"):
+            print("step_times_ms", np.round(st_ * 1e3, 3).tolist(), file=sys.stderr)
+        dev_total = float(st_.sum())  # per-step events: the L2 flush between steps is excluded
     else:
         dev_total = ev0.elapsed_time(ev1) * 1e-3  # device time of the whole K-step region on the simulation stream
         slab_sim.check_overflow()

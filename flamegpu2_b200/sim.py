@@ -130,11 +130,16 @@ class Simulation:
         return int(lib().fgbm_step_counter(self.h))
 
     def step_times(self) -> np.ndarray:
-        cap = 1 << 16
-        buf = (C.c_double * cap)()
+        """Device seconds of the steps run since the previous call (model created with timing=1).
+        CUDASimulation::getElapsedTimeSteps() keeps the whole history like the reference; this returns the new part."""
         n = C.c_uint()
-        _check(lib().fgbm_step_times(self.h, buf, cap, C.byref(n)), "fgbm_step_times")
-        return np.array(buf[: min(cap, n.value)])
+        _check(lib().fgbm_step_times(self.h, None, 0, C.byref(n)), "fgbm_step_times")
+        total = int(n.value)
+        buf = (C.c_double * max(total, 1))()
+        _check(lib().fgbm_step_times(self.h, buf, total, C.byref(n)), "fgbm_step_times")
+        seen = getattr(self, "_times_seen", 0)
+        self._times_seen = total
+        return np.array(buf[seen:total])
 
     def profile(self) -> dict:
         """{phase: (total_ms, calls)} since the last call (model created with profile=1)."""
