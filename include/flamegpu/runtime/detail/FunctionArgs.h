@@ -129,7 +129,14 @@ FGB_HD LocPtrs make_loc(const FunctionArgs &a) {
 // of up to 32 consecutive messages and keeps, per chunk with at least one message within the radius, the pair
 // {first message index, accepted bit mask} in dynamic shared memory: word w of thread t at [w * blockDim.x + t]
 // (conflict free).  The scheduler launches with kFilterQueueWords * blockDim.x words.
-constexpr unsigned int kFilterChunks = 16;                    // queued chunks per lane (up to 512 accepted messages)
+// 8 chunks = 64 B of shared memory per thread.  Shared memory is carved out of the L1: with 16 chunks per lane the
+// L1 hit rate of the message loads fell from 74 % to 9 % and the walk became latency bound (stress model 2x
+// slower than the unfiltered iterator); with 4 the queues fill too often.  Measured: 16 / 8 / 4 chunks ->
+// Circles 16.8 M move 9.2 / 8.0 / 9.9 ms, stress 4 M update 1.90 / 0.96 / 1.09 ms.
+#ifndef FGB_FILTER_CHUNKS
+#define FGB_FILTER_CHUNKS 8
+#endif
+constexpr unsigned int kFilterChunks = FGB_FILTER_CHUNKS;     // queued chunks per lane (each up to 32 accepted messages)
 constexpr unsigned int kFilterQueueWords = 2 * kFilterChunks;
 // location of the padding message a lane is shown while other lanes of its warp still have accepted messages:
 // far outside any environment, finite so that distance arithmetic on it stays on the fast paths

@@ -152,7 +152,7 @@ class MessageSpatial2D {
             }
           }
         }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return strip < (mode != 0 ? 4 : 3); }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return mode != 0 ? strip < 4 : idx < idx_end; }
         __device__ __forceinline__ bool operator==(const Message &rhs) const { return strip == rhs.strip && idx == rhs.idx; }
         __device__ __forceinline__ Message &operator++() {
           if (mode != 0) {
@@ -252,7 +252,7 @@ class MessageSpatial2D {
             next_cell();
           }
         }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return cell < 9; }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return idx < idx_end; }
         __device__ __forceinline__ bool operator==(const Message &rhs) const { return cell == rhs.cell && idx == rhs.idx; }
         __device__ __forceinline__ Message &operator++() {
           if (++idx >= idx_end) next_cell();

@@ -164,7 +164,9 @@ class MessageSpatial3D {
           }
         }
         __device__ __forceinline__ bool operator!=(const Message &) const {
-          return strip < (mode != 0 ? 10 : 9);
+          // reference order: after the last strip next_strip() leaves an empty range, so one compare serves both
+          // "advance within the strip" and "end of iteration"
+          return mode != 0 ? strip < 10 : idx < idx_end;
         }
         __device__ __forceinline__ bool operator==(const Message &rhs) const {
           return strip == rhs.strip && idx == rhs.idx;
@@ -275,7 +277,7 @@ class MessageSpatial3D {
             next_cell();
           }
         }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return cell < 27; }
+        __device__ __forceinline__ bool operator!=(const Message &) const { return idx < idx_end; }  // empty range after the last cell
         __device__ __forceinline__ bool operator==(const Message &rhs) const { return cell == rhs.cell && idx == rhs.idx; }
         __device__ __forceinline__ Message &operator++() {
           if (++idx >= idx_end) next_cell();

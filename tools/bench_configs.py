@@ -50,20 +50,25 @@ CONFIGS = {
                        params=lambda n: {"env_max": 318.0, "radius": 2.0, "death_mod": 10, "birth_mod": 20},
                        pop=lambda n: circles_pop(n, 318.0),
                        what="birth/death stress, [0,318)^3, radius 2: neighbour count + 10 % death + 5 % birth (agent_out) per step"),
+    # small variant for profiling runs (not a BASELINE configuration)
+    "stress_4m": dict(model="stress", agent="Circle", n=4_000_000,
+                      params=lambda n: {"env_max": 159.0, "radius": 2.0, "death_mod": 10, "birth_mod": 20},
+                      pop=lambda n: circles_pop(n, 159.0),
+                      what="birth/death stress, [0,159)^3, radius 2 (profiling size)"),
 }
 
 
-def run_ours(cfg, steps, warmup):
+def run_ours(cfg, steps, warmup, iter_mode=0):
     from flamegpu2_b200 import sim as fsim
 
     n = cfg["n"]
     pop = cfg["pop"](n)
     out = {}
-    s = fsim.Simulation(cfg["model"], device=0, timing=1, **cfg["params"](n))
+    s = fsim.Simulation(cfg["model"], device=0, timing=1, iter_mode=iter_mode, **cfg["params"](n))
     s.set_population(cfg["agent"], pop)
     s.step(warmup)
     s.sync()
-    s.step_times()
+    s.step_times()  # drop the warm-up steps (the first one runs on the unsorted initial population)
     n0 = s.count(cfg["agent"])
     s.step(steps)
     s.sync()
@@ -74,7 +79,7 @@ def run_ours(cfg, steps, warmup):
     out["ms_per_step"] = float(t.mean() * 1e3)
     out["value"] = float(agents / t.mean())
     out["agents_start_end"] = [n0, n1]
-    p = fsim.Simulation(cfg["model"], device=0, profile=1, **cfg["params"](n))
+    p = fsim.Simulation(cfg["model"], device=0, profile=1, iter_mode=iter_mode, **cfg["params"](n))
     p.set_population(cfg["agent"], pop)
     p.step(warmup)
     p.profile()
@@ -109,12 +114,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--iter-mode", type=int, default=0, help="1: opt-in radius-filtered iterator")
     args = ap.parse_args()
     for name, cfg in CONFIGS.items():
-        if args.only and name != args.only:
+        if (args.only and name != args.only) or (not args.only and name == "stress_4m"):
             continue
-        ours, pop = run_ours(cfg, args.steps, args.warmup)
-        line = {"config": name, "workload": cfg["what"], "agents": cfg["n"], "steps": args.steps, "warmup": args.warmup,
+        ours, pop = run_ours(cfg, args.steps, args.warmup, args.iter_mode)
+        line = {"config": name, "iterator_mode": args.iter_mode, "workload": cfg["what"], "agents": cfg["n"], "steps": args.steps, "warmup": args.warmup,
                 "unit": "agent-steps/s", **ours}
         if not args.no_ref:
             # same population trajectory (the models are deterministic), so the same mean agent count
