@@ -133,7 +133,7 @@ class MessageSpatial2D {
         }
         template <typename T>
         __device__ __forceinline__ T location(const char *base) const {
-          const T v = __ldg(reinterpret_cast<const T *>(base) + idx);
+          const T v = __ldg(reinterpret_cast<const T *>(base) + static_cast<unsigned int>(idx));
           return pad ? detail::pad_location<T>() : v;
         }
 
@@ -169,7 +169,7 @@ class MessageSpatial2D {
           if (h == detail::kHashY) return location<T>(loc.y);
           const int s = detail::find_slot(a.msg_in, h);
           if (s < 0 || pad) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<unsigned int>(idx));
         }
         template <typename T, flamegpu::size_type N, unsigned int M>
         __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
@@ -261,11 +261,11 @@ class MessageSpatial2D {
         template <typename T, unsigned int N>
         __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
           const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
-          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + idx);
-          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + idx);
+          if (h == detail::kHashX) return __ldg(reinterpret_cast<const T *>(loc.x) + static_cast<unsigned int>(idx));
+          if (h == detail::kHashY) return __ldg(reinterpret_cast<const T *>(loc.y) + static_cast<unsigned int>(idx));
           const int s = detail::find_slot(a.msg_in, h);
           if (s < 0) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + idx);
+          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<unsigned int>(idx));
         }
         template <typename T, flamegpu::size_type N, unsigned int M>
         __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {

@@ -6,9 +6,10 @@
 
 For each: whole CUDASimulation::step() device time of this repo (per-step CUDA events, working set >> L2),
 a per-phase breakdown from a profiled pass, and the reference's own CUDA build (oracle/_ref/ref_sim) on the same
-input when it is present.  One JSON line per configuration on stdout.
+input when it is present (which is why this script lives under tests/: it runs oracle/_ref).  One JSON line per
+configuration on stdout.
 
-  python tools/bench_configs.py [--only NAME] [--steps K] [--no-ref]
+  python tests/bench_configs.py [--only NAME] [--steps K] [--no-ref]
 """
 import argparse
 import json
@@ -20,7 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def circles_pop(n, L, seed=0):

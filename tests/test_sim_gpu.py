@@ -311,6 +311,38 @@ def test_boids_run_and_stay_in_bounds():
         s.close()
 
 
+def test_radius_filtered_iterator_other_models():
+    # the opt-in iterator on models with births / deaths (stress) and on Boids 3D / 2D: every in-radius message is
+    # presented once in the same relative order, so the results are bit-identical to the reference-order iterator
+    n, L = 40000, 34.0
+    pos = _circles_pop(n, L, seed=7)
+    res = []
+    for m in (0, 1):
+        s = _sim("stress", env_max=L, radius=2.0, death_mod=10, birth_mod=20, iter_mode=m)
+        s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+        s.step(4)
+        res.append([s.get("Circle", v, np.uint32) for v in ("_id", "neighbours", "parent")] + [s.get("Circle", "x", np.float32)])
+        s.close()
+    assert len(res[0][0]) == len(res[1][0]) and len(res[0][0]) != n
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(3)
+    nb = 20000
+    for model, dims in (("boids3d", 3), ("boids2d", 2)):
+        pop = {k: rng.uniform(-0.5, 0.5, nb).astype(np.float32) for k in ("x", "y", "z")[:dims]}
+        for k in ("fx", "fy", "fz")[:dims]:
+            pop[k] = rng.uniform(-0.5, 0.5, nb).astype(np.float32)
+        res = []
+        for m in (0, 1):
+            s = _sim(model, iter_mode=m, stable=1)
+            s.set_population("Boid", pop)
+            s.step(5)
+            res.append([s.get("Boid", k, np.float32) for k in ("x", "y", "fx", "fy")] + [s.get("Boid", "_id", np.uint32)])
+            s.close()
+        for a, b in zip(*res):
+            assert np.array_equal(a, b), model
+
+
 def test_true3d_sort_key_extension():
     # b200 extension: the intended x,y,z sort key (the reference's key collapses z, CUDASimulation.cu:487)
     n, L = 30000, 31.0
