@@ -300,6 +300,9 @@ def main():
         "clocks": clk,
     }
     if rank == 0 and world > 1:
+        if slab_sim is not None and os.environ.get("FGB_SLAB_PROFILE"):
+            rep = slab_sim.phase_report()  # includes the warm-up steps; diagnostic only
+            line["slab_phases_us"] = rep
         print(json.dumps(line), flush=True)
     if rank == 0 and world == 1:
         peak, peak_src = measured_peak()

@@ -198,6 +198,13 @@ int fgbm_end_step(void *h) {
 int fgbm_end_step_pipelined(void *h) {
   return guarded([&] { static_cast<Sim *>(h)->sim->endStepPipelined(); });
 }
+int fgbm_begin_exchange(void *h) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->beginMessageExchange(); });
+}
+int fgbm_end_exchange(void *h, const char *message) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->endMessageExchange(message); });
+}
+void *fgbm_exchange_stream(void *h) { return static_cast<Sim *>(h)->sim->exchangeStream(); }
 int fgbm_refresh_bounds(void *h) {
   return guarded([&] { static_cast<Sim *>(h)->sim->refreshBounds(); });
 }
@@ -213,10 +220,10 @@ int fgbm_list_layout(void *h, int is_message, const char *name, char *buf, size_
   });
 }
 int fgbm_slab_pack(void *h, int is_message, const char *name, const char *geometry_message, int lo, int hi, void *const *dst_lo,
-                   void *const *dst_hi, unsigned int capacity, int remove, unsigned int *d_counts) {
+                   void *const *dst_hi, unsigned int capacity, int remove, unsigned int *d_count_lo, unsigned int *d_count_hi) {
   return guarded([&] {
     static_cast<Sim *>(h)->sim->slabPack(is_message != 0, name, flamegpu::DEFAULT_STATE, geometry_message, lo, hi, dst_lo, dst_hi,
-                                         capacity, remove != 0, d_counts);
+                                         capacity, remove != 0, d_count_lo, d_count_hi);
   });
 }
 int fgbm_list_append(void *h, int is_message, const char *name, unsigned int n_max, const unsigned int *d_n, const void *const *src) {

@@ -336,10 +336,10 @@ class CUDASimulation {
   // Select the items of a list whose position along the slowest axis lies in planes < lo / >= hi
   // (fgb_plane_flags + fgb_compact), packed into caller-provided device buffers (one per variable, list
   // order); returns the two counts.  remove != 0 additionally drops them from the list (agent migration).
-  // Nothing returns to the host: the two counts go to the device words d_counts[0] (lo) and d_counts[1] (hi).
+  // Nothing returns to the host: the two counts go to the device words *d_count_lo and *d_count_hi.
   void slabPack(bool is_message, const std::string &name, const std::string &state, const std::string &geometry_message,
                 int lo, int hi, void *const *dst_lo, void *const *dst_hi, unsigned int capacity, bool remove,
-                unsigned int *d_counts);
+                unsigned int *d_count_lo, unsigned int *d_count_hi);
   // append up to n_max items (actual count in the device word d_n) from device buffers (one per variable,
   // list order) to a list
   void listAppend(bool is_message, const std::string &name, const std::string &state, unsigned int n_max,
@@ -349,6 +349,13 @@ class CUDASimulation {
   // Pipelined variant for the slab driver: the counts of step t are copied to pinned memory asynchronously and
   // consumed one step later, while the GPU is already running step t+1, so the host never drains the device.
   void endStepPipelined();
+  // Message exchange on its own stream (multi-GPU slab driver): between beginMessageExchange() and
+  // endMessageExchange() slabPack / listAppend run on exchangeStream() -- and so does the caller's NCCL traffic --
+  // while the main stream already sorts the agents of the reading layer; endMessageExchange() builds the PBM of
+  // `message` on that stream, and the reading functions wait for it right before their kernels.
+  void beginMessageExchange();
+  void endMessageExchange(const std::string &message);
+  cudaStream_t exchangeStream() const { return index_stream; }
   std::vector<std::pair<std::string, size_t>> listLayout(bool is_message, const std::string &name);
 
   // ---- b200 extensions used by the parity harness / bench (no reference counterpart) -------------
@@ -436,6 +443,7 @@ class CUDASimulation {
   cudaStream_t index_stream = nullptr;   // PBM builds of a layer's input lists (overlapIndexBuild)
   cudaEvent_t index_fork = nullptr, index_done = nullptr;
   bool index_pending = false;
+  bool exchange_active = false;   // slabPack / listAppend target the exchange stream (scratch slot 1)
   unsigned int *d_ctrl = nullptr;
   unsigned int next_slot = 1;
   unsigned int slab_tmp_slot = 0;

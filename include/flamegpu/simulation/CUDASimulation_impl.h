@@ -790,18 +790,21 @@ inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_
     // The PBMs this layer reads do not depend on the layer's own agent lists: build them on the index stream
     // while the functions' streams sort / partition their agents; each reader waits for index_done before its
     // kernel.  (Also orders the build before EVERY reader when several functions of a layer share a list.)
-    index_pending = false;
+    bool forked = false;
     for (auto &f : layer) {
       if (!(f.msg_in && f.msg_in->spatial && f.msg_in->pbm_dirty)) continue;
       const bool overlap = cuda_config.overlapIndexBuild && !cuda_config.profile;
-      if (overlap && !index_pending) {
+      if (overlap && !forked) {
         FGB_CUDA_THROW(cudaEventRecord(index_fork, main));
         FGB_CUDA_THROW(cudaStreamWaitEvent(index_stream, index_fork, 0));
-        index_pending = true;
+        forked = true;
       }
       build_input_index(*f.msg_in, overlap ? index_stream : main);
     }
-    if (index_pending) FGB_CUDA_THROW(cudaEventRecord(index_done, index_stream));
+    if (forked) {
+      FGB_CUDA_THROW(cudaEventRecord(index_done, index_stream));
+      index_pending = true;
+    }
     const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty();
     if (fork) FGB_CUDA_THROW(cudaEventRecord(fork_event, main));
     for (size_t i = 0; i < layer.size(); ++i) {
@@ -812,6 +815,10 @@ inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_
         FGB_CUDA_THROW(cudaEventRecord(join_events[i], st));
         FGB_CUDA_THROW(cudaStreamWaitEvent(main, join_events[i], 0));
       }
+    }
+    if (index_pending) {  // every reader has waited already; this joins the index stream back for everything else
+      FGB_CUDA_THROW(cudaStreamWaitEvent(main, index_done, 0));
+      index_pending = false;
     }
     // host-function layers run between graphs (eager mode only)
     if (!model->layers[li]->host_functions.empty()) {
@@ -895,8 +902,10 @@ inline std::vector<std::pair<std::string, size_t>> CUDASimulation::listLayout(bo
 
 inline void CUDASimulation::slabPack(bool is_message, const std::string &name, const std::string &state,
                                      const std::string &geometry_message, int lo, int hi, void *const *dst_lo, void *const *dst_hi,
-                                     unsigned int capacity, bool remove, unsigned int *d_counts) {
+                                     unsigned int capacity, bool remove, unsigned int *d_count_lo, unsigned int *d_count_hi) {
   initialise();
+  cudaStream_t xs = exchange_active ? index_stream : main_stream;
+  const unsigned int xslot = exchange_active ? 1u : 0u;  // own look-back scratch: the main stream may be sorting
   detail::DevList &l = is_message ? messages.at(name).list : state_list(name, state);
   const detail::CUDAMessage &G = messages.at(geometry_message);
   const int slow = G.desc->dims() - 1;
@@ -904,14 +913,15 @@ inline void CUDASimulation::slabPack(bool is_message, const std::string &name, c
   const int ip = l.index_of(axis);
   if (ip < 0) throw exception::InvalidAgentVar(std::string("list has no position variable '") + axis + "'");
   const unsigned int n = l.bound;
-  FGB_CUDA_THROW(cudaMemsetAsync(d_counts, 0, 8, main_stream));
+  FGB_CUDA_THROW(cudaMemsetAsync(d_count_lo, 0, 4, xs));
+  FGB_CUDA_THROW(cudaMemsetAsync(d_count_hi, 0, 4, xs));
   if (n == 0) return;
   unsigned int *d_n = slot_ptr(l.count_slot);
   for (auto &f : slab_flags) f.reserve(n);
-  FGB_ABI_THROW(fgb_ctx_reserve(ctx, 0, n, 0));
+  FGB_ABI_THROW(fgb_ctx_reserve(ctx, xslot, n, 0));
   FGB_ABI_THROW(fgb_plane_flags(ctx, reinterpret_cast<const float *>(l.data[ip]), n, d_n, G.md.min[slow], G.md.radius,
                                 static_cast<int>(G.md.grid_dim[slow]), lo, hi, slab_flags[0].p, slab_flags[1].p, slab_flags[2].p,
-                                main_stream));
+                                xs));
   for (int side = 0; side < 2; ++side) {
     void *const *dst = side == 0 ? dst_lo : dst_hi;
     if (!dst) continue;
@@ -922,13 +932,13 @@ inline void CUDASimulation::slabPack(bool is_message, const std::string &name, c
       vars[v].in = l.data[v];
       vars[v].out = dst[v];
     }
-    FGB_ABI_THROW(fgb_compact_limited(ctx, 0, slab_flags[side == 0 ? 0 : 2].p, 0, n, d_n, 0, 0, nullptr, capacity, vars.data(),
-                                      static_cast<unsigned int>(vars.size()), d_counts + side, nullptr, main_stream));
+    FGB_ABI_THROW(fgb_compact_limited(ctx, xslot, slab_flags[side == 0 ? 0 : 2].p, 0, n, d_n, 0, 0, nullptr, capacity, vars.data(),
+                                      static_cast<unsigned int>(vars.size()), side == 0 ? d_count_lo : d_count_hi, nullptr, xs));
   }
   if (remove) {
     std::vector<fgb_var> vars = l.vars(true);
-    FGB_ABI_THROW(fgb_compact(ctx, 0, slab_flags[1].p, 0, n, d_n, 0, 0, nullptr, vars.data(), static_cast<unsigned int>(vars.size()),
-                              nullptr, d_n, main_stream));
+    FGB_ABI_THROW(fgb_compact(ctx, xslot, slab_flags[1].p, 0, n, d_n, 0, 0, nullptr, vars.data(), static_cast<unsigned int>(vars.size()),
+                              nullptr, d_n, xs));
     l.swap_buffers();
   }
 }
@@ -937,10 +947,12 @@ inline void CUDASimulation::listAppend(bool is_message, const std::string &name,
                                        const unsigned int *d_n_src, const void *const *src) {
   initialise();
   if (n_max == 0) return;
+  cudaStream_t xs = exchange_active ? index_stream : main_stream;
+  const unsigned int xslot = exchange_active ? 1u : 0u;
   detail::DevList &l = is_message ? messages.at(name).list : state_list(name, state);
   unsigned int *d_n = slot_ptr(l.count_slot);
   if (l.bound + n_max > l.capacity) {
-    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    FGB_CUDA_THROW(cudaDeviceSynchronize());
     l.reserve(l.bound + n_max, l.capacity);
   }
   std::vector<fgb_var> vars(l.names.size());
@@ -951,11 +963,27 @@ inline void CUDASimulation::listAppend(bool is_message, const std::string &name,
   }
   // copy-all compaction: keep_front == n_max keeps every item below the device count; offset and the new
   // size are the list's own device count word
-  FGB_ABI_THROW(fgb_compact(ctx, 0, nullptr, 0, n_max, d_n_src, n_max, 0, d_n, vars.data(), static_cast<unsigned int>(vars.size()),
-                            nullptr, d_n, main_stream));
+  FGB_ABI_THROW(fgb_ctx_reserve(ctx, xslot, n_max, 0));
+  FGB_ABI_THROW(fgb_compact(ctx, xslot, nullptr, 0, n_max, d_n_src, n_max, 0, d_n, vars.data(), static_cast<unsigned int>(vars.size()),
+                            nullptr, d_n, xs));
   l.bound += n_max;
   l.appended_this_step += n_max;
   if (is_message) messages.at(name).pbm_dirty = true;
+}
+
+inline void CUDASimulation::beginMessageExchange() {
+  initialise();
+  FGB_CUDA_THROW(cudaEventRecord(index_fork, main_stream));
+  FGB_CUDA_THROW(cudaStreamWaitEvent(index_stream, index_fork, 0));
+  exchange_active = true;
+}
+
+inline void CUDASimulation::endMessageExchange(const std::string &message) {
+  detail::CUDAMessage &M = messages.at(message);
+  if (M.spatial && M.pbm_dirty) build_input_index(M, index_stream);
+  FGB_CUDA_THROW(cudaEventRecord(index_done, index_stream));
+  index_pending = true;  // consumed (and cleared) by the next record_layers
+  exchange_active = false;
 }
 
 inline void CUDASimulation::refresh_bounds() {
