@@ -1,6 +1,7 @@
 // examples/test_models.cuh -- small models that restate the reference's own black-box tests of the
 // hot path (tests/test_cases/runtime/messaging/test_spatial_{2,3}d.cu, simulation/test_cuda_simulation.cu,
-// runtime/agent/test_device_agent_creation.cu, runtime/agent/detail/test_spatial_agent_sort.cu) so the
+// runtime/agent/test_device_agent_creation.cu, runtime/agent/detail/test_spatial_agent_sort.cu,
+// runtime/messaging/test_bucket.cu) so the
 // same scenario can run on the reference build and on this repo and be compared.
 // FLAME GPU 2 API only.
 #pragma once
@@ -198,6 +199,48 @@ FLAMEGPU_AGENT_FUNCTION(t_cond_death_fn, flamegpu::MessageNone, flamegpu::Messag
 }
 FLAMEGPU_AGENT_FUNCTION_CONDITION(t_cond_mod3) { return FLAMEGPU->getVariable<int>("x") % 3 == 0; }
 
+// ---- test_bucket.cu:54-98 (out_mandatory, out_optional, in, in_range), key base 12 as in the reference test ----
+FLAMEGPU_AGENT_FUNCTION(t_bucket_out, flamegpu::MessageNone, flamegpu::MessageBucket) {
+  const int id = FLAMEGPU->getVariable<int>("id");
+  FLAMEGPU->message_out.setVariable<int>("id", id);
+  FLAMEGPU->message_out.setKey(12 + (id / 2));
+  return flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION(t_bucket_out_optional, flamegpu::MessageNone, flamegpu::MessageBucket) {
+  if (FLAMEGPU->getVariable<int>("do_output")) {
+    const int id = FLAMEGPU->getVariable<int>("id");
+    FLAMEGPU->message_out.setVariable<int>("id", id);
+    FLAMEGPU->message_out.setKey(12 + (id / 2));
+  }
+  return flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION(t_bucket_in, flamegpu::MessageBucket, flamegpu::MessageNone) {
+  const int id = FLAMEGPU->getVariable<int>("id");
+  const int id_m1 = id == 0 ? 0 : id - 1;
+  unsigned int count = 0, sum = 0;
+  for (auto &m : FLAMEGPU->message_in(12 + (id_m1 / 2))) {
+    count++;
+    sum += m.getVariable<int>("id");
+  }
+  FLAMEGPU->setVariable<unsigned int>("count1", count);
+  FLAMEGPU->setVariable<unsigned int>("count2", FLAMEGPU->message_in(12 + (id_m1 / 2)).size());
+  FLAMEGPU->setVariable<unsigned int>("sum", sum);
+  return flamegpu::ALIVE;
+}
+FLAMEGPU_AGENT_FUNCTION(t_bucket_in_range, flamegpu::MessageBucket, flamegpu::MessageNone) {
+  const int id = FLAMEGPU->getVariable<int>("id");
+  const int id_m4 = 12 + ((id / 8) * 4);
+  unsigned int count = 0, sum = 0;
+  for (auto &m : FLAMEGPU->message_in(id_m4, id_m4 + 4)) {
+    count++;
+    sum += m.getVariable<int>("id");
+  }
+  FLAMEGPU->setVariable<unsigned int>("count1", count);
+  FLAMEGPU->setVariable<unsigned int>("count2", FLAMEGPU->message_in(12 + id / 2).size());
+  FLAMEGPU->setVariable<unsigned int>("sum", sum);
+  return flamegpu::ALIVE;
+}
+
 enum TestModel {
   TM_COUNT3D = 0,        // Spatial3DMessageTest.Mandatory
   TM_OPTIONAL3D = 1,     // Spatial3DMessageTest.Optional
@@ -210,7 +253,10 @@ enum TestModel {
   TM_BIRTH_OPTIONAL_DEATH = 8,  // DeviceAgentCreationTest.Optional_Output_SameState_WithDeath
   TM_BIRTH_OTHER_AGENT = 9,     // DeviceAgentCreationTest.Mandatory_Output_DifferentAgent
   TM_CONDITION_SPLIT = 10,      // TestAgentFunctionConditions.SplitAgents
-  TM_CONDITION_DEATH = 11       // condition + death in the same state (order: disabled front, then survivors)
+  TM_CONDITION_DEATH = 11,      // condition + death in the same state (order: disabled front, then survivors)
+  TM_BUCKET = 12,               // BucketMessageTest.Mandatory
+  TM_BUCKET_OPTIONAL = 13,      // BucketMessageTest.Optional / OptionalNone (do_output all zero)
+  TM_BUCKET_RANGE = 14          // BucketMessageTest.Mandatory_Range
 };
 
 struct TestParams {
@@ -219,6 +265,7 @@ struct TestParams {
   float mx[3] = {5, 5, 5};
   float radius = 1.0f;
   unsigned int sort_period = 1;
+  int bucket_upper = 12 + 512;  // bucket models: bounds (12, bucket_upper), reference test: 12 + AGENT_COUNT / 2
 };
 
 inline void define_test_model(flamegpu::ModelDescription &model, const TestParams &p) {
@@ -237,7 +284,20 @@ inline void define_test_model(flamegpu::ModelDescription &model, const TestParam
     message.setRadius(p.radius);
     message.newVariable<flamegpu::id_t>("id");
   }
+  const bool isbucket = p.which == TM_BUCKET || p.which == TM_BUCKET_OPTIONAL || p.which == TM_BUCKET_RANGE;
+  if (isbucket) {
+    flamegpu::MessageBucket::Description message = model.newMessage<flamegpu::MessageBucket>("bucket");
+    message.setBounds(12, p.bucket_upper);  // non-zero lower bound, as the reference test
+    message.newVariable<int>("id");
+  }
   flamegpu::AgentDescription agent = model.newAgent("agent");
+  if (isbucket) {
+    agent.newVariable<int>("id");
+    agent.newVariable<int>("do_output", 1);
+    agent.newVariable<unsigned int>("count1", 0);
+    agent.newVariable<unsigned int>("count2", 0);
+    agent.newVariable<unsigned int>("sum", 0);
+  }
   if (is3d || is2d) {
     agent.newVariable<float>("x");
     agent.newVariable<float>("y");
@@ -349,6 +409,28 @@ inline void define_test_model(flamegpu::ModelDescription &model, const TestParam
       af.setFunctionCondition(t_cond_mod3);
       af.setAllowAgentDeath(true);
       model.newLayer().addAgentFunction(af);
+      break;
+    }
+    case TM_BUCKET:
+    case TM_BUCKET_RANGE:
+      agent.newFunction("out", t_bucket_out).setMessageOutput("bucket");
+      if (p.which == TM_BUCKET) {
+        agent.newFunction("in", t_bucket_in).setMessageInput("bucket");
+        model.newLayer().addAgentFunction(t_bucket_out);
+        model.newLayer().addAgentFunction(t_bucket_in);
+      } else {
+        agent.newFunction("in", t_bucket_in_range).setMessageInput("bucket");
+        model.newLayer().addAgentFunction(t_bucket_out);
+        model.newLayer().addAgentFunction(t_bucket_in_range);
+      }
+      break;
+    case TM_BUCKET_OPTIONAL: {
+      flamegpu::AgentFunctionDescription af = agent.newFunction("out", t_bucket_out_optional);
+      af.setMessageOutput("bucket");
+      af.setMessageOutputOptional(true);
+      agent.newFunction("in", t_bucket_in).setMessageInput("bucket");
+      model.newLayer().addAgentFunction(t_bucket_out_optional);
+      model.newLayer().addAgentFunction(t_bucket_in);
       break;
     }
     default:

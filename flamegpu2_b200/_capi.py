@@ -61,6 +61,10 @@ SIGNATURES = {
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),
     "fgb_build_index": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p]),
+    "fgb_bucket_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fgb_bucket_get_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "fgb_build_index_keys": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_uint,
+                                       C.c_void_p]),
     "fgb_bin_permutation": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_uint, C.c_void_p]),
     "fgb_exclusive_scan_u32": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]),

@@ -86,10 +86,11 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
   src.x = x;
   src.y = y;
   src.z = z;
-  src.keys = nullptr;
-  src.mask = 0;
+  src.keys = reinterpret_cast<const uint32_t *>(x);  // DIMS == 0: `x` carries the integer key array
+  src.key_min = static_cast<uint32_t>(sp->key_min);
+  src.key_span = sp->bin_count;
   src.g = make_geo(sp);
-  const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z)) && vars_in_aligned(vars, nvars);
+  const bool vec = aligned16(x) && (DIMS == 0 || aligned16(y)) && (DIMS != 3 || aligned16(z)) && vars_in_aligned(vars, nvars);
   const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
   const bool stable = (flags & FGB_BUILD_STABLE) != 0;
@@ -181,6 +182,30 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   if (flags & FGB_BUILD_STABLE)
     return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
   return launch_ok();
+}
+}  // namespace
+
+namespace {
+// histogram, PBM, scan look-back words, device metadata copy; frees sp on failure
+int alloc_index_buffers(fgb_spatial *sp) {
+  fgb_spatial_metadata &md = sp->md;
+  const size_t words = static_cast<size_t>(sp->bin_count) + 1;
+  sp->n_state = scan_num_tiles(sp->bin_count);
+  cudaError_t e = cudaMalloc(&sp->d_hist, words * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&md.PBM, words * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_state, static_cast<size_t>(sp->n_state) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_md, sizeof(fgb_spatial_metadata));
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_ctrl, 16);
+  if (e == cudaSuccess) e = cudaMemset(sp->d_hist, 0, words * 4);
+  if (e == cudaSuccess) e = cudaMemset(md.PBM, 0, words * 4);  // MessageSpatial3D.cu:77, MessageBucket.cu:69
+  if (e == cudaSuccess) e = cudaMemset(sp->d_state, 0, static_cast<size_t>(sp->n_state) * 8);
+  if (e == cudaSuccess) e = cudaMemset(sp->d_ctrl, 0, 16);
+  if (e == cudaSuccess) e = cudaMemcpy(sp->d_md, &md, sizeof(md), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    fgb_spatial_destroy(sp);
+    return static_cast<int>(e);
+  }
+  return FGB_OK;
 }
 }  // namespace
 
@@ -284,23 +309,39 @@ fgb_status fgb_spatial_create_window(fgb_ctx *ctx, int dims, const float *env_mi
     return FGB_ERR_INVALID_ARG;
   }
   sp->bin_count = static_cast<unsigned int>(bins);
-  const size_t words = static_cast<size_t>(sp->bin_count) + 1;
-  sp->n_state = scan_num_tiles(sp->bin_count);
-  cudaError_t e = cudaMalloc(&sp->d_hist, words * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&md.PBM, words * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&sp->d_state, static_cast<size_t>(sp->n_state) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&sp->d_md, sizeof(fgb_spatial_metadata));
-  if (e == cudaSuccess) e = cudaMalloc(&sp->d_ctrl, 16);
-  if (e == cudaSuccess) e = cudaMemset(sp->d_hist, 0, words * 4);
-  if (e == cudaSuccess) e = cudaMemset(md.PBM, 0, words * 4);  // MessageSpatial3D.cu:77
-  if (e == cudaSuccess) e = cudaMemset(sp->d_state, 0, static_cast<size_t>(sp->n_state) * 8);
-  if (e == cudaSuccess) e = cudaMemset(sp->d_ctrl, 0, 16);
-  if (e == cudaSuccess) e = cudaMemcpy(sp->d_md, &md, sizeof(md), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    fgb_spatial_destroy(sp);
-    return static_cast<int>(e);
-  }
+  const int r = alloc_index_buffers(sp);
+  if (r) return r;
   *out = sp;
+  return FGB_OK;
+}
+
+/* MessageBucket::CUDAModelHandler (MessageBucket.cu:36-78): keys lower..upper inclusive, bucketCount = upper - lower + 1 */
+fgb_status fgb_bucket_create(fgb_ctx *ctx, int lower_bound, int upper_bound, fgb_spatial **out) {
+  if (!ctx || !out || upper_bound <= lower_bound) return FGB_ERR_INVALID_ARG;
+  const long long bins = static_cast<long long>(upper_bound) - static_cast<long long>(lower_bound) + 1;
+  if (bins >= 0x7FFFFFFFll) return FGB_ERR_INVALID_ARG;
+  fgb_spatial *sp = new (std::nothrow) fgb_spatial();
+  if (!sp) return FGB_ERR_ALLOC;
+  sp->ctx = ctx;
+  sp->dims = 0;
+  std::memset(&sp->md, 0, sizeof(sp->md));
+  sp->md.grid_dim[0] = static_cast<unsigned int>(bins);
+  sp->md.grid_dim[1] = sp->md.grid_dim[2] = 1;
+  sp->key_min = lower_bound;
+  sp->win_begin = 0;
+  sp->win_count = 1;
+  sp->bin_count = static_cast<unsigned int>(bins);
+  const int r = alloc_index_buffers(sp);
+  if (r) return r;
+  *out = sp;
+  return FGB_OK;
+}
+
+fgb_status fgb_bucket_get_bounds(const fgb_spatial *sp, int *min_key, int *max_key_exclusive, const unsigned int **d_pbm) {
+  if (!sp || sp->dims != 0) return FGB_ERR_INVALID_ARG;
+  if (min_key) *min_key = sp->key_min;
+  if (max_key_exclusive) *max_key_exclusive = sp->key_min + static_cast<int>(sp->bin_count);  // MetaData::max, MessageBucket.cu:44
+  if (d_pbm) *d_pbm = sp->md.PBM;
   return FGB_OK;
 }
 
@@ -371,14 +412,27 @@ fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *
     FGB_CHECK(cudaMemsetAsync(sp->md.PBM, 0, (static_cast<size_t>(sp->bin_count) + 1) * 4, st));
     return FGB_OK;
   }
-  if (!x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;
+  if (sp->dims == 0 || !x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;  // bucket lists: fgb_build_index_keys
   if (sp->dims == 3) return build_index_impl<3>(sp, n, d_n, x, y, z, vars, nvars, flags, st);
   return build_index_impl<2>(sp, n, d_n, x, y, nullptr, vars, nvars, flags, st);
 }
 
+/* MessageBucket::CUDAModelHandler::buildIndex (MessageBucket.cu:105-137) */
+fgb_status fgb_build_index_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const int *keys, const fgb_var *vars,
+                                unsigned int nvars, unsigned int flags, void *stream) {
+  if (!sp || sp->dims != 0) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    FGB_CHECK(cudaMemsetAsync(sp->md.PBM, 0, (static_cast<size_t>(sp->bin_count) + 1) * 4, st));
+    return FGB_OK;
+  }
+  if (!keys) return FGB_ERR_INVALID_ARG;
+  return build_index_impl<0>(sp, n, d_n, reinterpret_cast<const float *>(keys), nullptr, nullptr, vars, nvars, flags, st);
+}
+
 fgb_status fgb_bin_permutation(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
                                const float *z, unsigned int *perm_out, unsigned int flags, void *stream) {
-  if (!sp || !perm_out) return FGB_ERR_INVALID_ARG;
+  if (!sp || !perm_out || sp->dims == 0) return FGB_ERR_INVALID_ARG;
   if (n == 0) return FGB_OK;
   if (!x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -48,15 +48,21 @@ constexpr int kBinItems = 4;
 template <int DIMS>  // DIMS 2/3: positions; DIMS 0: key array
 struct KeySrc {
   const float *x, *y, *z;
+  // DIMS == 0 (bucket lists, MessageBucket.cu:49-64): bin = keys[i] - key_min, clamped into [0, key_span) so that
+  // an out-of-range key (a seatbelts-only error in the reference) cannot write outside the histogram
   const uint32_t *keys;
-  uint32_t mask;
+  uint32_t key_min, key_span;
   Geo g;
+  __device__ __forceinline__ uint32_t int_key(uint32_t raw) const {
+    const uint32_t k = raw - key_min;  // below the minimum wraps to a huge value and is clamped as well
+    return k < key_span ? k : key_span - 1u;
+  }
   template <bool VEC>
   __device__ __forceinline__ void load4(uint32_t i0, uint32_t n, uint32_t k[4]) const {
     if (VEC && i0 + 4 <= n) {
       if (DIMS == 0) {
         uint4 q = ld_stream_u4(keys + i0);
-        k[0] = q.x & mask; k[1] = q.y & mask; k[2] = q.z & mask; k[3] = q.w & mask;
+        k[0] = int_key(q.x); k[1] = int_key(q.y); k[2] = int_key(q.z); k[3] = int_key(q.w);
       } else {
         const float4 X = __ldg(reinterpret_cast<const float4 *>(x + i0));
         const float4 Y = __ldg(reinterpret_cast<const float4 *>(y + i0));
@@ -72,7 +78,7 @@ struct KeySrc {
       for (int j = 0; j < 4; ++j) {
         const uint32_t i = i0 + j;
         if (i < n) {
-          if (DIMS == 0) k[j] = __ldg(keys + i) & mask;
+          if (DIMS == 0) k[j] = int_key(__ldg(keys + i));
           else k[j] = bin_key<DIMS == 0 ? 3 : DIMS>(g, __ldg(x + i), __ldg(y + i), DIMS == 3 ? __ldg(z + i) : 0.f);
         } else {
           k[j] = 0xFFFFFFFFu;

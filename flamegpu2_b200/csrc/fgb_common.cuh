@@ -238,6 +238,7 @@ struct fgb_spatial {
   fgb_spatial_metadata md{};
   unsigned int bin_count = 0;
   int win_begin = 0, win_count = 0;  // slab window on the slowest axis (planes stored locally)
+  int key_min = 0;                   // bucket lists (dims == 0): bin = key - key_min
   unsigned int *d_hist = nullptr;       // bin_count + 1, all-zero between builds
   unsigned long long *d_state = nullptr;  // look-back words for the PBM scan
   unsigned int n_state = 0;

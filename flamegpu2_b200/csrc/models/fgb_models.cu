@@ -102,6 +102,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
       p.mx[0] = getf(kv, "max_x", 5.f); p.mx[1] = getf(kv, "max_y", 5.f); p.mx[2] = getf(kv, "max_z", 5.f);
       p.radius = getf(kv, "radius", 1.f);
       p.sort_period = getu(kv, "sort_period", 1);
+      p.bucket_upper = static_cast<int>(getu(kv, "bucket_upper", 12 + 512));
       fgb_examples::define_test_model(*s->model, p);
     } else {
       throw std::runtime_error("unknown model '" + name + "'");

@@ -181,3 +181,43 @@ class Spatial:
         flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT
         _check(lib().fgb_build_index(self.h, n, _ptr(d_n), _ptr(x), _ptr(y), _ptr(z), arr, nv, flags, _stream_ptr()),
                "fgb_build_index")
+
+
+class Bucket:
+    """Index over an integer key range (MessageBucket): PBM of upper - lower + 2 words."""
+
+    def __init__(self, ctx: Context, lower: int, upper: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(lib().fgb_bucket_create(ctx.h, int(lower), int(upper), C.byref(h)), "fgb_bucket_create")
+        self.h = h
+        self.lower, self.upper = int(lower), int(upper)
+        self.bin_count = self.upper - self.lower + 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().fgb_spatial_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bounds(self):
+        mn, mx, p = C.c_int(), C.c_int(), C.c_void_p()
+        _check(lib().fgb_bucket_get_bounds(self.h, C.byref(mn), C.byref(mx), C.byref(p)), "fgb_bucket_get_bounds")
+        return mn.value, mx.value, p.value
+
+    def pbm(self):
+        import numpy as np
+
+        out = np.empty(self.bin_count + 1, dtype=np.uint32)
+        _check(lib().fgb_spatial_read_pbm(self.h, out.ctypes.data_as(C.c_void_p), _stream_ptr()), "fgb_spatial_read_pbm")
+        return out
+
+    def build_index(self, keys, ins, outs, n: int, *, stable=False, d_n=None):
+        arr, nv = make_vars(ins, outs)
+        flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT
+        _check(lib().fgb_build_index_keys(self.h, n, _ptr(d_n), _ptr(keys), arr, nv, flags, _stream_ptr()), "fgb_build_index_keys")

@@ -14,6 +14,7 @@
 #include <array>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
 #include <set>
@@ -44,6 +45,8 @@ FGB_DEF_EXC(InvalidStateName);
 FGB_DEF_EXC(InvalidMessageName);
 FGB_DEF_EXC(InvalidMessageVar);
 FGB_DEF_EXC(InvalidMessageType);
+FGB_DEF_EXC(InvalidMessage);
+FGB_DEF_EXC(ReservedName);
 FGB_DEF_EXC(InvalidArgument);
 FGB_DEF_EXC(InvalidEnvProperty);
 FGB_DEF_EXC(InvalidLayerMember);
@@ -84,7 +87,7 @@ class HostAPI;
 typedef void (*HostFunctionPointer)(HostAPI *);
 typedef bool (*HostConditionPointer)(HostAPI *);
 
-enum class MessageKind { BruteForce, Spatial2D, Spatial3D };
+enum class MessageKind { BruteForce, Spatial2D, Spatial3D, Bucket };
 
 struct MessageData {
   std::string name;
@@ -95,6 +98,9 @@ struct MessageData {
   float max[3] = {0.f, 0.f, 0.f};
   bool min_set[3] = {false, false, false}, max_set[3] = {false, false, false};
   bool persistent = false;
+  // bucket messaging (reference MessageBucket::Data, MessageBucketHost.h:125-130): upper == INT_MAX means "not set"
+  int bucket_lower = 0;
+  int bucket_upper = std::numeric_limits<int>::max();
   int dims() const { return kind == MessageKind::Spatial3D ? 3 : (kind == MessageKind::Spatial2D ? 2 : 0); }
 };
 
@@ -171,7 +177,8 @@ class MessageDescriptionBase {
  protected:
   template <typename T>
   void add(const std::string &name, unsigned int n) {
-    if (name.empty() || name[0] == '_') throw exception::InvalidMessageVar("message variable names may not be empty or begin with '_'");
+    if (!name.empty() && name[0] == '_') throw exception::ReservedName("message variable names may not begin with '_'");
+    if (name.empty()) throw exception::InvalidMessageVar("message variable names may not be empty");
     if (data->variables.count(name)) throw exception::InvalidMessageVar("message '" + data->name + "' already has variable '" + name + "'");
     data->variables.emplace(name, make_variable<T>(n, nullptr));
   }
@@ -238,6 +245,31 @@ class MessageSpatial3D::Description : public MessageSpatial2D::Description {
   float getMaxZ() const { return data->max[2]; }
 };
 
+// reference src/flamegpu/runtime/messaging/MessageBucket.cu:196-224 (setters, validation, the "_key" variable)
+class MessageBucket::Description : public detail::MessageDescriptionBase {
+ public:
+  explicit Description(std::shared_ptr<MessageData> d) : detail::MessageDescriptionBase(std::move(d)) {
+    if (!data->variables.count("_key")) data->variables.emplace("_key", make_variable<IntT>(1, nullptr));
+  }
+  static MessageKind kind() { return MessageKind::Bucket; }
+  void setLowerBound(IntT min) {
+    if (data->bucket_upper != std::numeric_limits<IntT>::max() && min >= data->bucket_upper)
+      throw exception::InvalidArgument("Bucket messaging minimum bound must be lower than upper bound");
+    data->bucket_lower = min;
+  }
+  void setUpperBound(IntT max) {
+    if (max <= data->bucket_lower) throw exception::InvalidArgument("Bucket messaging upperBound bound must be greater than lower bound");
+    data->bucket_upper = max;
+  }
+  void setBounds(IntT min, IntT max) {
+    if (max <= min) throw exception::InvalidArgument("Bucket messaging upperBound bound must be greater than lower bound");
+    data->bucket_lower = min;
+    data->bucket_upper = max;
+  }
+  IntT getLowerBound() const { return data->bucket_lower; }
+  IntT getUpperBound() const { return data->bucket_upper; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // agents and agent functions
 // ---------------------------------------------------------------------------------------------
@@ -299,7 +331,8 @@ class AgentFunctionDescription {
     const MessageKind k = it->second->kind;
     const std::type_index want = k == MessageKind::Spatial3D ? std::type_index(typeid(MessageSpatial3D))
                                : (k == MessageKind::Spatial2D ? std::type_index(typeid(MessageSpatial2D))
-                                                              : std::type_index(typeid(MessageBruteForce)));
+                                  : (k == MessageKind::Bucket ? std::type_index(typeid(MessageBucket))
+                                                              : std::type_index(typeid(MessageBruteForce))));
     if (want != fn_type)
       throw exception::InvalidMessageType(std::string("message ") + what + " type of function '" + function->name + "' does not match message '" + it->first + "'");
   }

@@ -11,6 +11,7 @@
 #include "flamegpu/runtime/DeviceAPI.cuh"
 #include "flamegpu/runtime/detail/FunctionArgs.h"
 #include "flamegpu/runtime/messaging/MessageBruteForce.cuh"
+#include "flamegpu/runtime/messaging/MessageBucket.cuh"
 #include "flamegpu/runtime/messaging/MessageNone.h"
 #include "flamegpu/runtime/messaging/MessageSpatial2D.cuh"
 #include "flamegpu/runtime/messaging/MessageSpatial3D.cuh"

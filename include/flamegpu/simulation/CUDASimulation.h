@@ -185,7 +185,8 @@ struct DevFlags {  // grow-only u32 scan-flag array (one per thread of a functio
 struct CUDAMessage {
   std::shared_ptr<MessageData> desc;
   DevList list;
-  fgb_spatial *spatial = nullptr;
+  fgb_spatial *spatial = nullptr;   // index handler: spatial 2D/3D lists and bucket lists (bucket == true)
+  bool bucket = false;
   fgb_spatial_metadata md{};
   bool pbm_dirty = true;
   bool truncate = true;

@@ -67,6 +67,15 @@ inline void CUDASimulation::initialise() {
       FGB_ABI_THROW(fgb_spatial_get_window(m.spatial, &m.win_begin, &m.win_count));
       unsigned int bins = 0;
       FGB_ABI_THROW(fgb_spatial_get_metadata(m.spatial, &m.md, &bins));
+    } else if (mp.second->kind == MessageKind::Bucket) {
+      // reference MessageBucket::Data validation (CUDASimulation construction throws InvalidMessage when the
+      // upper bound was never set, test_bucket.cu:38-47)
+      if (mp.second->bucket_upper == std::numeric_limits<int>::max())
+        throw exception::InvalidMessage("bucket message '" + mp.first + "' has no upper bound");
+      FGB_ABI_THROW(fgb_bucket_create(ctx, mp.second->bucket_lower, mp.second->bucket_upper, &m.spatial));
+      m.bucket = true;
+      unsigned int bins = 0;
+      FGB_ABI_THROW(fgb_spatial_get_metadata(m.spatial, &m.md, &bins));
     }
   }
   for (auto &ap : model->agents) {
@@ -605,7 +614,12 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     detail::CUDAMessage &M = *f.msg_in;
     M.list.fill_table(a.msg_in);
     a.d_msg_in_count = slot_ptr(M.list.count_slot);
-    if (M.spatial) {
+    if (M.bucket) {
+      // bucket lists: {min, max exclusive} travel in grid_dim[0..1] (MessageBucket.cuh reads them there)
+      a.in_meta.grid_dim[0] = M.desc->bucket_lower;
+      a.in_meta.grid_dim[1] = M.desc->bucket_upper + 1;
+      a.in_meta.pbm = M.md.PBM;
+    } else if (M.spatial) {
       for (int k = 0; k < 3; ++k) {
         a.in_meta.min[k] = M.md.min[k];
         a.in_meta.max[k] = M.md.max[k];
@@ -657,7 +671,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     if (index_pending && f.msg_in && f.msg_in->spatial) FGB_CUDA_THROW(cudaStreamWaitEvent(st, index_done, 0));
     prof_begin("function:" + fn.name, st);
     // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
-    const bool filtered = f.msg_in && f.msg_in->spatial && cuda_config.spatialIterationMode != 0 && fn.func_filtered;
+    const bool filtered = f.msg_in && f.msg_in->spatial && !f.msg_in->bucket && cuda_config.spatialIterationMode != 0 && fn.func_filtered;
     const size_t smem = filtered ? sizeof(uint32_t) * detail::kFilterQueueWords * bs : 0;
     FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(filtered ? fn.func_filtered : fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, smem, st));
     prof_end(st);
@@ -769,6 +783,19 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
 }
 
 inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream_t st) {
+  if (M.bucket) {
+    prof_begin("build_index", st);
+    std::vector<fgb_var> vars = M.list.vars(true);
+    const int ik = M.list.index_of("_key");
+    // also for an empty list: the PBM must read all-zero (reference MessageBucket.cu:108-112)
+    FGB_ABI_THROW(fgb_build_index_keys(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const int *>(M.list.data[ik]),
+                                       vars.data(), static_cast<unsigned int>(vars.size()),
+                                       cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+    if (M.list.bound > 0) M.list.swap_buffers();
+    prof_end(st);
+    M.pbm_dirty = false;
+    return;
+  }
   if (M.list.bound > 0) {
     prof_begin("build_index", st);
     std::vector<fgb_var> vars = M.list.vars(true);

@@ -143,6 +143,20 @@ enum fgb_build_flags {
 fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
                            const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, void *stream);
 
+/* ---- bucket lists (MessageBucket): integer keys instead of positions -------------------------------------
+ * MessageBucket::CUDAModelHandler (src/flamegpu/runtime/messaging/MessageBucket.cu:36-78): keys
+ * lower_bound..upper_bound (inclusive), bucketCount = upper_bound - lower_bound + 1, PBM of bucketCount + 1 words,
+ * zeroed (:69).  The handle is an fgb_spatial (destroy / read_pbm / reserve apply); positional entry points reject it. */
+fgb_status fgb_bucket_create(fgb_ctx *ctx, int lower_bound, int upper_bound, fgb_spatial **out);
+/* MessageBucket::MetaData {min, max (exclusive), PBM} (include/flamegpu/runtime/messaging/MessageBucket.h:40-55) */
+fgb_status fgb_bucket_get_bounds(const fgb_spatial *sp, int *min_key, int *max_key_exclusive, const unsigned int **d_pbm);
+/* MessageBucket::CUDAModelHandler::buildIndex (MessageBucket.cu:105-137): atomicHistogram1D over
+ * keys[i] - min (:49-64), exclusive scan, pbm_reorder of every variable.  keys is the `in` array of the "_key"
+ * variable (also listed in vars).  A key outside the bounds (a seatbelts-only error in the reference, :283-288 of
+ * MessageBucketDevice.cuh) is counted in the nearest valid bucket instead of writing out of bounds. */
+fgb_status fgb_build_index_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const int *keys, const fgb_var *vars,
+                                unsigned int nvars, unsigned int flags, void *stream);
+
 /* B200 extension (no reference counterpart): the permutation that WOULD group `n` points by bin,
  * without moving any payload: perm_out[j] = index of the point at grouped position j, and the
  * handler's PBM receives the bin offsets of the points.  Used by the step scheduler to run an agent

@@ -97,6 +97,34 @@ void orc_build_index(const orc_grid *g, uint32_t n, const float *x, const float 
   free(cursor);
 }
 
+void orc_bucket_build(int32_t lower, int32_t upper, uint32_t n, const int32_t *keys, uint32_t *pbm, uint32_t *perm) {
+  const uint32_t B = (uint32_t)(upper - lower + 1); /* MessageBucket.cu:45 */
+  uint32_t *cursor = (uint32_t *)calloc((size_t)B + 1, sizeof(uint32_t));
+  for (uint32_t i = 0; i < n; ++i) cursor[(uint32_t)(keys[i] - lower)]++; /* :60-62 */
+  uint32_t run = 0;
+  for (uint32_t b = 0; b < B; ++b) {
+    pbm[b] = run;
+    run += cursor[b];
+    cursor[b] = pbm[b];
+  }
+  pbm[B] = run;
+  if (perm)
+    for (uint32_t i = 0; i < n; ++i) perm[cursor[(uint32_t)(keys[i] - lower)]++] = i;
+  free(cursor);
+}
+
+uint32_t orc_bucket_range(int32_t lower, int32_t upper, const uint32_t *pbm, int32_t begin_key, int32_t end_key,
+                          uint32_t *first) {
+  const int32_t mn = lower, mx = upper + 1; /* MetaData::max is exclusive, MessageBucket.cu:42-44 */
+  uint32_t b = 0, e = 0;
+  if (begin_key >= mn && end_key < mx && begin_key <= end_key) { /* MessageBucketDevice.cuh:269 */
+    b = pbm[begin_key - mn];
+    e = pbm[end_key - mn];
+  }
+  if (first) *first = b;
+  return e - b;
+}
+
 void orc_gather(const uint32_t *perm, uint32_t n, uint32_t type_len, const void *in, void *out) {
   const char *src = (const char *)in;
   char *dst = (char *)out;

@@ -53,6 +53,16 @@ void orc_bin_keys(const orc_grid *g, uint32_t n, const float *x, const float *y,
 void orc_build_index(const orc_grid *g, uint32_t n, const float *x, const float *y, const float *z,
                      uint32_t *pbm, uint32_t *perm);
 
+/* MessageBucket (src/flamegpu/runtime/messaging/MessageBucket.cu:36-64,105-137): keys lower..upper inclusive,
+ * bucketCount = upper - lower + 1, hash = key - lower (atomicHistogram1D :49-64), exclusive scan, reorder.
+ * pbm has bucketCount + 1 entries; perm as in orc_build_index (stable).  Keys are expected inside the bounds. */
+void orc_bucket_build(int32_t lower, int32_t upper, uint32_t n, const int32_t *keys, uint32_t *pbm, uint32_t *perm);
+/* MessageBucket::In::Filter (MessageBucketDevice.cuh:264-274): messages [PBM[begin-min], PBM[end-min]) when
+ * begin >= min && end < max && begin <= end, with max = upper + 1 -- so operator()(key) = Filter(key, key + 1)
+ * yields nothing for key == upper (reference behaviour, kept).  Returns the count, *first = first index. */
+uint32_t orc_bucket_range(int32_t lower, int32_t upper, const uint32_t *pbm, int32_t begin_key, int32_t end_key,
+                          uint32_t *first);
+
 /* out[j] = in[perm[j]] for one variable of type_len bytes per item (CUDAScatter.cu:89-104 order) */
 void orc_gather(const uint32_t *perm, uint32_t n, uint32_t type_len, const void *in, void *out);
 

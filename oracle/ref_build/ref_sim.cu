@@ -130,7 +130,12 @@ void dump_messages(flamegpu::CUDASimulation &sim, const std::string &message, in
   flamegpu::detail::CUDAMessage &m = sim.getCUDAMessage(message);
   unsigned int bins = 1;
   unsigned int *d_pbm = nullptr;
-  if (dims == 3) {
+  if (dims == 0) {  // bucket list: MetaData {min, max exclusive, PBM}
+    flamegpu::MessageBucket::MetaData md;
+    cudaMemcpy(&md, m.getMetaDataDevicePtr(), sizeof(md), cudaMemcpyDeviceToHost);
+    bins = static_cast<unsigned int>(md.max - md.min);
+    d_pbm = md.PBM;
+  } else if (dims == 3) {
     flamegpu::MessageSpatial3D::MetaData md;
     cudaMemcpy(&md, m.getMetaDataDevicePtr(), sizeof(md), cudaMemcpyDeviceToHost);
     bins = md.gridDim[0] * md.gridDim[1] * md.gridDim[2];
@@ -218,7 +223,9 @@ int main(int argc, const char **argv) {
       p.mx[0] = getf(kv, "max_x", 5.f); p.mx[1] = getf(kv, "max_y", 5.f); p.mx[2] = getf(kv, "max_z", 5.f);
       p.radius = getf(kv, "radius", 1.f);
       p.sort_period = getu(kv, "sort_period", 1);
+      p.bucket_upper = static_cast<int>(getu(kv, "bucket_upper", 12 + 512));
       msg_dims = (p.which == fgb_examples::TM_COUNT2D || p.which == fgb_examples::TM_WRAP2D) ? 2 : 3;
+      if (p.which >= fgb_examples::TM_BUCKET && p.which <= fgb_examples::TM_BUCKET_RANGE) msg_dims = 0;
       fgb_examples::define_test_model(model, p);
       agent_name = "agent";
     } else {

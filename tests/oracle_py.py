@@ -50,6 +50,7 @@ def lib():
         _lib.orc_sort_max_bit.restype = C.c_int
         _lib.orc_sort_max_bit.argtypes = [C.c_void_p, C.c_int]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_bucket_range.restype = C.c_uint32
     return _lib
 
 
@@ -141,6 +142,22 @@ class Grid:
         lib().orc_circles_step(self.ref, C.c_uint32(len(x)), _p(ids), _p(x), _p(y), _p(z), _p(drift),
                                C.c_float(repulse), C.c_int(int(do_sort)), _p(pbm))
         return ids, x, y, z, drift, pbm
+
+
+def bucket_build(lower, upper, keys):
+    """MessageBucket index: (pbm[upper-lower+2], perm[n]) -- stable"""
+    keys = np.ascontiguousarray(keys, dtype=np.int32)
+    pbm = np.empty(upper - lower + 2, dtype=np.uint32)
+    perm = np.empty(len(keys), dtype=np.uint32)
+    lib().orc_bucket_build(C.c_int32(lower), C.c_int32(upper), C.c_uint32(len(keys)), _p(keys), _p(pbm), _p(perm))
+    return pbm, perm
+
+
+def bucket_range(lower, upper, pbm, begin_key, end_key):
+    """(first index, count) of MessageBucket::In::Filter(begin_key, end_key); operator()(key) is (key, key + 1)"""
+    first = C.c_uint32()
+    n = lib().orc_bucket_range(C.c_int32(lower), C.c_int32(upper), _p(pbm), C.c_int32(begin_key), C.c_int32(end_key), C.byref(first))
+    return int(first.value), int(n)
 
 
 def sort_perm(keys, max_bit):

@@ -191,6 +191,45 @@ def test_bin_permutation_global_and_tile_local(ctx, n, dims):
     sp.close()
 
 
+@pytest.mark.parametrize("stable", [False, True])
+@pytest.mark.parametrize("n,lower,upper,dist", [(1, 0, 1, "uniform"), (1024, 12, 12 + 512, "pairs"), (300007, -50, 4000, "uniform"),
+                                               (250000, 7, 9, "uniform"), (100000, 0, 99999, "sorted")])
+def test_bucket_build_index(ctx, n, lower, upper, dist, stable):
+    # fgb_build_index_keys == MessageBucket::CUDAModelHandler::buildIndex: PBM bit-exact, every variable travels
+    from flamegpu2_b200 import host
+
+    rng = np.random.default_rng(n + upper)
+    if dist == "pairs":
+        keys = (12 + np.arange(n) // 2).astype(np.int32)  # the reference test's keys
+    elif dist == "sorted":
+        keys = np.sort(rng.integers(lower, upper + 1, n)).astype(np.int32)
+    else:
+        keys = rng.integers(lower, upper + 1, n).astype(np.int32)
+    b = host.Bucket(ctx, lower, upper)
+    assert b.bounds()[:2] == (lower, upper + 1)
+    ids = np.arange(n, dtype=np.uint32)
+    arr = (np.arange(n * 3, dtype=np.uint32).reshape(n, 3) * 7)
+    ins = [t(keys), t(ids), t(arr)]
+    outs = [torch.zeros_like(a) for a in ins]
+    b.build_index(ins[0], ins, outs, n, stable=stable)
+    torch.cuda.synchronize()
+    pbm_ref, perm_ref = orc.bucket_build(lower, upper, keys)
+    pbm = b.pbm()
+    assert np.array_equal(pbm, pbm_ref), "PBM must be bit-exact"
+    got = as_u32(outs[1])
+    if stable:
+        assert np.array_equal(got, perm_ref)
+    else:
+        assert np.array_equal(np.sort(got), ids)
+        assert np.array_equal(keys[got] - lower, np.repeat(np.arange(upper - lower + 1), np.diff(pbm.astype(np.int64))))
+    assert np.array_equal(outs[0].cpu().numpy(), keys[got]) and np.array_equal(as_u32(outs[2]).reshape(n, 3), arr[got])
+    # empty list: PBM all zero
+    b.build_index(ins[0], ins, outs, 0)
+    torch.cuda.synchronize()
+    assert not b.pbm().any()
+    b.close()
+
+
 @pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 125001, 3000000])
 def test_exclusive_scan(ctx, n):
     rng = np.random.default_rng(n)

@@ -180,3 +180,36 @@ def test_boids3d_step_vs_reference(tmp_path):
     for k in ("x", "y", "z", "fx", "fy", "fz"):
         assert np.allclose(s.get("Boid", k, np.float32), ref[k], rtol=1e-4, atol=1e-5), k
     s.close()
+
+
+@pytest.mark.parametrize("which", [12, 13, 14])
+def test_bucket_messaging_vs_reference(tmp_path, which):
+    # bucket lists: PBM bit-exact, per-bucket message multisets equal, all (integer) agent results bit-exact
+    n = 4096
+    rng = np.random.default_rng(which)
+    ids = rng.permutation(n).astype(np.int32)  # keys arrive unordered
+    do_out = (rng.integers(0, 2, n) if which == 13 else np.ones(n)).astype(np.int32)
+    upper = 12 + n // 2
+    inp = str(tmp_path / "in.bin")
+    fgbs.write_state(inp, {"id": ids, "do_output": do_out})
+    fgbs.run_ref("test", {"which": which, "bucket_upper": upper}, inp, str(tmp_path / "ref"), steps=1, dump_messages="bucket")
+    ref = fgbs.read_state(str(tmp_path / "ref.agent.bin"))
+    ref_pbm = fgbs.read_state(str(tmp_path / "ref.pbm.bucket.bin"))["_pbm"]
+    ref_msg = fgbs.read_state(str(tmp_path / "ref.msg.bucket.bin"))
+    s = _sim("test", which=which, bucket_upper=upper)
+    s.set_population("agent", {"id": ids, "do_output": do_out})
+    s.step(1)
+    for v in ("id", "count1", "count2", "sum"):
+        assert np.array_equal(s.get("agent", v, np.uint32), ref[v]), v
+    pbm = s.message_pbm("bucket")
+    assert np.array_equal(pbm, ref_pbm), "PBM must match the reference bit-exactly"
+    nm = int(pbm[-1])
+    assert nm == len(ref_msg["id"]) == int(do_out.sum())
+    mid = s.message_variable("bucket", "id", np.uint32, nm)
+    assert _bins_multiset_equal(pbm, mid, ref_msg["id"])
+    assert np.array_equal(s.message_variable("bucket", "_key", np.uint32, nm), ref_msg["_key"])
+    # and the oracle agrees with both
+    sent = do_out.astype(bool)
+    pbm_o, _ = orc.bucket_build(12, upper, 12 + ids[sent] // 2)
+    assert np.array_equal(pbm_o, ref_pbm)
+    s.close()

@@ -78,11 +78,30 @@ def boids2d_case(ctx, n, reps, flush, peak, jitter_bins):
     sp.close()
 
 
+def bucket_case(ctx, n, buckets, reps, flush, peak, order):
+    """MessageBucket build: n messages {_key, id, payload}, keys uniform over `buckets` buckets"""
+    g = torch.Generator(device=DEV)
+    g.manual_seed(9)
+    keys = torch.randint(0, buckets, (n,), generator=g, device=DEV, dtype=torch.int32)
+    if order == "grouped":  # messages written by agents that are themselves ordered by key, slightly perturbed
+        keys = torch.sort(keys).values
+        keys = (keys + torch.randint(-1, 2, (n,), generator=g, device=DEV, dtype=torch.int32)).clamp_(0, buckets - 1)
+    b = host.Bucket(ctx, 0, buckets - 1)
+    ins = [keys, torch.arange(n, dtype=torch.int32, device=DEV), torch.rand(n, generator=g, device=DEV)]
+    outs = [torch.empty_like(a) for a in ins]
+    alg = n * 2 * 12 + 4 * (buckets + 1)
+    med, best = timed(lambda: b.build_index(ins[0], ins, outs, n), reps=reps, flush=flush)
+    print(json.dumps({"op": "bucket_build_index", "n": n, "buckets": buckets, "key_order": order, "us_median": med, "us_best": best,
+                      "alg_bytes": alg, "GBps": alg / med / 1e3, "frac_of_measured_peak": alg / med / 1e3 / peak}), flush=True)
+    b.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="1000000,16777216")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--boids2d", action="store_true", help="only the 2D (Boids) build / permutation cases")
+    ap.add_argument("--bucket", action="store_true", help="only the MessageBucket build cases")
     ap.add_argument("--jitter", type=float, default=None, help="--boids2d: displacement in bins since the list was sorted")
     args = ap.parse_args()
     peaks = {}
@@ -93,6 +112,11 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ctx = host.Context(0)
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=DEV)  # 256 MB > 126 MB L2
+    if args.bucket:
+        for n, buckets in ((1_000_000, 125_000), (16_777_216, 2_097_152)):
+            for order in ("grouped", "random"):
+                bucket_case(ctx, n, buckets, args.reps, flush, peak, order)
+        return
     if args.boids2d:
         for jit in ([args.jitter] if args.jitter is not None else [0.05, 0.7]):
             boids2d_case(ctx, 16_000_000, args.reps, flush, peak, jit)
