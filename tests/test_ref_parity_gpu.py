@@ -182,6 +182,35 @@ def test_boids3d_step_vs_reference(tmp_path):
     s.close()
 
 
+def test_boids2d_steps_vs_reference(tmp_path):
+    # the 2D PBM + 3-strip iterator path (BASELINE config 2 in miniature), one step (agent order -- the 2D sort
+    # key has no collapsed axis -- and PBM bit-exact) and three free-running steps (per-agent state within tolerance)
+    n = 20000
+    rng = np.random.default_rng(21)
+    pop = {k: rng.uniform(-0.5, 0.5, n).astype(np.float32) for k in ("x", "y")}
+    v = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+    v = (v / np.linalg.norm(v, axis=0) * rng.uniform(0.1, 1.0, n)).astype(np.float32)
+    pop.update({"fx": v[0].copy(), "fy": v[1].copy()})
+    params = {"interaction_radius": 0.02, "separation_radius": 0.004}
+    inp = str(tmp_path / "in.bin")
+    fgbs.write_state(inp, pop)
+    for steps in (1, 3):
+        fgbs.run_ref("boids2d", params, inp, str(tmp_path / f"ref{steps}"), steps=steps, dump_messages="location")
+        ref = fgbs.read_state(str(tmp_path / f"ref{steps}.Boid.bin"), F32)
+        s = _sim("boids2d", **params)
+        s.set_population("Boid", pop)
+        s.step(steps)
+        ids = s.get("Boid", "_id", np.uint32)
+        if steps == 1:  # identical inputs: order and PBM are bit-exact; later a 1-ulp difference may move a boid across a bin edge
+            assert np.array_equal(ids, ref["_id"])
+            assert np.array_equal(s.message_pbm("location"), fgbs.read_state(str(tmp_path / "ref1.pbm.location.bin"))["_pbm"])
+        oa, ob = np.argsort(ids), np.argsort(ref["_id"])
+        assert np.array_equal(ids[oa], ref["_id"][ob])
+        for k in ("x", "y", "fx", "fy"):
+            assert np.allclose(s.get("Boid", k, np.float32)[oa], ref[k][ob], rtol=1e-4, atol=1e-5), (k, steps)
+        s.close()
+
+
 @pytest.mark.parametrize("which", [12, 13, 14])
 def test_bucket_messaging_vs_reference(tmp_path, which):
     # bucket lists: PBM bit-exact, per-bucket message multisets equal, all (integer) agent results bit-exact
