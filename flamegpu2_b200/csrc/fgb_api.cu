@@ -525,13 +525,8 @@ fgb_status fgb_compact_limited(fgb_ctx *ctx, unsigned int stream_id, const unsig
   if (r) return r;
   unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
   uint32_t *done = static_cast<uint32_t *>(s.ctrl.p) + 1;
-  const bool vec = aligned16(flags) && vars_in_aligned(vars, nvars);
-  if (vec)
-    k_compact<true><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state,
-                                                   done, d_out_count, d_out_total);
-  else
-    k_compact<false><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt,
-                                                    state, done, d_out_count, d_out_total);
+  k_compact<<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state, done,
+                                           d_out_count, d_out_total);
   ctx->launches += 1;
   return launch_ok();
 }

@@ -28,7 +28,6 @@ inline unsigned int compact_num_tiles(unsigned int n) { return (n + kCmpTile - 1
 // kept items of one round are ranked with a ballot, every store instruction writes one contiguous
 // run of the output: no shared-memory staging and no alignment cases.  (The first version gave each
 // thread 8 consecutive items: vector loads, but eight strided 4-byte stores per variable.)
-template <bool VEC>
 __global__ void __launch_bounds__(kCmpThreads)
 k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const unsigned int *d_n, uint32_t keep_front,
           uint32_t out_offset, const unsigned int *d_out_offset, uint32_t out_limit, const __grid_constant__ VarTable vt,
