@@ -16,6 +16,8 @@ FGB_MAX_VARS = 32
 FGB_BUILD_DEFAULT = 0
 FGB_BUILD_STABLE = 1
 FGB_BUILD_TILE_LOCAL = 2
+FGB_REDUCE_SUM, FGB_REDUCE_MIN, FGB_REDUCE_MAX = 0, 1, 2
+FGB_F32, FGB_F64, FGB_I32, FGB_U32, FGB_I64, FGB_U64 = range(6)
 FGB_ERR_NO_DEVICE = -3
 
 
@@ -61,6 +63,7 @@ SIGNATURES = {
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),
     "fgb_build_index": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p]),
+    "fgb_reduce": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_bucket_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fgb_bucket_get_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "fgb_build_index_keys": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_uint,

@@ -4,12 +4,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <new>
 
 #include "fgb_binsort.cuh"
 #include "fgb_common.cuh"
 #include "fgb_compact.cuh"
 #include "fgb_radix.cuh"
+#include "fgb_reduce.cuh"
 #include "fgb_scan.cuh"
 
 using namespace fgb;
@@ -186,6 +188,22 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
 }  // namespace
 
 namespace {
+template <typename T, typename A>
+int launch_reduce(int op, const void *in, unsigned int n, const unsigned int *d_n, A id_min, A id_max, void *partial, uint32_t *done,
+                  void *d_out, unsigned int blocks, cudaStream_t st) {
+  const T *p = static_cast<const T *>(in);
+  A *pa = static_cast<A *>(partial), *po = static_cast<A *>(d_out);
+  if (op == FGB_REDUCE_SUM)
+    k_reduce<T, A, kOpSum><<<blocks, kRedThreads, 0, st>>>(p, n, d_n, static_cast<A>(0), pa, done, po);
+  else if (op == FGB_REDUCE_MIN)
+    k_reduce<T, A, kOpMin><<<blocks, kRedThreads, 0, st>>>(p, n, d_n, id_min, pa, done, po);
+  else
+    k_reduce<T, A, kOpMax><<<blocks, kRedThreads, 0, st>>>(p, n, d_n, id_max, pa, done, po);
+  return launch_ok();
+}
+}  // namespace
+
+namespace {
 // histogram, PBM, scan look-back words, device metadata copy; frees sp on failure
 int alloc_index_buffers(fgb_spatial *sp) {
   fgb_spatial_metadata &md = sp->md;
@@ -254,6 +272,7 @@ fgb_status fgb_ctx_destroy(fgb_ctx *ctx) {
     s.rs_state.release();
     for (auto &b : s.rs_keys) b.release();
     for (auto &b : s.rs_idx) b.release();
+    s.red.release();
   }
   delete ctx;
   return FGB_OK;
@@ -529,6 +548,46 @@ fgb_status fgb_compact_limited(fgb_ctx *ctx, unsigned int stream_id, const unsig
                                            d_out_count, d_out_total);
   ctx->launches += 1;
   return launch_ok();
+}
+
+fgb_status fgb_reduce(fgb_ctx *ctx, unsigned int stream_id, int op, int dtype, const void *in, unsigned int n,
+                      const unsigned int *d_n, void *d_out, void *stream) {
+  if (!ctx || !d_out || (n && !in) || stream_id >= FGB_MAX_STREAMS || op < FGB_REDUCE_SUM || op > FGB_REDUCE_MAX || dtype < FGB_F32 ||
+      dtype > FGB_U64)
+    return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  int r = reserve_zeroed(s.red, static_cast<size_t>(kRedMaxBlocks) * 8 + 8);
+  if (r) return r;
+  void *partial = s.red.p;
+  uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(s.red.p) + static_cast<size_t>(kRedMaxBlocks) * 8);
+  unsigned int blocks = (n + kRedThreads * 8 - 1) / (kRedThreads * 8);
+  blocks = blocks < 1u ? 1u : (blocks > static_cast<unsigned int>(kRedMaxBlocks) ? static_cast<unsigned int>(kRedMaxBlocks) : blocks);
+  ctx->launches += 1;
+  const bool sum = op == FGB_REDUCE_SUM;
+  switch (dtype) {
+    case FGB_F32:
+      if (sum) return launch_reduce<float, double>(op, in, n, d_n, 0.0, 0.0, partial, done, d_out, blocks, st);
+      return launch_reduce<float, float>(op, in, n, d_n, std::numeric_limits<float>::infinity(), -std::numeric_limits<float>::infinity(),
+                                         partial, done, d_out, blocks, st);
+    case FGB_F64:
+      return launch_reduce<double, double>(op, in, n, d_n, std::numeric_limits<double>::infinity(),
+                                           -std::numeric_limits<double>::infinity(), partial, done, d_out, blocks, st);
+    case FGB_I32:
+      if (sum) return launch_reduce<int, long long>(op, in, n, d_n, 0ll, 0ll, partial, done, d_out, blocks, st);
+      return launch_reduce<int, int>(op, in, n, d_n, std::numeric_limits<int>::max(), std::numeric_limits<int>::lowest(), partial, done,
+                                     d_out, blocks, st);
+    case FGB_U32:
+      if (sum) return launch_reduce<unsigned int, unsigned long long>(op, in, n, d_n, 0ull, 0ull, partial, done, d_out, blocks, st);
+      return launch_reduce<unsigned int, unsigned int>(op, in, n, d_n, std::numeric_limits<unsigned int>::max(), 0u, partial, done, d_out,
+                                                       blocks, st);
+    case FGB_I64:
+      return launch_reduce<long long, long long>(op, in, n, d_n, std::numeric_limits<long long>::max(),
+                                                 std::numeric_limits<long long>::lowest(), partial, done, d_out, blocks, st);
+    default:
+      return launch_reduce<unsigned long long, unsigned long long>(op, in, n, d_n, std::numeric_limits<unsigned long long>::max(), 0ull,
+                                                                   partial, done, d_out, blocks, st);
+  }
 }
 
 fgb_status fgb_scatter_all(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,

@@ -222,6 +222,7 @@ struct fgb_stream_scratch {
   fgb::DevBuf rs_state;     // radix sort: digit histograms + per-pass look-back words
   fgb::DevBuf rs_keys[2];   // radix sort: key ping-pong
   fgb::DevBuf rs_idx[2];    // radix sort: index ping-pong
+  fgb::DevBuf red;          // reductions: per-block partials (8 B each) + done counter
 };
 
 #define FGB_MAX_STREAMS 128

@@ -149,6 +149,18 @@ int fgbm_get_count(void *h, const char *agent, const char *state, unsigned int *
   return guarded([&] { *n = static_cast<Sim *>(h)->sim->getAgentCount(agent, state ? state : flamegpu::DEFAULT_STATE); });
 }
 
+// HostAgentAPI reductions (what a step function calls): op 0 sum, 1 min, 2 max; kind 'f' float, 'i' int, 'u' unsigned
+int fgbm_agent_reduce(void *h, const char *agent, const char *var, int op, char kind, double *out) {
+  return guarded([&] {
+    flamegpu::HostAgentAPI api = static_cast<Sim *>(h)->sim->hostAPI().agent(agent);
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      return static_cast<double>(op == 0 ? api.sum<T>(var) : (op == 1 ? api.min<T>(var) : api.max<T>(var)));
+    };
+    *out = kind == 'f' ? run(float{}) : (kind == 'i' ? run(int{}) : run(static_cast<unsigned int>(0)));
+  });
+}
+
 // Copy one variable of a state list to host memory (bytes = count * type_len, checked).
 int fgbm_get_variable(void *h, const char *agent, const char *state, const char *var, void *host_out, size_t bytes) {
   return guarded([&] {

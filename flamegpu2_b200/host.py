@@ -108,6 +108,27 @@ class Context:
             arr[i].type_len = d.numel() * d.element_size()
         _check(lib().fgb_broadcast_init(self.h, arr, nv, n, out_offset, _stream_ptr()), "fgb_broadcast_init")
 
+    _DTYPES = {torch.float32: _capi.FGB_F32, torch.float64: _capi.FGB_F64, torch.int32: _capi.FGB_I32, torch.int64: _capi.FGB_I64}
+
+    def reduce(self, inp: torch.Tensor, n: int, op: str, *, unsigned=False, d_n=None, stream_id: int = 0):
+        """sum / min / max of inp[:n] on the device; returns a Python number (sums: float or exact int)"""
+        dt = self._DTYPES[inp.dtype]
+        if unsigned:
+            dt = {_capi.FGB_I32: _capi.FGB_U32, _capi.FGB_I64: _capi.FGB_U64}[dt]
+        opc = {"sum": _capi.FGB_REDUCE_SUM, "min": _capi.FGB_REDUCE_MIN, "max": _capi.FGB_REDUCE_MAX}[op]
+        out = torch.zeros(1, dtype=torch.int64, device=inp.device)
+        _check(lib().fgb_reduce(self.h, stream_id, opc, dt, _ptr(inp), n, _ptr(d_n), _ptr(out), _stream_ptr()), "fgb_reduce")
+        raw = out.cpu().numpy()
+        import numpy as np
+
+        if op == "sum":
+            if dt in (_capi.FGB_F32, _capi.FGB_F64):
+                return float(raw.view(np.float64)[0])
+            return int(raw.view(np.uint64)[0]) if unsigned else int(raw[0])
+        view = {_capi.FGB_F32: np.float32, _capi.FGB_F64: np.float64, _capi.FGB_I32: np.int32, _capi.FGB_U32: np.uint32,
+                _capi.FGB_I64: np.int64, _capi.FGB_U64: np.uint64}[dt]
+        return raw.view(view)[0].item()
+
     def sort_keys(self, x, y, z, env_min, env_width, grid_dim, n: int, keys_out: torch.Tensor, d_n=None):
         mn = (C.c_float * 3)(*[float(v) for v in (list(env_min) + [0.0] * 3)[:3]])
         w = (C.c_float * 3)(*[float(v) for v in (list(env_width) + [1.0] * 3)[:3]])

@@ -222,9 +222,9 @@ struct FunctionRT {
 
 class CUDASimulation;
 
-// Host-side API handed to init/step/exit functions (tiny subset of the reference's HostAPI: the
-// reductions are OUT of the hot-path scope; they exist so that the examples' step
-// functions compile and run, and are implemented as a device-to-host copy + host loop).
+// Host-side API handed to init/step/exit functions (subset of the reference's HostAPI).
+// sum / min / max run on the device (fgb_reduce: one kernel, 8 bytes come back) instead of the reference's
+// cub::DeviceReduce + copy (HostAgentAPI.cuh:540-700).
 class HostAgentAPI {
  public:
   HostAgentAPI(CUDASimulation *s, std::string a, std::string st) : sim(s), agent(std::move(a)), state(std::move(st)) {}
@@ -237,8 +237,8 @@ class HostAgentAPI {
   inline T max(const std::string &variable);
 
  private:
-  template <typename T>
-  inline std::vector<T> download(const std::string &variable);
+  template <typename T, typename R>
+  inline R reduce(const std::string &variable, int op);
   CUDASimulation *sim;
   std::string agent, state;
 };
@@ -373,6 +373,7 @@ class CUDASimulation {
   void *getMessageVariableDevicePtr(const std::string &message_name, const std::string &var);
   unsigned int getMessageCount(const std::string &message_name);
   fgb_spatial *getSpatialHandler(const std::string &message_name);
+  HostAPI &hostAPI() { return host_api; }
   unsigned long long getLaunchCount() const { return (ctx ? fgb_launch_count(ctx) : 0ull) + own_launches; }
   unsigned int getGraphCount() const { return static_cast<unsigned int>(graphs.size()); }
   cudaStream_t getStream() const { return main_stream; }
@@ -441,6 +442,7 @@ class CUDASimulation {
   std::vector<cudaStream_t> side_streams;
   std::vector<cudaEvent_t> join_events;
   cudaEvent_t fork_event = nullptr;
+  void *d_reduce_out = nullptr;          // 8-byte result word of HostAgentAPI reductions
   cudaStream_t index_stream = nullptr;   // PBM builds of a layer's input lists (overlapIndexBuild)
   cudaEvent_t index_fork = nullptr, index_done = nullptr;
   bool index_pending = false;

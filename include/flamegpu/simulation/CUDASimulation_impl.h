@@ -29,6 +29,7 @@ inline void CUDASimulation::initialise() {
   FGB_CUDA_THROW(cudaEventCreateWithFlags(&index_fork, cudaEventDisableTiming));
   FGB_CUDA_THROW(cudaEventCreateWithFlags(&index_done, cudaEventDisableTiming));
   FGB_CUDA_THROW(cudaStreamCreateWithFlags(&index_stream, cudaStreamNonBlocking));
+  FGB_CUDA_THROW(cudaMalloc(&d_reduce_out, 8));
   FGB_CUDA_THROW(cudaMalloc(&d_ctrl, kCtrlWords * 4));
   FGB_CUDA_THROW(cudaMemset(d_ctrl, 0, kCtrlWords * 4));
   next_slot = 1;
@@ -220,6 +221,8 @@ inline void CUDASimulation::destroy() {
   if (index_fork) cudaEventDestroy(index_fork);
   if (index_done) cudaEventDestroy(index_done);
   if (index_stream) cudaStreamDestroy(index_stream);
+  if (d_reduce_out) cudaFree(d_reduce_out);
+  d_reduce_out = nullptr;
   fork_event = index_fork = index_done = nullptr;
   index_stream = nullptr;
   if (main_stream) cudaStreamDestroy(main_stream);
@@ -1135,32 +1138,42 @@ inline std::map<std::string, std::pair<double, unsigned int>> CUDASimulation::ge
 // ---- minimal HostAPI -------------------------------------------------------------------------
 inline unsigned int HostAPI::getStepCounter() const { return sim->getStepCounter(); }
 inline unsigned int HostAgentAPI::count() { return sim->getAgentCount(agent, state); }
-template <typename T>
-inline std::vector<T> HostAgentAPI::download(const std::string &variable) {
+namespace detail {
+template <typename T> struct reduce_dtype;
+template <> struct reduce_dtype<float> { static constexpr int value = FGB_F32; using sum_t = double; };
+template <> struct reduce_dtype<double> { static constexpr int value = FGB_F64; using sum_t = double; };
+template <> struct reduce_dtype<int> { static constexpr int value = FGB_I32; using sum_t = long long; };
+template <> struct reduce_dtype<unsigned int> { static constexpr int value = FGB_U32; using sum_t = unsigned long long; };
+template <> struct reduce_dtype<long long> { static constexpr int value = FGB_I64; using sum_t = long long; };
+template <> struct reduce_dtype<unsigned long long> { static constexpr int value = FGB_U64; using sum_t = unsigned long long; };
+}  // namespace detail
+
+// one reduction kernel over the state list's variable (device-resident count), then 8 bytes to the host
+template <typename T, typename R>
+inline R HostAgentAPI::reduce(const std::string &variable, int op) {
+  sim->initialise();
   detail::DevList &l = sim->state_list(agent, state);
   const int i = l.index_of(variable);
   if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
   if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
-  const unsigned int n = sim->read_slot(l.count_slot);
-  std::vector<T> h(n);
-  if (n) FGB_CUDA_THROW(cudaMemcpy(h.data(), l.data[i], static_cast<size_t>(n) * sizeof(T), cudaMemcpyDeviceToHost));
-  return h;
+  FGB_ABI_THROW(fgb_reduce(sim->ctx, 0, op, detail::reduce_dtype<T>::value, l.data[i], l.bound, sim->slot_ptr(l.count_slot),
+                           sim->d_reduce_out, sim->main_stream));
+  R r{};
+  FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(R), cudaMemcpyDeviceToHost, sim->main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
+  return r;
 }
 template <typename T>
 inline T HostAgentAPI::sum(const std::string &variable) {
-  T s = T{};
-  for (const T &v : download<T>(variable)) s += v;
-  return s;
+  return static_cast<T>(reduce<T, typename detail::reduce_dtype<T>::sum_t>(variable, FGB_REDUCE_SUM));
 }
 template <typename T>
 inline T HostAgentAPI::min(const std::string &variable) {
-  std::vector<T> h = download<T>(variable);
-  return h.empty() ? T{} : *std::min_element(h.begin(), h.end());
+  return count() ? reduce<T, T>(variable, FGB_REDUCE_MIN) : T{};
 }
 template <typename T>
 inline T HostAgentAPI::max(const std::string &variable) {
-  std::vector<T> h = download<T>(variable);
-  return h.empty() ? T{} : *std::max_element(h.begin(), h.end());
+  return count() ? reduce<T, T>(variable, FGB_REDUCE_MAX) : T{};
 }
 template <typename T>
 inline T HostEnvironment::getProperty(const std::string &name) { return sim->getEnvironmentProperty<T>(name); }

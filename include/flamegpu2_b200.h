@@ -213,6 +213,16 @@ fgb_status fgb_gather(fgb_ctx *ctx, const unsigned int *position, const fgb_var 
 fgb_status fgb_broadcast_init(fgb_ctx *ctx, const fgb_var *vars, unsigned int nvars, unsigned int n,
                               unsigned int out_offset, void *stream);
 
+/* ---- reductions behind HostAgentAPI::sum / min / max -------------------------------------------------------
+ * include/flamegpu/runtime/agent/HostAgentAPI.cuh:540-700 (cub::DeviceReduce::{Sum,Min,Max} + copy of the result).
+ * d_out receives ONE 8-byte value: sums of FGB_F32/FGB_F64 as double, sums of the integer types as 64-bit integers
+ * of the same signedness; min / max in the element type (low bytes of the word).  An empty input gives the
+ * operation's identity (0 for sums).  Nothing returns to the host; the caller copies the word when it needs it. */
+enum fgb_reduce_op { FGB_REDUCE_SUM = 0, FGB_REDUCE_MIN = 1, FGB_REDUCE_MAX = 2 };
+enum fgb_dtype { FGB_F32 = 0, FGB_F64 = 1, FGB_I32 = 2, FGB_U32 = 3, FGB_I64 = 4, FGB_U64 = 5 };
+fgb_status fgb_reduce(fgb_ctx *ctx, unsigned int stream_id, int op, int dtype, const void *in, unsigned int n,
+                      const unsigned int *d_n, void *d_out, void *stream);
+
 /* ---- automatic spatial agent sort ----------------------------------------------------------- */
 /* calculateSpatialHash kernels (src/flamegpu/simulation/CUDASimulation.cu:335-408):
  * key = floorf(((p-min)/width)*grid_dim) linearised, NOT clamped.  z == NULL for 2D.

@@ -230,6 +230,34 @@ def test_bucket_build_index(ctx, n, lower, upper, dist, stable):
     b.close()
 
 
+@pytest.mark.parametrize("n", [0, 1, 255, 2048, 100003, 3000001])
+def test_reduce_sum_min_max(ctx, n):
+    # fgb_reduce == the reductions behind HostAgentAPI::sum/min/max; integer results exact, float sums accumulated
+    # in double (tolerance: the rounding of the inputs' own sum order is not reproduced) and identical run to run
+    rng = np.random.default_rng(n)
+    cases = [(rng.normal(0, 100, n).astype(np.float32), False), (rng.normal(0, 1e6, n).astype(np.float64), False),
+             (rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), False), (rng.integers(0, 2**32 - 1, n).astype(np.uint32), True),
+             (rng.integers(-2**40, 2**40, n).astype(np.int64), False)]
+    for a, unsigned in cases:
+        d = t(a.view(np.int32) if a.dtype == np.uint32 else a)
+        if n == 0:
+            d = torch.zeros(1, dtype=d.dtype, device=DEV)
+        got = ctx.reduce(d, n, "sum", unsigned=unsigned)
+        if a.dtype.kind == "f":
+            ref = float(a.astype(np.float64).sum())
+            assert abs(got - ref) <= 1e-9 * max(1.0, float(np.abs(a.astype(np.float64)).sum())), a.dtype
+            assert ctx.reduce(d, n, "sum", unsigned=unsigned) == got, "reproducible"
+        else:
+            assert got == int(a.astype(object).sum()) if n else got == 0, a.dtype
+        if n:
+            assert ctx.reduce(d, n, "min", unsigned=unsigned) == a.min().item(), a.dtype
+            assert ctx.reduce(d, n, "max", unsigned=unsigned) == a.max().item(), a.dtype
+    # device-resident count smaller than the bound
+    a = rng.integers(0, 1000, 5000).astype(np.int32)
+    cnt = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    assert ctx.reduce(t(a), 5000, "sum", d_n=cnt) == int(a[:1234].sum())
+
+
 @pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 125001, 3000000])
 def test_exclusive_scan(ctx, n):
     rng = np.random.default_rng(n)

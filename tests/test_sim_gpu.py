@@ -374,6 +374,23 @@ def test_bucket_messaging_reference_tests(which):
         s.close()
 
 
+def test_host_agent_reductions():
+    # HostAgentAPI::sum / min / max (what step functions such as Circles' drift validation call) run on the device
+    n, L = 50000, 37.0
+    pos = _circles_pop(n, L, seed=2)
+    s = _sim("circles", env_max=L, radius=2.0)
+    s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+    s.step(2)
+    drift = s.get("Circle", "drift", np.float32)
+    ids = s.get("Circle", "_id", np.uint32)
+    assert abs(s.agent_reduce("Circle", "drift", "sum", "f") - float(drift.astype(np.float64).sum())) <= 1e-6 * float(drift.sum())
+    assert s.agent_reduce("Circle", "drift", "min", "f") == float(drift.min())
+    assert s.agent_reduce("Circle", "drift", "max", "f") == float(drift.max())
+    assert s.agent_reduce("Circle", "_id", "sum", "u") == float(ids.astype(np.uint64).sum() % (1 << 32))  # sum<unsigned> wraps like T
+    assert s.agent_reduce("Circle", "_id", "max", "u") == float(ids.max())
+    s.close()
+
+
 def test_true3d_sort_key_extension():
     # b200 extension: the intended x,y,z sort key (the reference's key collapses z, CUDASimulation.cu:487)
     n, L = 30000, 31.0
