@@ -63,6 +63,9 @@ SIGNATURES = {
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),
     "fgb_build_index": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p]),
+    "fgb_sort_spatial": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_uint), C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint,
+                                   C.c_void_p, C.c_void_p]),
     "fgb_reduce": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_bucket_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fgb_bucket_get_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),

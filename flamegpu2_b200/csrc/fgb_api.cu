@@ -188,6 +188,58 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
 }  // namespace
 
 namespace {
+// stable LSD radix sort of (key, index) + gather of every variable.  geo != NULL: the keys are computed from the
+// positions in the same pass that builds the digit histograms (and stored to `keys`); otherwise `keys` is read.
+int sort_impl(fgb_ctx *ctx, unsigned int stream_id, unsigned int *keys, int max_bit, unsigned int n, const unsigned int *d_n,
+              const fgb_var *vars, unsigned int nvars, unsigned int *position_out, cudaStream_t st, const float *x, const float *y,
+              const float *z, const SortGeo *geo) {
+  int r = fgb_ctx_reserve(ctx, stream_id, n, max_bit);
+  if (r) return r;
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const RadixPlan plan = make_radix_plan(max_bit);
+  const unsigned int tiles = radix_num_tiles(n);
+  uint32_t *ghist = static_cast<uint32_t *>(s.rs_state.p);
+  uint32_t *perm = position_out ? position_out : static_cast<uint32_t *>(s.perm.p);
+  size_t words = static_cast<size_t>(kRsMaxPasses) * kRsMaxDigits;
+  size_t state_off[kRsMaxPasses];
+  for (int p = 0; p < plan.passes; ++p) {
+    state_off[p] = words;
+    words += static_cast<size_t>(tiles) * (static_cast<size_t>(1) << plan.bits[p]);
+  }
+  FGB_CHECK(cudaMemsetAsync(ghist, 0, words * 4, st));
+  const unsigned int hgrid = std::min<unsigned int>(tiles, 4u * kNumSMs);
+  const uint32_t key_mask = (max_bit >= 32) ? 0xFFFFFFFFu : ((1u << max_bit) - 1u);
+  if (geo) {
+    if (z)
+      k_sort_keys_hist<3><<<hgrid, kRsThreads, 0, st>>>(x, y, z, *geo, n, d_n, keys, key_mask, plan, ghist);
+    else
+      k_sort_keys_hist<2><<<hgrid, kRsThreads, 0, st>>>(x, y, nullptr, *geo, n, d_n, keys, key_mask, plan, ghist);
+  } else {
+    k_radix_hist<<<hgrid, kRsThreads, 0, st>>>(keys, n, d_n, plan, ghist);
+  }
+  for (int p = 0; p < plan.passes; ++p) {
+    const bool last = p == plan.passes - 1;
+    const uint32_t *kin = p == 0 ? keys : static_cast<const uint32_t *>(s.rs_keys[(p - 1) & 1].p);
+    const uint32_t *iin = p == 0 ? nullptr : static_cast<const uint32_t *>(s.rs_idx[(p - 1) & 1].p);
+    uint32_t *kout = last ? nullptr : static_cast<uint32_t *>(s.rs_keys[p & 1].p);
+    uint32_t *iout = last ? perm : static_cast<uint32_t *>(s.rs_idx[p & 1].p);
+    k_radix_onesweep<<<tiles, kRsThreads, 0, st>>>(kin, iin, kout, iout, n, d_n, plan.shift[p], plan.bits[p], key_mask,
+                                                    ghist + p * kRsMaxDigits, ghist + state_off[p]);
+  }
+  ctx->launches += 1 + plan.passes;
+  if (nvars) {
+    VarTable vt;
+    r = make_var_table(vars, nvars, &vt);
+    if (r) return r;
+    if (aligned16(perm) && vars_out_aligned(vars, nvars))
+      k_gather<true><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    else
+      k_gather<false><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
+    ctx->launches += 1;
+  }
+  return launch_ok();
+}
+
 template <typename T, typename A>
 int launch_reduce(int op, const void *in, unsigned int n, const unsigned int *d_n, A id_min, A id_max, void *partial, uint32_t *done,
                   void *d_out, unsigned int blocks, cudaStream_t st) {
@@ -660,45 +712,23 @@ fgb_status fgb_sort_by_key(fgb_ctx *ctx, unsigned int stream_id, const unsigned 
                            unsigned int *position_out, void *stream) {
   if (!ctx || stream_id >= FGB_MAX_STREAMS || max_bit < 1 || max_bit > 30 || (n && !keys)) return FGB_ERR_INVALID_ARG;
   if (n == 0) return FGB_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int r = fgb_ctx_reserve(ctx, stream_id, n, max_bit);
-  if (r) return r;
-  fgb_stream_scratch &s = ctx->slot[stream_id];
-  const RadixPlan plan = make_radix_plan(max_bit);
-  const unsigned int tiles = radix_num_tiles(n);
-  uint32_t *ghist = static_cast<uint32_t *>(s.rs_state.p);
-  uint32_t *perm = position_out ? position_out : static_cast<uint32_t *>(s.perm.p);
-  size_t words = static_cast<size_t>(kRsMaxPasses) * kRsMaxDigits;
-  size_t state_off[kRsMaxPasses];
-  for (int p = 0; p < plan.passes; ++p) {
-    state_off[p] = words;
-    words += static_cast<size_t>(tiles) * (static_cast<size_t>(1) << plan.bits[p]);
-  }
-  FGB_CHECK(cudaMemsetAsync(ghist, 0, words * 4, st));
-  const unsigned int hgrid = std::min<unsigned int>(tiles, 4u * kNumSMs);
-  k_radix_hist<<<hgrid, kRsThreads, 0, st>>>(keys, n, d_n, plan, ghist);
-  const uint32_t key_mask = (max_bit >= 32) ? 0xFFFFFFFFu : ((1u << max_bit) - 1u);
-  for (int p = 0; p < plan.passes; ++p) {
-    const bool last = p == plan.passes - 1;
-    const uint32_t *kin = p == 0 ? keys : static_cast<const uint32_t *>(s.rs_keys[(p - 1) & 1].p);
-    const uint32_t *iin = p == 0 ? nullptr : static_cast<const uint32_t *>(s.rs_idx[(p - 1) & 1].p);
-    uint32_t *kout = last ? nullptr : static_cast<uint32_t *>(s.rs_keys[p & 1].p);
-    uint32_t *iout = last ? perm : static_cast<uint32_t *>(s.rs_idx[p & 1].p);
-    k_radix_onesweep<<<tiles, kRsThreads, 0, st>>>(kin, iin, kout, iout, n, d_n, plan.shift[p], plan.bits[p], key_mask,
-                                                    ghist + p * kRsMaxDigits, ghist + state_off[p]);
-  }
-  ctx->launches += 1 + plan.passes;
-  if (nvars) {
-    VarTable vt;
-    r = make_var_table(vars, nvars, &vt);
-    if (r) return r;
-    if (aligned16(perm) && vars_out_aligned(vars, nvars))
-      k_gather<true><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
-    else
-      k_gather<false><<<bin_grid(n), kBinThreads, 0, st>>>(perm, n, d_n, vt);
-    ctx->launches += 1;
-  }
-  return launch_ok();
+  return sort_impl(ctx, stream_id, const_cast<unsigned int *>(keys), max_bit, n, d_n, vars, nvars, position_out,
+                   static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
+}
+
+fgb_status fgb_sort_spatial(fgb_ctx *ctx, unsigned int stream_id, const float *x, const float *y, const float *z,
+                            const float *env_min, const float *env_width, const unsigned int *grid_dim, int max_bit,
+                            unsigned int n, const unsigned int *d_n, unsigned int *keys_out, const fgb_var *vars,
+                            unsigned int nvars, unsigned int *position_out, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || max_bit < 1 || max_bit > 30 || !x || !y || !env_min || !env_width || !grid_dim ||
+      !keys_out)
+    return FGB_ERR_INVALID_ARG;
+  if (n == 0) return FGB_OK;
+  SortGeo g{};
+  g.min0 = env_min[0]; g.min1 = env_min[1]; g.min2 = z ? env_min[2] : 0.f;
+  g.w0 = env_width[0]; g.w1 = env_width[1]; g.w2 = z ? env_width[2] : 1.f;
+  g.g0 = grid_dim[0]; g.g1 = grid_dim[1]; g.g2 = z ? grid_dim[2] : 1u;
+  return sort_impl(ctx, stream_id, keys_out, max_bit, n, d_n, vars, nvars, position_out, static_cast<cudaStream_t>(stream), x, y, z, &g);
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 //   a 12-bit key needs 2 passes and a 17-bit key 2 passes (CUB: 8-bit digits, 2 and 3 passes).
 #pragma once
 #include "fgb_common.cuh"
+#include "fgb_compact.cuh"  // SortGeo, sort_key
 
 namespace fgb {
 
@@ -61,6 +62,42 @@ __global__ void __launch_bounds__(kRsThreads) k_radix_hist(const uint32_t *__res
     const uint32_t i = base + threadIdx.x;
     const bool valid = i < n;
     const uint32_t k = valid ? ld_stream_u32(keys + i) : 0u;
+    for (int p = 0; p < plan.passes; ++p) {
+      const uint32_t d = (k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
+      if (valid && lane == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&sh[p][d], static_cast<uint32_t>(__popc(peers)));
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < plan.passes; ++p)
+    for (int d = threadIdx.x; d < (1 << plan.bits[p]); d += kRsThreads) {
+      const uint32_t c = sh[p][d];
+      if (c) atomicAdd(ghist + p * kRsMaxDigits + d, c);
+    }
+}
+
+// calculateSpatialHash (CUDASimulation.cu:376-408) fused with the digit histograms: the key of every agent is
+// computed, stored (it is the agent's _auto_sort_bin_index) and counted in the same pass.
+template <int DIMS>
+__global__ void __launch_bounds__(kRsThreads) k_sort_keys_hist(const float *__restrict__ x, const float *__restrict__ y,
+                                                               const float *__restrict__ z, SortGeo g, uint32_t n_max,
+                                                               const unsigned int *d_n, uint32_t *__restrict__ keys,
+                                                               uint32_t key_mask, RadixPlan plan, uint32_t *ghist) {
+  __shared__ uint32_t sh[kRsMaxPasses][kRsMaxDigits];
+  for (int i = threadIdx.x; i < kRsMaxPasses * kRsMaxDigits; i += kRsThreads) (&sh[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t stride = gridDim.x * kRsThreads;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * kRsThreads; base < n; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t k = 0u;
+    if (valid) {
+      k = sort_key<DIMS>(g, __ldg(x + i), __ldg(y + i), DIMS == 3 ? __ldg(z + i) : 0.f);
+      keys[i] = k;
+      k &= key_mask;
+    }
     for (int p = 0; p < plan.passes; ++p) {
       const uint32_t d = (k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
       const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);

@@ -136,6 +136,15 @@ class Context:
         _check(lib().fgb_sort_keys(self.h, _ptr(x), _ptr(y), _ptr(z), mn, w, g, n, _ptr(d_n), _ptr(keys_out),
                                    _stream_ptr()), "fgb_sort_keys")
 
+    def sort_spatial(self, x, y, z, env_min, env_width, grid_dim, max_bit: int, keys_out: torch.Tensor, ins, outs, n: int,
+                     position_out=None, d_n=None, stream_id: int = 0):
+        arr, nv = make_vars(ins, outs)
+        mn = (C.c_float * 3)(*[float(v) for v in env_min])
+        wd = (C.c_float * 3)(*[float(v) for v in env_width])
+        gd = (C.c_uint * 3)(*[int(v) for v in grid_dim])
+        _check(lib().fgb_sort_spatial(self.h, stream_id, _ptr(x), _ptr(y), _ptr(z), mn, wd, gd, max_bit, n, _ptr(d_n), _ptr(keys_out),
+                                      arr, nv, _ptr(position_out), _stream_ptr()), "fgb_sort_spatial")
+
     def sort_by_key(self, keys: torch.Tensor, max_bit: int, ins, outs, n: int, position_out=None, d_n=None,
                     stream_id: int = 0):
         arr, nv = make_vars(ins, outs)

@@ -35,6 +35,11 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
   // function condition: the agents that failed it sit at the front of the list and do not execute
   // (reference CUDAFatAgent::processFunctionCondition, CUDAFatAgent.cu:186-236)
   const unsigned int offset = args.d_agent_offset ? __ldg(args.d_agent_offset) : 0u;
+  if (MessageOut::HAS_OUTPUT) {
+    // mandatory output into an emptied list: every executing agent writes exactly one message, so the count is
+    // known here (the reference derives it on the host, CUDAMessage.cu:196-205; a separate 1-thread kernel before)
+    if (index == 0 && args.d_msg_out_count) *args.d_msg_out_count = n > offset ? n - offset : 0u;
+  }
   if (index + offset >= n) return;
   // Run agents in the bin order of the input list when the scheduler provides it: lanes of a warp then
   // walk the same message strips (coalesced / broadcast loads).  Every per-agent slot (variables, scan

@@ -75,6 +75,8 @@ struct FunctionArgs {
   SpatialMeta in_meta;
   const unsigned int *d_msg_in_count;   // brute-force style inputs
   const unsigned int *d_msg_out_offset; // append offset of the output list (NULL -> 0)
+  unsigned int *d_msg_out_count;        // non-NULL: mandatory output into a truncated list, the kernel itself publishes
+                                        // the list's new count (= number of executing agents)
   unsigned int *death_flag;      // scan flags, one per thread (NULL when the feature is off)
   unsigned int *msg_out_flag;
   unsigned int *agent_out_flag;

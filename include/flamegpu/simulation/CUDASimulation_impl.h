@@ -547,10 +547,10 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     const int ix = L.index_of("x"), iy = L.index_of("y"), iz = f.sort_dims == 3 ? L.index_of("z") : -1;
     const int ik = L.index_of("_auto_sort_bin_index");
     unsigned int *keys = reinterpret_cast<unsigned int *>(L.data[ik]);
-    FGB_ABI_THROW(fgb_sort_keys(ctx, reinterpret_cast<const float *>(L.data[ix]), reinterpret_cast<const float *>(L.data[iy]),
-                                iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, mn, width, gd, n, d_n, keys, st));
     std::vector<fgb_var> vars = L.vars(true);
-    FGB_ABI_THROW(fgb_sort_by_key(ctx, sid, keys, max_bit, n, d_n, vars.data(), static_cast<unsigned int>(vars.size()), nullptr, st));
+    FGB_ABI_THROW(fgb_sort_spatial(ctx, sid, reinterpret_cast<const float *>(L.data[ix]), reinterpret_cast<const float *>(L.data[iy]),
+                                   iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, mn, width, gd, max_bit, n, d_n, keys,
+                                   vars.data(), static_cast<unsigned int>(vars.size()), nullptr, st));
     L.swap_buffers();
     prof_end(st);
   }
@@ -645,6 +645,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     if (fn.message_output_optional) {
       f.msg_flag.reserve(n);
       a.msg_out_flag = f.msg_flag.p;
+    } else if (f.msg_out->truncate) {
+      a.d_msg_out_count = slot_ptr(O.count_slot);  // published by the function kernel itself (step 5)
     }
   }
   if (f.out_agent) {
@@ -692,9 +694,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
                                 static_cast<unsigned int>(vars.size()), nullptr, d_mc, st));
       O.list.bound = (O.truncate ? 0u : O.list.bound) + n;
     } else if (O.truncate) {
-      O.list.swap_buffers();
-      detail::k_copy_word<<<1, 1, 0, st>>>(d_mc, d_exec);
-      ++own_launches;
+      O.list.swap_buffers();  // the count word was written by the function kernel (FunctionArgs::d_msg_out_count)
       O.list.bound = n;
     } else {
       std::vector<fgb_var> vars = O.list.vars(false);

@@ -240,6 +240,15 @@ fgb_status fgb_sort_by_key(fgb_ctx *ctx, unsigned int stream_id, const unsigned 
                            unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars,
                            unsigned int *position_out, void *stream);
 
+/* fgb_sort_keys + fgb_sort_by_key in one call (the whole of CUDASimulation::spatialSortAgent_async,
+ * CUDASimulation.cu:463-573): the key of every agent is computed, stored to keys_out (the agent's
+ * _auto_sort_bin_index, which is also listed in vars and therefore travels with the sort) and counted into the digit
+ * histograms in ONE pass; results are identical to the two separate calls. */
+fgb_status fgb_sort_spatial(fgb_ctx *ctx, unsigned int stream_id, const float *x, const float *y, const float *z,
+                            const float *env_min, const float *env_width, const unsigned int *grid_dim, int max_bit,
+                            unsigned int n, const unsigned int *d_n, unsigned int *keys_out, const fgb_var *vars,
+                            unsigned int nvars, unsigned int *position_out, void *stream);
+
 /* Scratch (look-back words, histograms, permutations) grows on demand with cudaMalloc, which is
  * not allowed during CUDA stream capture: reserve for the largest n / max_bit up front (or run
  * one warm-up call outside the capture).  stream_id < 128 selects the scratch slot, like the

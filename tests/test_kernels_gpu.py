@@ -372,6 +372,13 @@ def test_agent_sort(ctx, n, true3d):
     assert np.array_equal(outs[0].cpu().numpy(), pos[0][perm_ref])
     if n == 4:
         assert list(as_u32(outs[3])) == [3, 2, 1, 0]
+    # the fused entry point (keys computed inside the histogram pass) gives the same keys and the same order
+    keys2 = torch.zeros(n, dtype=torch.int32, device=DEV)
+    outs2 = [torch.zeros_like(a) for a in ins2]
+    pos2 = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ctx.sort_spatial(ins[0], ins[1], ins[2], mn, w, gd, mb, keys2, ins2, outs2, n, position_out=pos2)
+    assert np.array_equal(as_u32(keys2), keys_ref) and np.array_equal(as_u32(pos2), perm_ref)
+    assert np.array_equal(as_u32(outs2[3]), order[perm_ref])
     # compaction right after a sort on the same scratch slot
     flags = (rng.random(n) < 0.5).astype(np.uint32)
     cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
