@@ -118,6 +118,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->CUDAConfig().binOrderExecution = getu(kv, "bin_order", 1) != 0;
     s->sim->CUDAConfig().spatialIterationMode = static_cast<int>(getu(kv, "iter_mode", 0));
     s->sim->CUDAConfig().overlapIndexBuild = getu(kv, "overlap", 1) != 0;
+    s->sim->CUDAConfig().agentFunctionBlockSize = static_cast<int>(getu(kv, "block", 128));
     s->sim->CUDAConfig().tileLocalExecOrder = getu(kv, "tile_order", 1) != 0;
     *out = s.release();
   });

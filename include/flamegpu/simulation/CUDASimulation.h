@@ -283,6 +283,7 @@ class CUDASimulation {
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
     int spatialIterationMode = 0;     // b200: 0 reference order, 1 radius-filtered lock-step walk (FunctionArgs.h)
     bool binOrderExecution = true;    // b200: run functions that read spatial messages in bin order
+    int agentFunctionBlockSize = 128;  // b200: threads per block of the agent function kernels
     bool tileLocalExecOrder = true;   // b200: bin-order execution groups inside 2048-agent tiles when the list was just sorted
     bool overlapIndexBuild = true;    // b200: build the input list's PBM on a second stream while the agents are sorted
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())

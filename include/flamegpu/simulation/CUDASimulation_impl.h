@@ -672,7 +672,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   // 4. the agent function itself
   {
     void *kargs[] = {&a};
-    const unsigned int bs = static_cast<unsigned int>(f.block_size);
+    const unsigned int bs = static_cast<unsigned int>(cuda_config.agentFunctionBlockSize > 0 ? cuda_config.agentFunctionBlockSize : f.block_size);
     if (index_pending && f.msg_in && f.msg_in->spatial) FGB_CUDA_THROW(cudaStreamWaitEvent(st, index_done, 0));
     prof_begin("function:" + fn.name, st);
     // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
