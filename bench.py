@@ -226,8 +226,8 @@ def main():
         planes_per_rank = int(np.ceil(L / RADIUS))
         planes = planes_per_rank * world
         Lz = float(planes * RADIUS)
-        halo_cap = int(2 * n // planes_per_rank + 8192)      # a boundary plane holds ~n/planes_per_rank messages
-        mig_cap = int(n // planes_per_rank // 4 + 4096)       # a few percent of a plane changes slab per step
+        halo_cap = int(3 * n // planes_per_rank + 8192)      # a boundary plane holds ~n/planes_per_rank messages (3x: clustering)
+        mig_cap = int(n // planes_per_rank // 2 + 4096)       # a few percent of a plane changes slab per step
         slab_sim = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, planes, halo_capacity=halo_cap,
                                        migrate_capacity=mig_cap, env_max=L, env_max_z=Lz, radius=RADIUS, repulse=REPULSE,
                                        stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode, overlap=args.overlap, tile_order=args.tile_order, block=args.block)
