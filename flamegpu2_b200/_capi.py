@@ -67,6 +67,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_uint), C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint,
                                    C.c_void_p, C.c_void_p]),
     "fgb_reduce": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgb_transform_reduce": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "fgb_bucket_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fgb_bucket_get_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "fgb_build_index_keys": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(fgb_var), C.c_uint, C.c_uint,

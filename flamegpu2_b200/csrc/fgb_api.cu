@@ -240,6 +240,20 @@ int sort_impl(fgb_ctx *ctx, unsigned int stream_id, unsigned int *keys, int max_
   return launch_ok();
 }
 
+// count of elements equal to `value` (as unsigned long long) or sum of squared deviations from `mean` (as double)
+template <typename T>
+int launch_transform_reduce(int transform, const void *in, unsigned int n, const unsigned int *d_n, double mean, T value, void *partial,
+                            uint32_t *done, void *d_out, unsigned int blocks, cudaStream_t st) {
+  const T *p = static_cast<const T *>(in);
+  if (transform == FGB_TRANSFORM_COUNT_EQUAL)
+    k_reduce<T, unsigned long long, kOpSum, kTrEqual><<<blocks, kRedThreads, 0, st>>>(
+        p, n, d_n, 0ull, static_cast<unsigned long long *>(partial), done, static_cast<unsigned long long *>(d_out), 0.0, value);
+  else
+    k_reduce<T, double, kOpSum, kTrSqDev><<<blocks, kRedThreads, 0, st>>>(p, n, d_n, 0.0, static_cast<double *>(partial), done,
+                                                                             static_cast<double *>(d_out), mean, T());
+  return launch_ok();
+}
+
 template <typename T, typename A>
 int launch_reduce(int op, const void *in, unsigned int n, const unsigned int *d_n, A id_min, A id_max, void *partial, uint32_t *done,
                   void *d_out, unsigned int blocks, cudaStream_t st) {
@@ -639,6 +653,32 @@ fgb_status fgb_reduce(fgb_ctx *ctx, unsigned int stream_id, int op, int dtype, c
     default:
       return launch_reduce<unsigned long long, unsigned long long>(op, in, n, d_n, std::numeric_limits<unsigned long long>::max(), 0ull,
                                                                    partial, done, d_out, blocks, st);
+  }
+}
+
+fgb_status fgb_transform_reduce(fgb_ctx *ctx, unsigned int stream_id, int transform, int dtype, const void *in, unsigned int n,
+                                const unsigned int *d_n, const void *param, void *d_out, void *stream) {
+  if (!ctx || !d_out || !param || (n && !in) || stream_id >= FGB_MAX_STREAMS || dtype < FGB_F32 || dtype > FGB_U64 ||
+      (transform != FGB_TRANSFORM_COUNT_EQUAL && transform != FGB_TRANSFORM_SUM_SQ_DEV))
+    return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  int r = reserve_zeroed(s.red, static_cast<size_t>(kRedMaxBlocks) * 8 + 8);
+  if (r) return r;
+  void *partial = s.red.p;
+  uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(s.red.p) + static_cast<size_t>(kRedMaxBlocks) * 8);
+  unsigned int blocks = (n + kRedThreads * 8 - 1) / (kRedThreads * 8);
+  blocks = blocks < 1u ? 1u : (blocks > static_cast<unsigned int>(kRedMaxBlocks) ? static_cast<unsigned int>(kRedMaxBlocks) : blocks);
+  ctx->launches += 1;
+  const double mean = transform == FGB_TRANSFORM_SUM_SQ_DEV ? *static_cast<const double *>(param) : 0.0;
+  const bool cnt = transform == FGB_TRANSFORM_COUNT_EQUAL;
+  switch (dtype) {
+    case FGB_F32: return launch_transform_reduce<float>(transform, in, n, d_n, mean, cnt ? *static_cast<const float *>(param) : 0.f, partial, done, d_out, blocks, st);
+    case FGB_F64: return launch_transform_reduce<double>(transform, in, n, d_n, mean, cnt ? *static_cast<const double *>(param) : 0.0, partial, done, d_out, blocks, st);
+    case FGB_I32: return launch_transform_reduce<int>(transform, in, n, d_n, mean, cnt ? *static_cast<const int *>(param) : 0, partial, done, d_out, blocks, st);
+    case FGB_U32: return launch_transform_reduce<unsigned int>(transform, in, n, d_n, mean, cnt ? *static_cast<const unsigned int *>(param) : 0u, partial, done, d_out, blocks, st);
+    case FGB_I64: return launch_transform_reduce<long long>(transform, in, n, d_n, mean, cnt ? *static_cast<const long long *>(param) : 0ll, partial, done, d_out, blocks, st);
+    default: return launch_transform_reduce<unsigned long long>(transform, in, n, d_n, mean, cnt ? *static_cast<const unsigned long long *>(param) : 0ull, partial, done, d_out, blocks, st);
   }
 }
 

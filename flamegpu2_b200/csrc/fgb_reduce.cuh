@@ -22,16 +22,30 @@ __device__ __forceinline__ A red_combine(A a, A b) {
   return b > a ? b : a;
 }
 
+// element transforms applied before a SUM: none, "== value" (thrust::count, HostAgentAPI.cuh:700-718) and
+// "(x - mean)^2" (standard_deviation_subtract_mean, HostAgentAPI.cuh:598-600)
+enum { kTrNone = 0, kTrEqual = 1, kTrSqDev = 2 };
+template <typename T, typename A, int TR>
+__device__ __forceinline__ A red_transform(T v, double param, T tvalue) {
+  if (TR == kTrEqual) return static_cast<A>(v == tvalue ? 1 : 0);
+  if (TR == kTrSqDev) {
+    const double d = static_cast<double>(v) - param;
+    return static_cast<A>(d * d);
+  }
+  return static_cast<A>(v);
+}
+
 // T: element type; A: accumulator (double for floating-point sums, else T widened to 64 bits for integer sums)
-template <typename T, typename A, int OP>
+template <typename T, typename A, int OP, int TR = kTrNone>
 __global__ void __launch_bounds__(kRedThreads)
-k_reduce(const T *__restrict__ in, uint32_t n_max, const unsigned int *d_n, A identity, A *partial, uint32_t *done, A *out) {
+k_reduce(const T *__restrict__ in, uint32_t n_max, const unsigned int *d_n, A identity, A *partial, uint32_t *done, A *out,
+         double tparam = 0.0, T tvalue = T()) {
   __shared__ A s_warp[kRedThreads / 32];
   __shared__ uint32_t s_last;
   const uint32_t n = load_count(d_n, n_max);
   A acc = identity;
   for (uint32_t i = blockIdx.x * kRedThreads + threadIdx.x; i < n; i += gridDim.x * kRedThreads)
-    acc = red_combine<A, OP>(acc, static_cast<A>(in[i]));
+    acc = red_combine<A, OP>(acc, red_transform<T, A, TR>(in[i], tparam, tvalue));
   auto block_reduce = [&](A v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = red_combine<A, OP>(v, __shfl_down_sync(0xffffffffu, v, o));

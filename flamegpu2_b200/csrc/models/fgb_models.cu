@@ -150,12 +150,18 @@ int fgbm_get_count(void *h, const char *agent, const char *state, unsigned int *
   return guarded([&] { *n = static_cast<Sim *>(h)->sim->getAgentCount(agent, state ? state : flamegpu::DEFAULT_STATE); });
 }
 
-// HostAgentAPI reductions (what a step function calls): op 0 sum, 1 min, 2 max; kind 'f' float, 'i' int, 'u' unsigned
+// HostAgentAPI reductions (what a step function calls): op 0 sum, 1 min, 2 max, 3 count(value), 4 mean, 5 std;
+// kind 'f' float, 'i' int, 'u' unsigned
 int fgbm_agent_reduce(void *h, const char *agent, const char *var, int op, char kind, double *out) {
   return guarded([&] {
     flamegpu::HostAgentAPI api = static_cast<Sim *>(h)->sim->hostAPI().agent(agent);
+    // op 3: count(variable, value = *out on entry); 4: mean; 5: population standard deviation
+    const double arg = *out;
     auto run = [&](auto tag) {
       using T = decltype(tag);
+      if (op == 3) return static_cast<double>(api.count<T>(var, static_cast<T>(arg)));
+      if (op == 4) return api.meanStandardDeviation<T>(var).first;
+      if (op == 5) return api.meanStandardDeviation<T>(var).second;
       return static_cast<double>(op == 0 ? api.sum<T>(var) : (op == 1 ? api.min<T>(var) : api.max<T>(var)));
     };
     *out = kind == 'f' ? run(float{}) : (kind == 'i' ? run(int{}) : run(static_cast<unsigned int>(0)));

@@ -107,11 +107,11 @@ class Simulation:
                                        out.ctypes.data_as(C.c_void_p), out.nbytes), "fgbm_get_variable")
         return out
 
-    def agent_reduce(self, agent: str, var: str, op: str, kind: str) -> float:
-        """HostAgentAPI::sum/min/max of an agent variable (kind: 'f' float, 'i' int, 'u' unsigned int)"""
-        out = C.c_double()
+    def agent_reduce(self, agent: str, var: str, op: str, kind: str, value: float = 0.0) -> float:
+        """HostAgentAPI::sum/min/max/count(value)/mean/std of an agent variable (kind: 'f' float, 'i' int, 'u' unsigned int)"""
+        out = C.c_double(value)
         lib().fgbm_agent_reduce.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char, C.POINTER(C.c_double)]
-        _check(lib().fgbm_agent_reduce(self.h, agent.encode(), var.encode(), {"sum": 0, "min": 1, "max": 2}[op], kind.encode(), C.byref(out)),
+        _check(lib().fgbm_agent_reduce(self.h, agent.encode(), var.encode(), {"sum": 0, "min": 1, "max": 2, "count": 3, "mean": 4, "std": 5}[op], kind.encode(), C.byref(out)),
                "fgbm_agent_reduce")
         return float(out.value)
 

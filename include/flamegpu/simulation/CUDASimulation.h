@@ -235,10 +235,17 @@ class HostAgentAPI {
   inline T min(const std::string &variable);
   template <typename T>
   inline T max(const std::string &variable);
+  // reference HostAgentAPI.cuh:700-718 (thrust::count) and :561-604 (mean, POPULATION standard deviation)
+  template <typename T>
+  inline unsigned int count(const std::string &variable, T value);
+  template <typename T>
+  inline std::pair<double, double> meanStandardDeviation(const std::string &variable);
 
  private:
   template <typename T, typename R>
   inline R reduce(const std::string &variable, int op);
+  template <typename T, typename R>
+  inline R transform_reduce(const std::string &variable, int transform, const void *param);
   CUDASimulation *sim;
   std::string agent, state;
 };

@@ -1163,6 +1163,32 @@ inline R HostAgentAPI::reduce(const std::string &variable, int op) {
   FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
   return r;
 }
+template <typename T, typename R>
+inline R HostAgentAPI::transform_reduce(const std::string &variable, int transform, const void *param) {
+  sim->initialise();
+  detail::DevList &l = sim->state_list(agent, state);
+  const int i = l.index_of(variable);
+  if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
+  if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
+  FGB_ABI_THROW(fgb_transform_reduce(sim->ctx, 0, transform, detail::reduce_dtype<T>::value, l.data[i], l.bound,
+                                     sim->slot_ptr(l.count_slot), param, sim->d_reduce_out, sim->main_stream));
+  R r{};
+  FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(R), cudaMemcpyDeviceToHost, sim->main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
+  return r;
+}
+template <typename T>
+inline unsigned int HostAgentAPI::count(const std::string &variable, T value) {
+  return static_cast<unsigned int>(transform_reduce<T, unsigned long long>(variable, FGB_TRANSFORM_COUNT_EQUAL, &value));
+}
+template <typename T>
+inline std::pair<double, double> HostAgentAPI::meanStandardDeviation(const std::string &variable) {
+  const unsigned int n = count();
+  if (n == 0) return std::make_pair(0.0, 0.0);
+  const double mean = static_cast<double>(reduce<T, typename detail::reduce_dtype<T>::sum_t>(variable, FGB_REDUCE_SUM)) / static_cast<double>(n);
+  const double ss = transform_reduce<T, double>(variable, FGB_TRANSFORM_SUM_SQ_DEV, &mean);
+  return std::make_pair(mean, std::sqrt(ss / static_cast<double>(n)));
+}
 template <typename T>
 inline T HostAgentAPI::sum(const std::string &variable) {
   return static_cast<T>(reduce<T, typename detail::reduce_dtype<T>::sum_t>(variable, FGB_REDUCE_SUM));

@@ -223,6 +223,13 @@ enum fgb_dtype { FGB_F32 = 0, FGB_F64 = 1, FGB_I32 = 2, FGB_U32 = 3, FGB_I64 = 4
 fgb_status fgb_reduce(fgb_ctx *ctx, unsigned int stream_id, int op, int dtype, const void *in, unsigned int n,
                       const unsigned int *d_n, void *d_out, void *stream);
 
+/* HostAgentAPI::count(variable, value) (thrust::count, HostAgentAPI.cuh:700-718) and the second pass of
+ * HostAgentAPI::meanStandardDeviation (sum of (x - mean)^2, :598-600).  param points to HOST memory: the value to
+ * count in the element type, or the mean as a double.  d_out receives 8 bytes: an unsigned 64-bit count, or a double. */
+enum fgb_transform { FGB_TRANSFORM_COUNT_EQUAL = 1, FGB_TRANSFORM_SUM_SQ_DEV = 2 };
+fgb_status fgb_transform_reduce(fgb_ctx *ctx, unsigned int stream_id, int transform, int dtype, const void *in, unsigned int n,
+                                const unsigned int *d_n, const void *param, void *d_out, void *stream);
+
 /* ---- automatic spatial agent sort ----------------------------------------------------------- */
 /* calculateSpatialHash kernels (src/flamegpu/simulation/CUDASimulation.cu:335-408):
  * key = floorf(((p-min)/width)*grid_dim) linearised, NOT clamped.  z == NULL for 2D.

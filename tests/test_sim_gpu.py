@@ -388,6 +388,14 @@ def test_host_agent_reductions():
     assert s.agent_reduce("Circle", "drift", "max", "f") == float(drift.max())
     assert s.agent_reduce("Circle", "_id", "sum", "u") == float(ids.astype(np.uint64).sum() % (1 << 32))  # sum<unsigned> wraps like T
     assert s.agent_reduce("Circle", "_id", "max", "u") == float(ids.max())
+    # count(variable, value), mean and POPULATION standard deviation (reference HostAgentAPI.cuh:561-604, 700-718)
+    keys = s.get("Circle", "_auto_sort_bin_index", np.uint32)
+    v = int(np.bincount(keys).argmax())
+    assert s.agent_reduce("Circle", "_auto_sort_bin_index", "count", "u", value=v) == float((keys == v).sum())
+    assert s.agent_reduce("Circle", "_id", "count", "u", value=0) == 0.0
+    x = s.get("Circle", "x", np.float32).astype(np.float64)
+    assert abs(s.agent_reduce("Circle", "x", "mean", "f") - x.mean()) <= 1e-9 * L
+    assert abs(s.agent_reduce("Circle", "x", "std", "f") - x.std()) <= 1e-9 * L
     s.close()
 
 
