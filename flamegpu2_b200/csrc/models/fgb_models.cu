@@ -150,6 +150,64 @@ int fgbm_get_count(void *h, const char *agent, const char *state, unsigned int *
   return guarded([&] { *n = static_cast<Sim *>(h)->sim->getAgentCount(agent, state ? state : flamegpu::DEFAULT_STATE); });
 }
 
+// Host-side description validation, restating the reference's DescriptionValidation / DataValidation / reserved_name
+// tests (test_bucket.cu:23-52, test_spatial_3d.cu DescriptionValidation).  Pure host code: returns 0 when every
+// expectation holds, otherwise the 1-based index of the first failed check.  No GPU needed.
+int fgbm_selftest_descriptions(void) {
+  using namespace flamegpu;
+  int check = 0;
+#define EXPECT_THROWS(expr, exc)   \
+  ++check;                         \
+  try {                            \
+    expr;                          \
+    return check;                  \
+  } catch (const exc &) {          \
+  } catch (...) {                  \
+    return check;                  \
+  }
+#define EXPECT_OK(expr) \
+  ++check;              \
+  try {                 \
+    expr;               \
+  } catch (...) {       \
+    return check;       \
+  }
+  {
+    ModelDescription model("BucketMessageTest");
+    MessageBucket::Description message = model.newMessage<MessageBucket>("buckets");
+    EXPECT_THROWS(message.setUpperBound(0), exception::InvalidArgument);  // min defaults to 0: no buckets
+    EXPECT_OK(message.setLowerBound(10));
+    EXPECT_OK(message.setUpperBound(11));
+    EXPECT_THROWS(message.setUpperBound(0), exception::InvalidArgument);  // max < min
+    EXPECT_OK(message.setUpperBound(12));
+    EXPECT_THROWS(message.setLowerBound(13), exception::InvalidArgument);  // min > max
+    EXPECT_THROWS(message.setBounds(12, 12), exception::InvalidArgument);
+    EXPECT_THROWS(message.setBounds(13, 12), exception::InvalidArgument);
+    EXPECT_OK(message.setBounds(12, 13));
+    EXPECT_OK(message.newVariable<int>("somevar"));
+    EXPECT_THROWS(message.newVariable<int>("_"), exception::ReservedName);
+    EXPECT_THROWS(message.newVariable<int>("somevar"), exception::InvalidMessageVar);
+  }
+  {
+    ModelDescription model("Spatial3DMessageTest");
+    MessageSpatial3D::Description message = model.newMessage<MessageSpatial3D>("location");
+    EXPECT_THROWS(message.setRadius(0), exception::InvalidArgument);
+    EXPECT_THROWS(message.setRadius(-10), exception::InvalidArgument);
+    EXPECT_OK(message.setRadius(1));
+    EXPECT_OK(message.setMinX(0));
+    EXPECT_THROWS(message.setMaxX(-1), exception::InvalidArgument);  // max <= min
+    EXPECT_OK(message.setMax(5, 5, 5));
+    EXPECT_THROWS(message.setMinZ(5), exception::InvalidArgument);   // min >= max
+    EXPECT_THROWS(model.newMessage<MessageSpatial3D>("location"), exception::InvalidMessageName);
+    AgentDescription agent = model.newAgent("agent");
+    EXPECT_THROWS(model.newAgent("agent"), exception::InvalidAgentName);
+    EXPECT_OK(agent.newVariable<float>("x"));
+  }
+#undef EXPECT_THROWS
+#undef EXPECT_OK
+  return 0;
+}
+
 // HostAgentAPI reductions (what a step function calls): op 0 sum, 1 min, 2 max, 3 count(value), 4 mean, 5 std;
 // kind 'f' float, 'i' int, 'u' unsigned
 int fgbm_agent_reduce(void *h, const char *agent, const char *var, int op, char kind, double *out) {

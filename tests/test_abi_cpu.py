@@ -52,3 +52,11 @@ def test_struct_layouts_match_reference():
     assert C.sizeof(md) == 72
     assert md.PBM.offset == 32 and md.grid_dim.offset == 40 and md.environment_width.offset == 52
     assert md.wrap_compatible.offset == 64
+
+
+def test_description_validation_host_side():
+    # the reference's DescriptionValidation / reserved_name host tests (test_bucket.cu:23-52, test_spatial_3d.cu),
+    # restated in C++ inside libfgb_models.so (fgbm_selftest_descriptions); pure host code, no GPU
+    from flamegpu2_b200 import sim
+
+    assert sim.lib().fgbm_selftest_descriptions() == 0
