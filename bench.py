@@ -7,7 +7,14 @@
 One "step" is one whole CUDASimulation::step() of the Circles model (output_message -> automatic
 agent sort -> PBM buildIndex -> move) over all agents.  N=1 runs BASELINE.json configs[1]
 (1 M agents, [0,100)^3, radius 2 => 50^3 bins, 8 agents/bin); N>1 is weak scaling with the same
-number of agents per GPU.  Prints ONE JSON line on rank 0.
+number of agents per GPU: the global box is the single-GPU box stacked N times along z, decomposed into z-slabs
+with halo and migration exchange over NCCL every step (flamegpu2_b200/slab.py).  Prints ONE JSON line on rank 0.
+
+Besides the contract's keys the N=1 line carries: `roofline` (buildIndex, algorithmic bytes / its measured
+duration against the measured HBM peak), `phases_us` (per-phase device times from an eager profiled pass), `e2e`
+(host buffers in and out through the C ABI), `cpu_baseline` (the OpenMP port on the host cores), `reference_cuda`
+(the reference's own CUDA build on the same GPU, when oracle/_ref/ref_sim exists) and `opt_in` (the radius-filtered
+iterator, off by default, over the same number of steps).
 
 Timing: the agent state is resident in HBM; every step is timed with CUDA events recorded on the
 simulation's own stream (where its graph is launched); the whole working set (~80 MB) fits the
