@@ -4,6 +4,8 @@
 // Model definition follows the reference example examples/cpp/circles_spatial3D/src/main.cu:5-54,
 // 77-113 (same variables, same arithmetic); population size, extent and radius are parameters.
 #pragma once
+#include <cstdio>
+
 #include "flamegpu/flamegpu.h"
 
 namespace fgb_examples {
@@ -57,12 +59,34 @@ FLAMEGPU_AGENT_FUNCTION(circles_move, flamegpu::MessageSpatial3D, flamegpu::Mess
   return flamegpu::ALIVE;
 }
 
+// The example's own step function (reference examples/cpp/circles_spatial3D/src/main.cu:55-70): one device reduction
+// per step whose result the host inspects.  The per-step printf of the example is kept behind `verbose`.
+struct CirclesValidationState {
+  float prev_total_drift = 3.402823466e+38f;
+  unsigned int dropped = 0, increased = 0;
+  bool verbose = false;
+};
+inline CirclesValidationState &circles_validation_state() {
+  static CirclesValidationState s;
+  return s;
+}
+FLAMEGPU_STEP_FUNCTION(circles_validation) {
+  CirclesValidationState &v = circles_validation_state();
+  const float totalDrift = FLAMEGPU->agent("Circle").sum<float>("drift");
+  if (totalDrift <= v.prev_total_drift) v.dropped++;
+  else v.increased++;
+  v.prev_total_drift = totalDrift;
+  if (v.verbose) printf("%.2f%% Drift correct\n", 100 * v.dropped / static_cast<float>(v.dropped + v.increased));
+}
+
 struct CirclesParams {
   float env_max = 25.0f;   // reference example: floor(cbrt(16384)) = 25
   float env_max_z = 0.0f;  // > 0: non-cubic box [0,env_max)^2 x [0,env_max_z) (multi-GPU weak scaling stacks slabs in z)
   float radius = 2.0f;
   float repulse = 0.05f;
   unsigned int sort_period = 1;
+  unsigned int validation = 1;      // attach the example's Validation step function (sum of "drift" every step)
+  unsigned int radius_filtered = 1; // this repo only: declare that `move` ignores messages beyond the radius (see below)
 };
 
 inline void define_circles(flamegpu::ModelDescription &model, const CirclesParams &p) {
@@ -81,9 +105,16 @@ inline void define_circles(flamegpu::ModelDescription &model, const CirclesParam
     agent.newVariable<float>("drift");
     agent.setSortPeriod(p.sort_period);
     agent.newFunction("output_message", circles_output).setMessageOutput("location");
-    agent.newFunction("move", circles_move).setMessageInput("location");
+    flamegpu::AgentFunctionDescription mv = agent.newFunction("move", circles_move);
+    mv.setMessageInput("location");
+#ifdef FLAMEGPU2_B200
+    // b200 extension (no reference counterpart): `move` tests `separation < RADIUS` itself, so it may be shown only the
+    // messages within the radius of its search origin (AgentFunctionDescription::setMessageInputRadiusFiltered).
+    mv.setMessageInputRadiusFiltered(p.radius_filtered != 0);
+#endif
   }
   model.Environment().newProperty("repulse", p.repulse);
+  if (p.validation) model.addStepFunction(circles_validation);
   model.newLayer().addAgentFunction(circles_output);
   model.newLayer().addAgentFunction(circles_move);
 }

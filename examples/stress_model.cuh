@@ -84,6 +84,9 @@ inline void define_stress(flamegpu::ModelDescription &model, const StressParams 
   upd.setMessageInput("location");
   upd.setAllowAgentDeath(true);
   upd.setAgentOutput(agent);
+#ifdef FLAMEGPU2_B200
+  upd.setMessageInputRadiusFiltered(true);  // b200 extension: `update` counts only messages within the radius
+#endif
   flamegpu::EnvironmentDescription env = model.Environment();
   env.newProperty<unsigned int>("death_mod", p.death_mod);
   env.newProperty<unsigned int>("birth_mod", p.birth_mod);

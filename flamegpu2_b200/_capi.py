@@ -16,6 +16,7 @@ FGB_MAX_VARS = 32
 FGB_BUILD_DEFAULT = 0
 FGB_BUILD_STABLE = 1
 FGB_BUILD_TILE_LOCAL = 2
+FGB_BUILD_KEYS_READY = 4
 FGB_REDUCE_SUM, FGB_REDUCE_MIN, FGB_REDUCE_MAX = 0, 1, 2
 FGB_F32, FGB_F64, FGB_I32, FGB_U32, FGB_I64, FGB_U64 = range(6)
 FGB_ERR_NO_DEVICE = -3
@@ -48,6 +49,7 @@ SIGNATURES = {
     "fgb_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "fgb_ctx_destroy": (C.c_int, [C.c_void_p]),
     "fgb_launch_count": (C.c_ulonglong, [C.c_void_p]),
+    "fgb_alloc_generation": (C.c_ulonglong, [C.c_void_p]),
     "fgb_spatial_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                      C.POINTER(C.c_void_p)]),
     "fgb_spatial_create_window": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
@@ -61,6 +63,10 @@ SIGNATURES = {
     "fgb_spatial_read_pbm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_spatial_reserve": (C.c_int, [C.c_void_p, C.c_uint]),
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),
+    "fgb_spatial_writer_args": (C.c_int, [C.c_void_p, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fgb_spatial_clear_histogram": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fgb_build_index_ex": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_build_index": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p]),
     "fgb_sort_spatial": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -77,13 +77,10 @@ int stable_tail(fgb_ctx *ctx, const uint32_t *pbm, unsigned int bins, uint32_t *
   return launch_ok();
 }
 
+// keys + histogram for the items [*d_keyed, n) of a list (d_keyed NULL: all of them)
 template <int DIMS>
-int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
-                     const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, cudaStream_t st) {
-  fgb_ctx *ctx = sp->ctx;
-  VarTable vt;
-  int r = make_var_table(vars, nvars, &vt);
-  if (r) return r;
+int launch_bin_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const unsigned int *d_keyed, const float *x, const float *y,
+                    const float *z, cudaStream_t st) {
   KeySrc<DIMS> src{};
   src.x = x;
   src.y = y;
@@ -92,47 +89,77 @@ int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, c
   src.key_min = static_cast<uint32_t>(sp->key_min);
   src.key_span = sp->bin_count;
   src.g = make_geo(sp);
-  const bool vec = aligned16(x) && (DIMS == 0 || aligned16(y)) && (DIMS != 3 || aligned16(z)) && vars_in_aligned(vars, nvars);
+  const bool vec = aligned16(x) && (DIMS == 0 || aligned16(y)) && (DIMS != 3 || aligned16(z));
+  uint32_t *keys = static_cast<uint32_t *>(sp->keys.p);
+  const unsigned int grid = tile_grid(n);
+  if (vec)
+    k_bin_keys<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, d_keyed, keys, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+  else
+    k_bin_keys<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, d_keyed, keys, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl);
+  sp->ctx->launches += 1;
+  return launch_ok();
+}
+
+// scan + scatter from the stored keys (sp->keys, sp->d_hist complete for [0, n))
+int scatter_from_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars, unsigned int flags,
+                      unsigned int *src_slot_out, cudaStream_t st) {
+  fgb_ctx *ctx = sp->ctx;
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  const bool vec = vars_in_aligned(vars, nvars);
   const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
   const bool stable = (flags & FGB_BUILD_STABLE) != 0;
+  const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
+  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
+  uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
+  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
+  if (!stable) {
+    if (vec) {
+      k_bin_scatter_direct<true, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state);
+      k_bin_scatter_staged<true, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
+    } else {
+      k_bin_scatter_direct<false, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state);
+      k_bin_scatter_staged<false, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
+    }
+    ctx->launches += 3;
+    return launch_ok();
+  }
+  k_bin_scatter_direct<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm, sp->d_state, sp->n_state);
+  k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm);
+  ctx->launches += 3;
+  r = stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars, st);
+  if (r == 0 && src_slot_out) r = static_cast<int>(cudaMemcpyAsync(src_slot_out, perm, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, st));
+  return r;
+}
+
+int reserve_index(fgb_spatial *sp, unsigned int n, bool stable) {
+  int r = sp->keys.reserve((static_cast<size_t>(n) + 8) * 4);
+  if (r) return r;
+  r = sp->tile_mode.reserve((static_cast<size_t>(tile_grid(n)) + 1) * 4);
+  if (r) return r;
   if (stable) {
     r = sp->perm.reserve(static_cast<size_t>(n) * 4);
     if (r) return r;
     r = sp->worklist.reserve(worklist_bytes(n));
+  }
+  return r;
+}
+
+template <int DIMS>
+int build_index_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                     const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, const unsigned int *d_keyed,
+                     unsigned int *src_slot_out, cudaStream_t st) {
+  int r = reserve_index(sp, n, (flags & FGB_BUILD_STABLE) != 0);
+  if (r) return r;
+  // keys + histogram: skipped when the list's writer published them for every item (FGB_BUILD_KEYS_READY without a
+  // d_keyed word); with a d_keyed word only the items behind it are keyed here
+  if (!(flags & FGB_BUILD_KEYS_READY) || d_keyed) {
+    r = launch_bin_keys<DIMS>(sp, n, d_n, (flags & FGB_BUILD_KEYS_READY) ? d_keyed : nullptr, x, y, z, st);
     if (r) return r;
   }
-  r = sp->tile_mode.reserve((static_cast<size_t>(grid) + 1) * 4);
-  if (r) return r;
-  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
-  uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
-  const unsigned int dgrid = bin_grid(n);
-  if (vec)
-    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
-  else
-    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
-  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-  if (!stable) {
-    if (vec) {
-      k_bin_scatter_direct<DIMS, true, false><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
-      k_bin_scatter_staged<DIMS, true, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
-    } else {
-      k_bin_scatter_direct<DIMS, false, false><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
-      k_bin_scatter_staged<DIMS, false, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, nullptr, tm);
-    }
-    ctx->launches += 4;
-    return launch_ok();
-  }
-  if (vec) {
-    k_bin_scatter_direct<DIMS, true, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
-    k_bin_scatter_staged<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
-  } else {
-    k_bin_scatter_direct<DIMS, false, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
-    k_bin_scatter_staged<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, vt, perm, tm);
-  }
-  ctx->launches += 4;
-  return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars,
-                     st);
+  return scatter_from_keys(sp, n, d_n, vars, nvars, flags, src_slot_out, st);
 }
 
 }  // namespace
@@ -142,15 +169,14 @@ template <int DIMS>
 int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
                          const float *z, unsigned int *perm, unsigned int flags, cudaStream_t st) {
   fgb_ctx *ctx = sp->ctx;
-  KeySrc<DIMS> src{};
-  src.x = x;
-  src.y = y;
-  src.z = z;
-  src.g = make_geo(sp);
-  const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
-  const unsigned int grid = tile_grid(n);
-  const unsigned int B = sp->bin_count;
   if (flags & FGB_BUILD_TILE_LOCAL) {
+    KeySrc<DIMS> src{};
+    src.x = x;
+    src.y = y;
+    src.z = z;
+    src.g = make_geo(sp);
+    const bool vec = aligned16(x) && aligned16(y) && (DIMS == 2 || aligned16(z));
+    const unsigned int grid = tile_grid(n);
     if (vec)
       k_group_tile<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, perm);
     else
@@ -158,31 +184,22 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
     ctx->launches += 1;
     return launch_ok();
   }
+  const bool stable = (flags & FGB_BUILD_STABLE) != 0;
+  int r = reserve_index(sp, n, stable);
+  if (r) return r;
+  r = launch_bin_keys<DIMS>(sp, n, d_n, nullptr, x, y, z, st);
+  if (r) return r;
+  const unsigned int grid = tile_grid(n);
+  const unsigned int B = sp->bin_count;
+  const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
+  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
   VarTable none{};
   none.n = 0;
-  if (flags & FGB_BUILD_STABLE) {
-    int r = sp->worklist.reserve(worklist_bytes(n));
-    if (r) return r;
-  }
-  int r2 = sp->tile_mode.reserve((static_cast<size_t>(grid) + 1) * 4);
-  if (r2) return r2;
-  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
-  const unsigned int dgrid = bin_grid(n);
-  if (vec) {
-    k_bin_hist<DIMS, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
-    k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-    k_bin_scatter_direct<DIMS, true, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
-    k_bin_scatter_staged<DIMS, true, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
-  } else {
-    k_bin_hist<DIMS, false><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->d_hist, sp->d_state, sp->n_state, sp->d_ctrl, tm);
-    k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-    k_bin_scatter_direct<DIMS, false, true><<<dgrid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
-    k_bin_scatter_staged<DIMS, false, true><<<grid, kBinThreads, 0, st>>>(src, n, d_n, sp->md.PBM, none, perm, tm);
-  }
-  ctx->launches += 1;
+  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
+  k_bin_scatter_direct<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm, sp->d_state, sp->n_state);
+  k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm);
   ctx->launches += 3;
-  if (flags & FGB_BUILD_STABLE)
-    return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
+  if (stable) return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
   return launch_ok();
 }
 }  // namespace
@@ -346,6 +363,8 @@ fgb_status fgb_ctx_destroy(fgb_ctx *ctx) {
 
 unsigned long long fgb_launch_count(const fgb_ctx *ctx) { return ctx ? ctx->launches : 0ull; }
 
+unsigned long long fgb_alloc_generation(const fgb_ctx *ctx) { return ctx ? ctx->generation : 0ull; }
+
 fgb_status fgb_spatial_create(fgb_ctx *ctx, int dims, const float *env_min, const float *env_max, float radius,
                               fgb_spatial **out) {
   return fgb_spatial_create_window(ctx, dims, env_min, env_max, radius, 0, -1, out);
@@ -358,6 +377,7 @@ fgb_status fgb_spatial_create_window(fgb_ctx *ctx, int dims, const float *env_mi
   if (!sp) return FGB_ERR_ALLOC;
   sp->ctx = ctx;
   sp->dims = dims;
+  sp->perm.gen = sp->worklist.gen = sp->tile_mode.gen = sp->keys.gen = &ctx->generation;
   fgb_spatial_metadata &md = sp->md;
   std::memset(&md, 0, sizeof(md));
   md.radius = radius;
@@ -409,6 +429,7 @@ fgb_status fgb_bucket_create(fgb_ctx *ctx, int lower_bound, int upper_bound, fgb
   if (!sp) return FGB_ERR_ALLOC;
   sp->ctx = ctx;
   sp->dims = 0;
+  sp->perm.gen = sp->worklist.gen = sp->tile_mode.gen = sp->keys.gen = &ctx->generation;
   std::memset(&sp->md, 0, sizeof(sp->md));
   sp->md.grid_dim[0] = static_cast<unsigned int>(bins);
   sp->md.grid_dim[1] = sp->md.grid_dim[2] = 1;
@@ -440,6 +461,7 @@ fgb_status fgb_spatial_destroy(fgb_spatial *sp) {
   sp->perm.release();
   sp->worklist.release();
   sp->tile_mode.release();
+  sp->keys.release();
   delete sp;
   return FGB_OK;
 }
@@ -480,17 +502,31 @@ fgb_status fgb_spatial_read_pbm(const fgb_spatial *sp, unsigned int *host_out, v
   return FGB_OK;
 }
 
-fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max) {
+fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max) { return sp ? reserve_index(sp, n_max, true) : FGB_ERR_INVALID_ARG; }
+
+fgb_status fgb_spatial_clear_histogram(fgb_spatial *sp, void *stream) {
   if (!sp) return FGB_ERR_INVALID_ARG;
-  int r = sp->tile_mode.reserve((static_cast<size_t>(tile_grid(n_max)) + 1) * 4);
+  FGB_CHECK(cudaMemsetAsync(sp->d_hist, 0, (static_cast<size_t>(sp->bin_count) + 1) * 4, static_cast<cudaStream_t>(stream)));
+  return FGB_OK;
+}
+
+fgb_status fgb_spatial_writer_args(fgb_spatial *sp, unsigned int n_max, unsigned int **d_keys, unsigned int **d_hist) {
+  if (!sp || !d_keys || !d_hist) return FGB_ERR_INVALID_ARG;
+  const int r = reserve_index(sp, n_max, false);
   if (r) return r;
-  r = sp->perm.reserve(static_cast<size_t>(n_max) * 4);
-  if (r) return r;
-  return sp->worklist.reserve(worklist_bytes(n_max));
+  *d_keys = static_cast<unsigned int *>(sp->keys.p);
+  *d_hist = sp->d_hist;
+  return FGB_OK;
 }
 
 fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
                            const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags, void *stream) {
+  return fgb_build_index_ex(sp, n, d_n, x, y, z, vars, nvars, flags & ~static_cast<unsigned int>(FGB_BUILD_KEYS_READY), nullptr, nullptr, stream);
+}
+
+fgb_status fgb_build_index_ex(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                              const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags,
+                              const unsigned int *d_keyed, unsigned int *src_slot_out, void *stream) {
   if (!sp) return FGB_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) {  // MessageSpatial3D.cu:116-120
@@ -498,8 +534,8 @@ fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *
     return FGB_OK;
   }
   if (sp->dims == 0 || !x || !y || (sp->dims == 3 && !z)) return FGB_ERR_INVALID_ARG;  // bucket lists: fgb_build_index_keys
-  if (sp->dims == 3) return build_index_impl<3>(sp, n, d_n, x, y, z, vars, nvars, flags, st);
-  return build_index_impl<2>(sp, n, d_n, x, y, nullptr, vars, nvars, flags, st);
+  if (sp->dims == 3) return build_index_impl<3>(sp, n, d_n, x, y, z, vars, nvars, flags, d_keyed, src_slot_out, st);
+  return build_index_impl<2>(sp, n, d_n, x, y, nullptr, vars, nvars, flags, d_keyed, src_slot_out, st);
 }
 
 /* MessageBucket::CUDAModelHandler::buildIndex (MessageBucket.cu:105-137) */
@@ -512,7 +548,8 @@ fgb_status fgb_build_index_keys(fgb_spatial *sp, unsigned int n, const unsigned 
     return FGB_OK;
   }
   if (!keys) return FGB_ERR_INVALID_ARG;
-  return build_index_impl<0>(sp, n, d_n, reinterpret_cast<const float *>(keys), nullptr, nullptr, vars, nvars, flags, st);
+  return build_index_impl<0>(sp, n, d_n, reinterpret_cast<const float *>(keys), nullptr, nullptr, vars, nvars,
+                             flags & ~static_cast<unsigned int>(FGB_BUILD_KEYS_READY), nullptr, nullptr, st);
 }
 
 fgb_status fgb_bin_permutation(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,

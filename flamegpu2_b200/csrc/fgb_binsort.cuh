@@ -149,40 +149,40 @@ __device__ __forceinline__ uint32_t block_run_count(const uint32_t k[kTileItems]
   return *s_counter;
 }
 
-// ---- phase 1: histogram ------------------------------------------------------------------
-// Also zeroes the look-back words of the scan that follows and the big-bin counter.
-// hist[] must be all-zero on entry; the scan re-zeroes it.
-// Per tile: grouped input -> one RED per run straight to global memory; ungrouped input -> aggregate in
-// the shared-memory table first, one RED per distinct key.
+// ---- phase 1: keys + histogram --------------------------------------------------------------
+// keys[i] = bin of item i (stored once; the scatter kernels never re-hash positions) and hist[key] += 1 for the items
+// [first, n), first = *d_first (NULL: 0): the range form lets a list whose leading part was already counted by its
+// writer (agent_function_wrapper publishes key + histogram for mandatory spatial output, AgentFunction.cuh) take
+// further items (ghost messages appended by the slab exchange) without recounting.  One RED per run of equal keys of
+// a thread's 8 consecutive items: lists arrive grouped (the writer runs in bin order), so ~1 RED per bin visit.
+// Also zeroes the look-back words of the scan that follows and the big-bin counter.  hist[] must hold only the
+// counts of items [0, first) on entry; the scan re-zeroes it.
 template <int DIMS, bool VEC>
-__global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
-                                                          uint32_t *hist, unsigned long long *state,
-                                                          uint32_t n_state, uint32_t *ctrl, uint32_t *tile_mode) {
-  __shared__ uint32_t s_key[kTabSlots];
-  __shared__ uint32_t s_cnt[kTabSlots];
-  __shared__ uint32_t s_runs;
+__global__ void __launch_bounds__(kBinThreads) k_bin_keys(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
+                                                          const unsigned int *d_first, uint32_t *__restrict__ keys,
+                                                          uint32_t *hist, unsigned long long *state, uint32_t n_state,
+                                                          uint32_t *ctrl) {
   const uint32_t gtid = blockIdx.x * kBinThreads + threadIdx.x;
   const uint32_t total = gridDim.x * kBinThreads;
   for (uint32_t s = gtid; s < n_state; s += total) state[s] = 0ull;
   if (gtid == 0 && ctrl) ctrl[0] = 0u;
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t tile0 = blockIdx.x * kTile;
-  if (tile0 >= n) return;
-  const uint32_t i0 = gtid * kTileItems;
-  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  const uint32_t first = d_first ? __ldg(d_first) : 0u;
+  // the first item of a thread stays a multiple of 8 (aligned vector accesses); items below `first` are skipped
+  const uint32_t i0 = (first & ~7u) + gtid * kTileItems;
+  if (i0 >= n) return;
+  const int cnt = (n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems;
   uint32_t k[kTileItems];
-  if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
-  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
-  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
-  if (threadIdx.x == 0) tile_mode[blockIdx.x] = grouped ? 1u : 0u;  // the scatter kernels follow this choice
-  if (!grouped) {
-    for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
-      s_key[s] = kTabEmpty;
-      s_cnt[s] = 0u;
-    }
-    __syncthreads();
+  load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  const int lo = first > i0 ? static_cast<int>(first - i0) : 0;  // > 0 only in the thread that straddles `first`
+  if (VEC && lo == 0 && cnt == kTileItems && (reinterpret_cast<uintptr_t>(keys + i0) & 31u) == 0) {
+    st_u8(keys + i0, k);
+  } else {
+#pragma unroll
+    for (int t = 0; t < kTileItems; ++t)
+      if (t >= lo && t < cnt) keys[i0 + t] = k[t];
   }
-  int j = 0;
+  int j = lo;
 #pragma unroll
   for (int r = 0; r < kTileItems; ++r) {
     if (r == j && j < cnt) {
@@ -190,16 +190,9 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
 #pragma unroll
       for (int t = 1; t < kTileItems; ++t)
         if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
-      if (grouped) atomicAdd(hist + k[r], static_cast<uint32_t>(e - j));
-      else atomicAdd(s_cnt + tab_insert(s_key, k[r]), static_cast<uint32_t>(e - j));
+      atomicAdd(hist + k[r], static_cast<uint32_t>(e - j));
       j = e;
     }
-  }
-  if (grouped) return;
-  __syncthreads();
-  for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
-    const uint32_t key = s_key[s];
-    if (key != kTabEmpty) atomicAdd(hist + key, s_cnt[s]);
   }
 }
 
@@ -213,60 +206,94 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_hist(KeySrc<DIMS> src, uint
 // shared memory (the table is indexed by the low key bits, so x-adjacent bins -- adjacent in the
 // output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
 // items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
-// Grouped tiles: 4 items per thread, no shared memory, full occupancy (two blocks per 2048-item tile).
-template <int DIMS, bool VEC, bool IDX_ONLY>
-__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_direct(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
-                                                                    uint32_t *cursor, const __grid_constant__ VarTable vt,
-                                                                    uint32_t *perm, const uint32_t *__restrict__ tile_mode) {
+// Grouped tiles.  Reads the stored keys (8 per thread, one 256-bit load), classifies its 2048-item tile by the number
+// of runs of equal keys -- a tile of a bin-ordered list has few, any other order one per item -- and records the
+// choice for k_bin_scatter_staged, which runs next and takes the ungrouped tiles.  No shared-memory table: one
+// global atomic per run claims its output range, the items of a run land on consecutive addresses.
+// Also re-zeroes the scan's look-back words (the scan is complete by now) for the next build.
+template <bool VEC, bool IDX_ONLY>
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_direct(const uint32_t *__restrict__ keys, uint32_t n_max,
+                                                                    const unsigned int *d_n, uint32_t *cursor,
+                                                                    const __grid_constant__ VarTable vt, uint32_t *perm,
+                                                                    uint32_t *tile_mode, unsigned long long *state,
+                                                                    uint32_t n_state) {
+  __shared__ uint32_t s_runs;
+  for (uint32_t s = blockIdx.x * kBinThreads + threadIdx.x; s < n_state; s += gridDim.x * kBinThreads) state[s] = 0ull;
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t i0 = (blockIdx.x * kBinThreads + threadIdx.x) * kBinItems;
-  if (i0 >= n) return;
-  if (tile_mode[(blockIdx.x * kBinThreads * kBinItems) / kTile] == 0u) return;  // handled by the staged kernel
-  uint32_t k[4], dst[4];
-  src.template load4<VEC>(i0, n, k);
-  const int cnt = (n - i0) < 4u ? static_cast<int>(n - i0) : 4;
-  // claim one contiguous slot range per run of equal keys (independent atomics, all in flight)
-  const bool v1 = cnt > 1, v2 = cnt > 2, v3 = cnt > 3;
-  const bool s1 = v1 && k[1] == k[0], s2 = v2 && k[2] == k[1], s3 = v3 && k[3] == k[2];
-  const bool h1 = v1 && !s1, h2 = v2 && !s2, h3 = v3 && !s3;
-  const uint32_t len2 = 1u + (s3 ? 1u : 0u);
-  const uint32_t len1 = 1u + (s2 ? len2 : 0u);
-  const uint32_t len0 = 1u + (s1 ? len1 : 0u);
-  const uint32_t b0 = atomicAdd(cursor + k[0] + 1, len0);
-  const uint32_t b1 = h1 ? atomicAdd(cursor + k[1] + 1, len1) : 0u;
-  const uint32_t b2 = h2 ? atomicAdd(cursor + k[2] + 1, len2) : 0u;
-  const uint32_t b3 = h3 ? atomicAdd(cursor + k[3] + 1, 1u) : 0u;
-  dst[0] = b0;
-  dst[1] = h1 ? b1 : dst[0] + 1;
-  dst[2] = h2 ? b2 : dst[1] + 1;
-  dst[3] = h3 ? b3 : dst[2] + 1;
+  const uint32_t tile0 = blockIdx.x * kTile;
+  if (tile0 >= n) return;
+  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
+  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+  uint32_t k[kTileItems];
+  if (cnt == kTileItems && VEC) {
+    ld_nc_u8(keys + i0, k);
+  } else {
+#pragma unroll
+    for (int t = 0; t < kTileItems; ++t) k[t] = t < cnt ? __ldg(keys + i0 + t) : 0xFFFFFFFFu;
+  }
+  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
+  if (threadIdx.x == 0) tile_mode[blockIdx.x] = grouped ? 1u : 0u;
+  if (!grouped || cnt == 0) return;
+  // one atomic per run (all of a thread's atomics are in flight together)
+  uint32_t dst[kTileItems];
+  {
+    int j = 0;
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      if (r == j && j < cnt) {
+        int e = j + 1;
+#pragma unroll
+        for (int t = 1; t < kTileItems; ++t)
+          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
+        const uint32_t b = atomicAdd(cursor + k[r] + 1, static_cast<uint32_t>(e - j));
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (r + t < e && t < kTileItems - r) dst[r + t] = b + t;
+        j = e;
+      }
+    }
+  }
   if constexpr (IDX_ONLY) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < kTileItems; ++t)
       if (t < cnt) perm[dst[t]] = i0 + t;
   } else {
     for (uint32_t v = 0; v < vt.n; ++v) {
-      if (VEC && vt.len[v] == 4 && cnt == 4) {
-        const uint4 q = ld_stream_u4(vt.in[v] + static_cast<size_t>(i0) * 4);
+      if (vt.len[v] == 4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]);
         uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
-        o[dst[0]] = q.x;
-        o[dst[1]] = q.y;
-        o[dst[2]] = q.z;
-        o[dst[3]] = q.w;
+        uint32_t w[kTileItems];
+        if (VEC && cnt == kTileItems && (reinterpret_cast<uintptr_t>(in + i0) & 31u) == 0) {
+          ld_nc_u8(in + i0, w);
+        } else {
+#pragma unroll
+          for (int t = 0; t < kTileItems; ++t)
+            if (t < cnt) w[t] = __ldg(in + i0 + t);
+        }
+#pragma unroll
+        for (int t = 0; t < kTileItems; ++t)
+          if (t < cnt) o[dst[t]] = w[t];
       } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+        for (int t = 0; t < kTileItems; ++t)
           if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
       }
+    }
+    if (perm) {  // source slot of every sorted item (the scheduler derives the readers' bin-ordered execution from it)
+#pragma unroll
+      for (int t = 0; t < kTileItems; ++t)
+        if (t < cnt) perm[dst[t]] = i0 + t;
     }
   }
 }
 
 // Ungrouped tiles: shared-memory table + staged, coalesced write-out.
-template <int DIMS, bool VEC, bool IDX_ONLY>
-__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(KeySrc<DIMS> src, uint32_t n_max, const unsigned int *d_n,
-                                                                    uint32_t *cursor, const __grid_constant__ VarTable vt,
-                                                                    uint32_t *perm, const uint32_t *__restrict__ tile_mode) {
+template <bool VEC, bool IDX_ONLY>
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(const uint32_t *__restrict__ keys, uint32_t n_max,
+                                                                    const unsigned int *d_n, uint32_t *cursor,
+                                                                    const __grid_constant__ VarTable vt, uint32_t *perm,
+                                                                    const uint32_t *__restrict__ tile_mode) {
   __shared__ uint32_t s_key[kTabSlots];   // key of the slot, later the slot's offset in the staged tile
   __shared__ uint32_t s_cnt[kTabSlots];   // count of the key in this tile, later its global base
   __shared__ uint32_t s_dst[kTile];       // staged tile: destination index ...
@@ -280,7 +307,12 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(KeySrc<DIMS>
   const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
   const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
   uint32_t k[kTileItems];
-  if (cnt) load_tile_keys<DIMS, VEC>(src, i0, n, k);
+  if (cnt == kTileItems && VEC) {
+    ld_nc_u8(keys + i0, k);
+  } else {
+#pragma unroll
+    for (int t = 0; t < kTileItems; ++t) k[t] = t < cnt ? __ldg(keys + i0 + t) : 0xFFFFFFFFu;
+  }
 
   for (int s = threadIdx.x; s < kTabSlots; s += kBinThreads) {
     s_key[s] = kTabEmpty;
@@ -372,6 +404,8 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(KeySrc<DIMS>
         for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) copy_item(vt, v, tile0 + s_src[e], s_dst[e]);
       }
     }
+    if (perm)
+      for (uint32_t e = threadIdx.x; e < tile_n; e += kBinThreads) perm[s_dst[e]] = tile0 + s_src[e];
   }
 }
 

@@ -51,6 +51,15 @@ __device__ __forceinline__ uint32_t load_count(const unsigned int *d_n, uint32_t
   return n_max;
 }
 
+// same, for a count word that the calling kernel may also WRITE through another argument (aliased device words)
+__device__ __forceinline__ uint32_t load_count_coherent(const unsigned int *d_n, uint32_t n_max) {
+  if (d_n) {
+    const uint32_t v = *reinterpret_cast<const volatile unsigned int *>(d_n);
+    return v < n_max ? v : n_max;
+  }
+  return n_max;
+}
+
 // streaming (read-once) loads / stores: keep them out of L1
 __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
   uint4 r;
@@ -69,6 +78,12 @@ __device__ __forceinline__ void ld_nc_u8(const uint32_t *p, uint32_t v[8]) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p));
+}
+// 256-bit store; p must be 32-byte aligned
+__device__ __forceinline__ void st_u8(uint32_t *p, const uint32_t v[8]) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
   uint32_t r;
@@ -185,8 +200,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
+  unsigned long long *gen = nullptr;  // owner's allocation generation: bumped whenever this buffer moves
   int reserve(size_t need) {
     if (need <= bytes) return 0;
+    if (gen) ++*gen;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
@@ -230,7 +247,17 @@ struct fgb_stream_scratch {
 struct fgb_ctx {
   int device = 0;
   unsigned long long launches = 0;
+  // Counts every (re)allocation of scratch owned by this context or by its fgb_spatial handles.  A caller that
+  // captured launches into a CUDA graph compares it before a replay: the graph holds the old pointers.
+  unsigned long long generation = 0;
   fgb_stream_scratch slot[FGB_MAX_STREAMS];
+  fgb_ctx() {
+    for (auto &s : slot) {
+      fgb::DevBuf *all[] = {&s.tile_state, &s.sort_hist, &s.sort_cursor, &s.perm, &s.worklist, &s.ctrl, &s.rs_state,
+                            &s.rs_keys[0], &s.rs_keys[1], &s.rs_idx[0], &s.rs_idx[1], &s.red};
+      for (fgb::DevBuf *b : all) b->gen = &generation;
+    }
+  }
 };
 
 struct fgb_spatial {
@@ -248,4 +275,6 @@ struct fgb_spatial {
   fgb::DevBuf worklist;  // stable mode: big bins
   unsigned int *d_ctrl = nullptr;  // [0] = big-bin count
   fgb::DevBuf tile_mode;           // per 2048-item tile: 1 = grouped (direct scatter), 0 = ungrouped (staged scatter)
+  fgb::DevBuf keys;                // bin of every item of the list being indexed (written once, by k_bin_keys or by the
+                                   // list's writer: fgb_spatial_writer_args)
 };

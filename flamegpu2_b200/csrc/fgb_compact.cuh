@@ -35,12 +35,15 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
   __shared__ uint32_t s_warp[kCmpThreads / 32];
   __shared__ uint32_t s_excl;
   __shared__ uint32_t s_last;
-  const uint32_t n = load_count(d_n, n_max);
+  // d_n and d_out_offset may alias d_out_total (callers pass a list's own count word for all three), which the last
+  // tile of this very kernel writes: plain (volatile) loads, never the non-coherent path.  The write cannot overtake
+  // a read: the last tile resolves its prefix only after every other tile has published, i.e. has read both words.
+  const uint32_t n = load_count_coherent(d_n, n_max);
   const int tile = blockIdx.x;
   const bool last_tile = tile == static_cast<int>(gridDim.x) - 1;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t w0 = static_cast<uint32_t>(tile) * kCmpTile + warp * (32u * kCmpItems);
-  if (d_out_offset) out_offset = __ldg(d_out_offset);
+  if (d_out_offset) out_offset = *reinterpret_cast<const volatile unsigned int *>(d_out_offset);
 
   // ---- keep ballots of the warp's 8 rounds
   uint32_t bal[kCmpItems];
@@ -144,8 +147,15 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
   }
 
   // ---- self-clean the look-back words once every block is past its look-back
+  // Release/acquire around the arrival counter: this block's st_state() words must be visible before its arrival
+  // is, and the block that sees the last arrival must observe every such word before it overwrites them with zero
+  // (otherwise a zero could land first and a stale {inclusive|value} word would survive into the next launch).
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __threadfence();
+  }
   __syncthreads();
   if (s_last) {
     for (uint32_t t = threadIdx.x; t < gridDim.x; t += blockDim.x) state[t] = 0ull;

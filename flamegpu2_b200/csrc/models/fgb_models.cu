@@ -79,6 +79,8 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
       p.repulse = getf(kv, "repulse", p.repulse);
       p.sort_period = getu(kv, "sort_period", p.sort_period);
       p.env_max_z = getf(kv, "env_max_z", p.env_max_z);
+      p.validation = getu(kv, "validation", p.validation);
+      p.radius_filtered = getu(kv, "radius_filtered", p.radius_filtered);
       fgb_examples::define_circles(*s->model, p);
     } else if (name == "boids3d" || name == "boids2d") {
       fgb_examples::BoidsParams p;
@@ -103,12 +105,18 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
       p.radius = getf(kv, "radius", 1.f);
       p.sort_period = getu(kv, "sort_period", 1);
       p.bucket_upper = static_cast<int>(getu(kv, "bucket_upper", 12 + 512));
+      p.birth_optional = static_cast<int>(getu(kv, "birth_optional", 0));
+      p.birth_death = static_cast<int>(getu(kv, "birth_death", 0));
+      p.birth_condition = static_cast<int>(getu(kv, "birth_condition", 0));
+      p.birth_target = static_cast<int>(getu(kv, "birth_target", 0));
+      p.append_optional = static_cast<int>(getu(kv, "append_optional", 0));
       fgb_examples::define_test_model(*s->model, p);
     } else {
       throw std::runtime_error("unknown model '" + name + "'");
     }
     s->sim = std::make_unique<flamegpu::CUDASimulation>(*s->model);
     s->sim->CUDAConfig().device_id = device;
+    s->sim->CUDAConfig().inLayerConcurrency = getu(kv, "concurrency", 1) != 0;
     if (kv.count("win_count")) s->sim->setMessageWindow("location", static_cast<int>(getu(kv, "win_begin", 0)), static_cast<int>(getu(kv, "win_count", 0)));
     s->sim->CUDAConfig().useCUDAGraphs = getu(kv, "graphs", 1) != 0;
     s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
@@ -116,7 +124,8 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim->SimulationConfig().timing = getu(kv, "timing", 0) != 0;
     s->sim->CUDAConfig().profile = getu(kv, "profile", 0) != 0;
     s->sim->CUDAConfig().binOrderExecution = getu(kv, "bin_order", 1) != 0;
-    s->sim->CUDAConfig().spatialIterationMode = static_cast<int>(getu(kv, "iter_mode", 0));
+    // -1 (default): per function, as declared by the model; 0: reference visit order everywhere; 1: radius-filtered everywhere
+    s->sim->CUDAConfig().spatialIterationMode = kv.count("iter_mode") ? std::atoi(kv.at("iter_mode").c_str()) : -1;
     s->sim->CUDAConfig().overlapIndexBuild = getu(kv, "overlap", 1) != 0;
     s->sim->CUDAConfig().agentFunctionBlockSize = static_cast<int>(getu(kv, "block", 128));
     s->sim->CUDAConfig().tileLocalExecOrder = getu(kv, "tile_order", 1) != 0;
@@ -139,6 +148,7 @@ int fgbm_set_population(void *h, const char *agent, const char *state, unsigned 
     stg->resize(0);
     stg->resize(n);
     for (unsigned int v = 0; v < nvars; ++v) {
+      if (std::strcmp(names[v], "_n") == 0) continue;  // carries only the population size
       std::vector<char> &col = stg->raw(names[v]);
       std::memcpy(col.data(), host_ptrs[v], col.size());
     }
@@ -255,6 +265,12 @@ int fgbm_sync(void *h) {
 void *fgbm_stream(void *h) { return static_cast<Sim *>(h)->sim->getStream(); }
 unsigned long long fgbm_launch_count(void *h) { return static_cast<Sim *>(h)->sim->getLaunchCount(); }
 unsigned int fgbm_graph_count(void *h) { return static_cast<Sim *>(h)->sim->getGraphCount(); }
+// widest level (kernel nodes at equal depth) of the most recently captured step graph: > 1 means parallel branches
+unsigned int fgbm_graph_width(void *h) { return static_cast<Sim *>(h)->sim->getGraphWidth(); }
+// host-side launch bound and capacity of a state list (tests: both must stay bounded under conditional transitions)
+int fgbm_list_bound(void *h, const char *agent, const char *state, unsigned int *bound, unsigned int *capacity) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->getListBound(agent, state ? state : flamegpu::DEFAULT_STATE, bound, capacity); });
+}
 unsigned int fgbm_step_counter(void *h) { return static_cast<Sim *>(h)->sim->getStepCounter(); }
 
 // Per-step device times (seconds) recorded when the model was created with timing=1.

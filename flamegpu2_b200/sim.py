@@ -47,6 +47,9 @@ def lib():
         L.fgbm_launch_count.restype = C.c_ulonglong
         L.fgbm_graph_count.argtypes = [C.c_void_p]
         L.fgbm_graph_count.restype = C.c_uint
+        L.fgbm_graph_width.argtypes = [C.c_void_p]
+        L.fgbm_graph_width.restype = C.c_uint
+        L.fgbm_list_bound.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
         L.fgbm_step_counter.argtypes = [C.c_void_p]
         L.fgbm_step_counter.restype = C.c_uint
         L.fgbm_step_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint, C.POINTER(C.c_uint)]
@@ -132,6 +135,17 @@ class Simulation:
     @property
     def graphs(self) -> int:
         return int(lib().fgbm_graph_count(self.h))
+
+    @property
+    def graph_width(self) -> int:
+        """Kernel nodes on the widest level of the last captured step graph (> 1: parallel branches)."""
+        return int(lib().fgbm_graph_width(self.h))
+
+    def list_bound(self, agent: str, state: Optional[str] = None):
+        """(host-side launch bound, capacity) of a state list."""
+        b, c = C.c_uint(), C.c_uint()
+        _check(lib().fgbm_list_bound(self.h, agent.encode(), state.encode() if state else None, C.byref(b), C.byref(c)), "fgbm_list_bound")
+        return int(b.value), int(c.value)
 
     @property
     def step_counter(self) -> int:

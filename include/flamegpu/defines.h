@@ -5,6 +5,10 @@
 
 #include <cstdint>
 
+// Defined by THIS implementation of the FLAME GPU 2 API: model sources shared with the reference build use it to
+// guard the few b200 extension calls (e.g. AgentFunctionDescription::setMessageInputRadiusFiltered).
+#define FLAMEGPU2_B200 1
+
 namespace flamegpu {
 
 typedef unsigned int id_t;         // reference defines.h:8

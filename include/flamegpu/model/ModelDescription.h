@@ -113,6 +113,9 @@ struct AgentFunctionData {
   std::type_index out_type = std::type_index(typeid(void));
   std::string message_input, message_output;
   bool message_output_optional = false;
+  // b200 extension: the function ignores input messages beyond the list's radius of its search origin (it tests the
+  // distance itself), so the spatial iterator may skip them (radius-filtered lock-step walk, MessageSpatial3D.cuh)
+  bool radius_filtered_input = false;
   std::string agent_output, agent_output_state;
   bool has_agent_death = false;
   std::string initial_state = DEFAULT_STATE, end_state = DEFAULT_STATE;
@@ -300,6 +303,13 @@ class AgentFunctionDescription {
   template <typename Desc>
   void setMessageOutput(const Desc &d) { setMessageOutput(d.getName()); }
   void setMessageOutputOptional(bool optional) { function->message_output_optional = optional; }
+  // b200 extension (no reference counterpart).  Declares the radius contract of this function's spatial input: every
+  // message within the radius of the search origin is presented exactly once, in the reference's relative order;
+  // messages farther away MAY be skipped and far-away padding messages may be presented.  Safe for any function
+  // that tests the distance itself and neither breaks out of the loop nor counts rejected messages (Circles, Boids).
+  // CUDAConfig().spatialIterationMode = 0 overrides it (strict reference visit order for every function).
+  void setMessageInputRadiusFiltered(bool filtered) { function->radius_filtered_input = filtered; }
+  bool getMessageInputRadiusFiltered() const { return function->radius_filtered_input; }
   void setAgentOutput(const std::string &agent_name, const std::string &state = DEFAULT_STATE) {
     auto it = model->agents.find(agent_name);
     if (it == model->agents.end()) throw exception::InvalidAgentName("agent '" + agent_name + "' was not found");
@@ -487,23 +497,35 @@ class LayerDescription {
   std::shared_ptr<LayerData> layer;
 
  private:
-  // reference LayerDescription.cpp:35-85: functions of one layer run concurrently, so they may not
-  // share an agent state, nor read a message list another one writes
+  // reference LayerDescription.cpp:100-190: functions of one layer run concurrently, so they may not share an agent
+  // state, read a message list another one writes, nor birth into a state another one executes on
   void add(const std::shared_ptr<AgentFunctionData> &f) {
     if (!layer->host_functions.empty()) throw exception::InvalidLayerMember("a layer cannot hold both agent and host functions");
-    auto fp = f->parent.lock();
-    for (auto &g : layer->functions) {
-      if (g == f) throw exception::InvalidAgentFunc("function '" + f->name + "' is already in this layer");
-      auto gp = g->parent.lock();
-      if (gp == fp && (g->initial_state == f->initial_state || g->end_state == f->end_state || g->initial_state == f->end_state ||
-                       g->end_state == f->initial_state))
-        throw exception::InvalidAgentFunc("two functions of one layer share an agent state");
-      if ((!f->message_output.empty() && (f->message_output == g->message_input || f->message_output == g->message_output)) ||
-          (!g->message_output.empty() && g->message_output == f->message_input))
-        throw exception::InvalidLayerMember("functions of one layer may not write a message list another one uses");
-    }
+    for (auto &g : layer->functions) check_pair(*f, *g);
     layer->functions.push_back(f);
   }
+
+ public:
+  // Throws if f and g cannot run in the same layer.  Also used by CUDASimulation::initialise() to re-validate every
+  // layer, because setInitialState / setEndState / setAgentOutput may be called after the function joined its layer.
+  static void check_pair(const AgentFunctionData &f, const AgentFunctionData &g) {
+    if (&g == &f) throw exception::InvalidAgentFunc("function '" + f.name + "' is already in this layer");
+    auto fp = f.parent.lock(), gp = g.parent.lock();
+    if (gp == fp && (g.initial_state == f.initial_state || g.end_state == f.end_state || g.initial_state == f.end_state ||
+                     g.end_state == f.initial_state))
+      throw exception::InvalidAgentFunc("two functions of one layer share an agent state");
+    // births (reference LayerDescription.cpp:138-165): the state a function births into may not be the initial state
+    // of another member, in either direction
+    if (!f.agent_output.empty() && gp && gp->name == f.agent_output && g.initial_state == f.agent_output_state)
+      throw exception::InvalidLayerMember("function '" + f.name + "' births into the state function '" + g.name + "' executes on");
+    if (!g.agent_output.empty() && fp && fp->name == g.agent_output && f.initial_state == g.agent_output_state)
+      throw exception::InvalidLayerMember("function '" + g.name + "' births into the state function '" + f.name + "' executes on");
+    if ((!f.message_output.empty() && (f.message_output == g.message_input || f.message_output == g.message_output)) ||
+        (!g.message_output.empty() && g.message_output == f.message_input))
+      throw exception::InvalidLayerMember("functions of one layer may not write a message list another one uses");
+  }
+
+ private:
   std::shared_ptr<ModelData> model;
 };
 

@@ -38,14 +38,21 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
   if (MessageOut::HAS_OUTPUT) {
     // mandatory output into an emptied list: every executing agent writes exactly one message, so the count is
     // known here (the reference derives it on the host, CUDAMessage.cu:196-205; a separate 1-thread kernel before)
-    if (index == 0 && args.d_msg_out_count) *args.d_msg_out_count = n > offset ? n - offset : 0u;
+    if (index == 0 && args.d_msg_out_count) {
+      *args.d_msg_out_count = n > offset ? n - offset : 0u;
+      if (args.d_keyed) *args.d_keyed = n > offset ? n - offset : 0u;
+    }
   }
   if (index + offset >= n) return;
   // Run agents in the bin order of the input list when the scheduler provides it: lanes of a warp then
   // walk the same message strips (coalesced / broadcast loads).  Every per-agent slot (variables, scan
   // flags, message and new-agent slots) is addressed by the AGENT index, so results do not change.
   const unsigned int agent = args.exec_perm ? __ldg(args.exec_perm + index) : offset + index;
-  const unsigned int slot = agent - offset;  // message / new-agent slot: index among the executing agents
+  if (agent >= n) return;  // a stale permutation must never address outside the list (the scheduler versions it)
+  // message / new-agent slot: index among the executing agents, or -- for a mandatory output that the scheduler runs in
+  // bin order -- the thread index, so that the list is WRITTEN bin-grouped (any bijection agent <-> slot is a legal
+  // instance: the reference's order inside a PBM bin is atomic-arrival order)
+  const unsigned int slot = args.slot_by_thread ? index : agent - offset;
   DeviceAPI<MessageIn, MessageOut> api(args, agent, slot, ITER_MODE);
   const AGENT_STATUS status = AgentFunction()(&api);
   // one flag store per thread, no memset beforehand (reference AgentFunction.cuh:111-119 +
@@ -53,6 +60,7 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
   if (args.death_flag) args.death_flag[agent] = static_cast<unsigned int>(status);
   if (MessageOut::HAS_OUTPUT) {
     if (args.msg_out_flag) args.msg_out_flag[slot] = api.message_out.written() ? 1u : 0u;
+    if constexpr (MessageOut::SPATIAL) api.message_out.template publish_index<MessageOut::DIMS>();
   }
   api.agent_out.finalise();
 }

@@ -73,6 +73,17 @@ struct FunctionArgs {
   uint32_t agent_out_len[b200::kMaxVars];       // bytes per item
   const char *agent_out_defaults[b200::kMaxVars];  // device pointer to the default value
   SpatialMeta in_meta;
+  // Fused index build (mandatory spatial output into an emptied list): the kernel publishes the bin key of every
+  // message it writes and counts it in the list's histogram, so buildIndex starts at the scan and never re-reads the
+  // locations (fgb_spatial_writer_args / fgb_build_index_ex in flamegpu2_b200.h).  NULL: off.
+  unsigned int *out_keys;
+  unsigned int *out_hist;
+  unsigned int *d_keyed;         // receives the number of messages keyed here (== the list's new count)
+  float out_min[3];
+  float out_radius;
+  int out_grid_dim[3];
+  int out_win_begin, out_win_count;
+  unsigned int slot_by_thread;   // 1: message / new-agent slot = thread index (bin-ordered output), 0: = agent index
   const unsigned int *d_msg_in_count;   // brute-force style inputs
   const unsigned int *d_msg_out_offset; // append offset of the output list (NULL -> 0)
   unsigned int *d_msg_out_count;        // non-NULL: mandatory output into a truncated list, the kernel itself publishes

@@ -5,6 +5,8 @@
 #ifndef FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL2D_CUH_
 #define FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL2D_CUH_
 
+#include <type_traits>
+
 #include "flamegpu/runtime/detail/FunctionArgs.h"
 #include "flamegpu/runtime/messaging/MessageBruteForce.cuh"
 
@@ -319,11 +321,58 @@ class MessageSpatial2D {
   class Out : public MessageBruteForce::Out {
    public:
     __device__ __forceinline__ Out(const detail::FunctionArgs &args, unsigned int index)
-        : MessageBruteForce::Out(args, index) {}
+        : MessageBruteForce::Out(args, index), lx(0.f), ly(0.f), lz(0.f) {}
+    // the location is remembered in registers as it is written (through setLocation or setVariable("x"|"y"|"z")),
+    // so that the kernel wrapper can publish the message's bin without reading it back (publish_index)
+    template <typename T, unsigned int N>
+    __device__ __forceinline__ void setVariable(const char (&name)[N], T value) const {
+      MessageBruteForce::Out::setVariable<T>(name, value);
+      if constexpr (std::is_same<T, float>::value) {
+        const uint32_t h = detail::name_hash(name);  // folds to a constant
+        if (h == detail::kHashX) lx = value;
+        if (h == detail::kHashY) ly = value;
+        if (h == detail::kHashZ) lz = value;
+      }
+    }
+    template <typename T, flamegpu::size_type N, unsigned int M>
+    __device__ __forceinline__ void setVariable(const char (&name)[M], unsigned int index, T value) const {
+      MessageBruteForce::Out::setVariable<T, N>(name, index, value);
+    }
     __device__ __forceinline__ void setLocation(float x, float y) const {
       this->template setVariable<float>("x", x);
       this->template setVariable<float>("y", y);
     }
+    // bin of the written message: getGridPosition + getHash (reference MessageSpatial3DDevice.cuh:646-672), plane index
+    // rebased to the slab window exactly as fgb::bin_key (csrc/fgb_binsort.cuh); one warp-aggregated RED per distinct
+    // bin of the warp (the writer runs in bin order, so neighbouring lanes share bins)
+    template <int DIMS>
+    __device__ __forceinline__ void publish_index() const {
+      if (!a.out_keys) return;
+      auto cell = [&](int axis, float p) {
+        const int c = static_cast<int>(floorf(__fdiv_rn(p - a.out_min[axis], a.out_radius)));
+        const int d = a.out_grid_dim[axis];
+        return c < 0 ? 0 : (c >= d ? d - 1 : c);
+      };
+      const int cx = cell(0, lx);
+      int cy = cell(1, ly);
+      unsigned int key;
+      if (DIMS == 3) {
+        int cz = cell(2, lz) - a.out_win_begin;
+        cz = cz < 0 ? 0 : (cz >= a.out_win_count ? a.out_win_count - 1 : cz);
+        key = (static_cast<unsigned int>(cz) * a.out_grid_dim[1] + cy) * a.out_grid_dim[0] + cx;
+      } else {
+        cy -= a.out_win_begin;
+        cy = cy < 0 ? 0 : (cy >= a.out_win_count ? a.out_win_count - 1 : cy);
+        key = static_cast<unsigned int>(cy) * a.out_grid_dim[0] + cx;
+      }
+      a.out_keys[slot] = key;
+      const unsigned int active = __activemask();
+      const unsigned int peers = __match_any_sync(active, key);
+      if ((threadIdx.x & 31u) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(a.out_hist + key, static_cast<unsigned int>(__popc(peers)));
+    }
+
+   protected:
+    mutable float lx, ly, lz;
   };
 #endif  // __CUDACC__
 };

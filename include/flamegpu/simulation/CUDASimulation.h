@@ -92,6 +92,16 @@ struct DevList {
   unsigned int count_slot = 0;  // control-block slot of the device count
   unsigned int appended_this_step = 0;  // upper bound of what listAppend added since the last endStep
   bool double_buffered = true;
+  // the owning simulation's allocation generation, bumped whenever a buffer of this list moves: launches captured
+  // into a CUDA graph hold raw pointers, CUDASimulation::step() drops its cached graphs when the generation moved
+  unsigned long long *gen = nullptr;
+  // Bin-order permutation of this list's items computed by its most recent spatial reader (thread t ran item
+  // cached_perm[t]); valid while the list's membership and order are unchanged (order_version).  A mandatory spatial
+  // OUTPUT function of the same list reuses it to write its messages bin-grouped (run_function step 3).
+  unsigned long long order_version = 1, cached_perm_version = 0;
+  const unsigned int *cached_perm = nullptr;
+  void touch() { ++order_version; }
+  bool perm_valid() const { return cached_perm != nullptr && cached_perm_version == order_version; }
 
   void init(const VariableMap &vars, bool dbl) {
     double_buffered = dbl;
@@ -110,6 +120,7 @@ struct DevList {
   // grow to at least `need` items, keeping the first `keep` items of data[]
   void reserve(unsigned int need, unsigned int keep) {
     if (need <= capacity) return;
+    if (gen) ++*gen;
     unsigned int cap = std::max(capacity, 256u);
     while (cap < need) cap = static_cast<unsigned int>(std::min<unsigned long long>(0xFFFFFFF0ull, static_cast<unsigned long long>(cap) * 5 / 4 + 64));
     cap = (cap + 63u) & ~63u;
@@ -127,8 +138,9 @@ struct DevList {
     }
     capacity = cap;
   }
-  void swap_buffers() {
+  void swap_buffers() {  // every caller swaps because it just reordered or compacted the list
     for (size_t v = 0; v < names.size(); ++v) std::swap(data[v], swap[v]);
+    touch();
   }
   void release() {
     for (auto &p : data)
@@ -168,8 +180,10 @@ struct DevList {
 struct DevFlags {  // grow-only u32 scan-flag array (one per thread of a function)
   unsigned int *p = nullptr;
   unsigned int cap = 0;
+  unsigned long long *gen = nullptr;  // see DevList::gen
   void reserve(unsigned int n) {
     if (n <= cap) return;
+    if (gen) ++*gen;
     if (p) cudaFree(p);
     cap = (n + n / 4 + 255u) & ~255u;
     FGB_CUDA_THROW(cudaMalloc(&p, static_cast<size_t>(cap) * 4));
@@ -190,6 +204,11 @@ struct CUDAMessage {
   fgb_spatial_metadata md{};
   bool pbm_dirty = true;
   bool truncate = true;
+  // fused index build: the function that wrote the list published every message's bin key and histogram count
+  bool keyed_by_writer = false;      // keys + histogram exist for the first *keyed_slot items
+  bool appended_after_keyed = false; // ... and more items were appended since (they are keyed by the build)
+  bool hist_dirty = false;           // the histogram holds counts that no build has consumed yet
+  unsigned int keyed_slot = 0;       // control word: number of items keyed by the writer
   int win_begin = 0, win_count = -1;  // slab window (planes of the slowest axis held by this process)
 };
 
@@ -198,6 +217,15 @@ struct CUDAAgent {
   std::map<std::string, DevList> states;
   unsigned int next_id_slot = 0;
   id_t host_next_id = 1;
+  // Host-known upper bound of the agents of this type over ALL states.  State transitions move agents between
+  // lists but cannot create any, so a list bound never needs to exceed it: without this clamp a conditional
+  // transition A -> B adds the source bound to B's bound every step (the device counts are not read back).
+  unsigned int pop_bound = 0;
+  void recompute_pop_bound() {
+    unsigned long long t = 0;
+    for (const auto &s : states) t += s.second.bound;
+    pop_bound = static_cast<unsigned int>(std::min<unsigned long long>(t, 0xFFFFFFF0ull));
+  }
 };
 
 struct FunctionRT {
@@ -288,12 +316,16 @@ class CUDASimulation {
     bool inLayerConcurrency = true;
     bool useCUDAGraphs = true;        // b200: capture each step as a CUDA graph
     bool stableMessageOrder = false;  // b200: deterministic (source) order inside PBM bins
-    int spatialIterationMode = 0;     // b200: 0 reference order, 1 radius-filtered lock-step walk (FunctionArgs.h)
+    int spatialIterationMode = -1;    // b200: -1 per function (radius-filtered where the function declared the radius
+                                      // contract, setMessageInputRadiusFiltered), 0 reference order everywhere,
+                                      // 1 radius-filtered lock-step walk for every spatial reader (FunctionArgs.h)
     bool binOrderExecution = true;    // b200: run functions that read spatial messages in bin order
     int agentFunctionBlockSize = 128;  // b200: threads per block of the agent function kernels
     bool tileLocalExecOrder = true;   // b200: bin-order execution groups inside 2048-agent tiles when the list was just sorted
     bool overlapIndexBuild = true;    // b200: build the input list's PBM on a second stream while the agents are sorted
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
+    bool fusedIndexBuild = true;      // b200: mandatory spatial output publishes bin keys + histogram (buildIndex starts at the scan)
+    bool binOrderedOutput = true;     // b200: mandatory spatial output writes its messages in the bin order of the last reader
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
                                       // key collapses z, CUDASimulation.cu:487; see sort_geometry())
   };
@@ -384,6 +416,13 @@ class CUDASimulation {
   HostAPI &hostAPI() { return host_api; }
   unsigned long long getLaunchCount() const { return (ctx ? fgb_launch_count(ctx) : 0ull) + own_launches; }
   unsigned int getGraphCount() const { return static_cast<unsigned int>(graphs.size()); }
+  unsigned int getGraphWidth() const { return last_graph_width; }
+  void getListBound(const std::string &agent_name, const std::string &state, unsigned int *bound, unsigned int *capacity) {
+    initialise();
+    const detail::DevList &l = state_list(agent_name, state);
+    if (bound) *bound = l.bound;
+    if (capacity) *capacity = l.capacity;
+  }
   cudaStream_t getStream() const { return main_stream; }
   // phase name -> (total milliseconds, calls) since the last call; only filled when CUDAConfig().profile
   std::map<std::string, std::pair<double, unsigned int>> getProfile();
@@ -430,9 +469,11 @@ class CUDASimulation {
   void record_end_of_step(cudaStream_t main);
   void run_function(detail::FunctionRT &f, cudaStream_t st, unsigned int stream_id);
   void build_input_index(detail::CUDAMessage &M, cudaStream_t st);
+  bool filtered_iteration(const detail::FunctionRT &f) const;
   void refresh_bounds();                    // births only: read the counts back once per step
   int sort_geometry(const detail::FunctionRT &f, float mn[3], float width[3], unsigned int gd[3]) const;
   std::vector<unsigned long long> graph_key() const;
+  static unsigned int graph_width(cudaGraph_t graph);
   static unsigned int quantise(unsigned int n) {
     if (n <= 4096u) return (n + 255u) & ~255u;
     unsigned int p = 1u;
@@ -473,6 +514,7 @@ class CUDASimulation {
   cudaEvent_t ctrl_events[2] = {nullptr, nullptr};
   unsigned long long pipelined_steps = 0;
   std::vector<std::vector<detail::FunctionRT>> layers;  // [layer][function]
+  std::vector<bool> layer_serial;                        // layer whose members must not run concurrently
   bool model_has_births = false;
   bool model_has_host_layers = false;
   unsigned int step_count = 0;
@@ -486,6 +528,9 @@ class CUDASimulation {
     std::vector<unsigned long long> post_state;
   };
   std::vector<GraphEntry> graphs;
+  unsigned int last_graph_width = 0;
+  unsigned long long alloc_gen = 0;          // bumped by every reallocation of a list / flag array of this simulation
+  unsigned long long graphs_generation = 0;  // allocation generation the cached graphs were captured under
   struct ProfRec {
     std::string name;
     cudaEvent_t e0, e1;

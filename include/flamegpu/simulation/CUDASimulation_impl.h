@@ -54,7 +54,9 @@ inline void CUDASimulation::initialise() {
     detail::CUDAMessage &m = messages[mp.first];
     m.desc = mp.second;
     m.list.init(mp.second->variables, true);
+    m.list.gen = &alloc_gen;
     m.list.count_slot = alloc_slot();
+    m.keyed_slot = alloc_slot();
     if (!mp.second->persistent) zero_slots.push_back(m.list.count_slot);
     if (mp.second->dims() > 0) {
       if (!(mp.second->radius > 0.f)) throw exception::InvalidMessageType("spatial message '" + mp.first + "' has no radius");
@@ -88,6 +90,7 @@ inline void CUDASimulation::initialise() {
     for (const auto &s : ap.second->states) {
       detail::DevList &l = a.states[s];
       l.init(ap.second->variables, true);
+      l.gen = &alloc_gen;
       l.count_slot = alloc_slot();
     }
   }
@@ -99,6 +102,18 @@ inline void CUDASimulation::initialise() {
 
   size_t max_width = 1;
   for (auto &lp : model->layers) {
+    // functions may have changed states / outputs after they joined the layer: validate again (reference
+    // LayerDescription.cpp:100-190 validates at add time only, ModelData::validate at construction)
+    bool shared_birth_target = false;
+    for (size_t i = 0; i < lp->functions.size(); ++i)
+      for (size_t j = i + 1; j < lp->functions.size(); ++j) {
+        LayerDescription::check_pair(*lp->functions[i], *lp->functions[j]);
+        const AgentFunctionData &fi = *lp->functions[i], &fj = *lp->functions[j];
+        if (!fi.agent_output.empty() && fi.agent_output == fj.agent_output && fi.agent_output_state == fj.agent_output_state)
+          shared_birth_target = true;
+      }
+    // two members appending newborns to the same list would race on its count word: such a layer runs serially
+    layer_serial.push_back(shared_birth_target);
     layers.emplace_back();
     if (!lp->host_functions.empty()) model_has_host_layers = true;
     for (auto &fp : lp->functions) {
@@ -112,6 +127,8 @@ inline void CUDASimulation::initialise() {
       f.tmp_slot = alloc_slot();
       f.failed_slot = alloc_slot();
       f.active_slot = alloc_slot();
+      for (detail::DevFlags *fl : {&f.death_flag, &f.msg_flag, &f.birth_flag, &f.cond_flag, &f.move_flag, &f.exec_perm}) fl->gen = &alloc_gen;
+      f.scratch_new.gen = &alloc_gen;
       if (!fp->agent_output.empty()) {
         model_has_births = true;
         f.out_agent = &agent_rt(fp->agent_output);
@@ -259,6 +276,8 @@ inline void CUDASimulation::setPopulationData(AgentVector &pop, const std::strin
     write_slot(a.next_id_slot, a.host_next_id);
   }
   l.bound = model_has_births ? quantise(n) : n;
+  l.touch();
+  a.recompute_pop_bound();
   l.reserve(std::max(l.bound, 1u), 0);
   for (size_t v = 0; v < l.names.size(); ++v) {
     const size_t b = l.meta[v].bytes();
@@ -315,6 +334,8 @@ inline void CUDASimulation::setPopulationDataSoA(const std::string &agent_name, 
     l.reserve(std::max(bound, 1u), 0);
   }
   l.bound = bound;
+  l.touch();
+  a.recompute_pop_bound();
   for (size_t v = 0; v < l.names.size(); ++v) {
     const size_t b = l.meta[v].bytes();
     const void *src = nullptr;
@@ -395,12 +416,16 @@ inline std::vector<unsigned long long> CUDASimulation::snapshot_host_state() con
       s.push_back(reinterpret_cast<unsigned long long>(l.data[v]));
       s.push_back(reinterpret_cast<unsigned long long>(l.swap[v]));
     }
+    s.push_back(l.perm_valid() ? reinterpret_cast<unsigned long long>(l.cached_perm) : 0ull);
   };
-  for (const auto &a : agents)
+  for (const auto &a : agents) {
+    s.push_back(a.second.pop_bound);
     for (const auto &st : a.second.states) put_list(st.second);
+  }
   for (const auto &m : messages) {
     put_list(m.second.list);
-    s.push_back((m.second.pbm_dirty ? 1ull : 0ull) | (m.second.truncate ? 2ull : 0ull));
+    s.push_back((m.second.pbm_dirty ? 1ull : 0ull) | (m.second.truncate ? 2ull : 0ull) | (m.second.keyed_by_writer ? 4ull : 0ull) |
+                (m.second.appended_after_keyed ? 8ull : 0ull) | (m.second.hist_dirty ? 16ull : 0ull));
   }
   return s;
 }
@@ -413,14 +438,21 @@ inline void CUDASimulation::restore_host_state(const std::vector<unsigned long l
       l.data[v] = reinterpret_cast<char *>(s[k++]);
       l.swap[v] = reinterpret_cast<char *>(s[k++]);
     }
+    l.cached_perm = reinterpret_cast<const unsigned int *>(s[k++]);
+    l.cached_perm_version = l.cached_perm ? l.order_version : 0ull;
   };
-  for (auto &a : agents)
+  for (auto &a : agents) {
+    a.second.pop_bound = static_cast<unsigned int>(s[k++]);
     for (auto &st : a.second.states) get_list(st.second);
+  }
   for (auto &m : messages) {
     get_list(m.second.list);
     const unsigned long long f = s[k++];
     m.second.pbm_dirty = (f & 1ull) != 0;
     m.second.truncate = (f & 2ull) != 0;
+    m.second.keyed_by_writer = (f & 4ull) != 0;
+    m.second.appended_after_keyed = (f & 8ull) != 0;
+    m.second.hist_dirty = (f & 16ull) != 0;
   }
 }
 inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
@@ -436,7 +468,8 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
   k.push_back(sort_bits);
   k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull) |
               (cuda_config.binOrderExecution ? 4ull : 0ull) | (cuda_config.overlapIndexBuild ? 8ull : 0ull) |
-              (cuda_config.tileLocalExecOrder ? 16ull : 0ull) | (static_cast<unsigned long long>(cuda_config.spatialIterationMode) << 8));
+              (cuda_config.tileLocalExecOrder ? 16ull : 0ull) | (cuda_config.fusedIndexBuild ? 32ull : 0ull) |
+              (cuda_config.binOrderedOutput ? 64ull : 0ull) | (static_cast<unsigned long long>(cuda_config.spatialIterationMode + 1) << 8));
   return k;
 }
 
@@ -474,6 +507,8 @@ inline void CUDASimulation::plan_step() {
   };
   std::map<const detail::CUDAMessage *, bool> trunc;
   for (auto &m : messages) trunc[&m.second] = true;
+  std::map<const detail::CUDAAgent *, unsigned int> pop;  // running population bounds (births raise them)
+  for (auto &a : agents) pop[&a.second] = a.second.pop_bound;
   for (auto &layer : layers)
     for (auto &f : layer) {
       detail::DevList &L = f.agent->states.at(f.fn->initial_state);
@@ -500,7 +535,7 @@ inline void CUDASimulation::plan_step() {
       if (f.fn->initial_state != f.fn->end_state) {
         detail::DevList &E = f.agent->states.at(f.fn->end_state);
         unsigned int &eb = bound_of(E);
-        eb += n;
+        eb = std::min(eb + n, std::max(pop[f.agent], 1u));
         E.reserve(eb, E.capacity);
       }
       if (f.out_agent) {
@@ -510,6 +545,7 @@ inline void CUDASimulation::plan_step() {
         unsigned int &tb = bound_of(T);
         if (&T == &L && f.fn->initial_state != f.fn->end_state) tb = n;
         else tb += n;
+        pop[f.out_agent] += n;
         T.reserve(tb, T.capacity);
       }
       if (f.fn->initial_state != f.fn->end_state && !f.fn->condition &&
@@ -600,6 +636,8 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
                                       reinterpret_cast<const float *>(L.data[iy]),
                                       iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, f.exec_perm.p,
                                       sorted_now ? FGB_BUILD_TILE_LOCAL : FGB_BUILD_DEFAULT, st));
+    L.cached_perm = f.exec_perm.p;  // an output function of this list may reuse it while the list is unchanged
+    L.cached_perm_version = L.order_version;
     prof_end(st);
   }
 
@@ -632,21 +670,47 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       a.in_meta.win_begin = M.win_begin;
       a.in_meta.win_count = M.win_count;
       a.in_meta.radius = M.md.radius;
-      a.in_meta.iter_mode = cuda_config.spatialIterationMode;
+      a.in_meta.iter_mode = filtered_iteration(f) ? 1 : 0;
       a.in_meta.radius2_eps = M.md.radius * M.md.radius * 1.00001f;
       a.in_meta.wrap_compatible = M.md.wrap_compatible ? 1 : 0;
       a.in_meta.pbm = M.md.PBM;
     }
   }
   if (f.msg_out) {
-    detail::DevList &O = f.msg_out->list;
-    O.reserve((f.msg_out->truncate ? 0u : O.bound) + n, O.capacity);
+    detail::CUDAMessage &MO = *f.msg_out;
+    detail::DevList &O = MO.list;
+    O.reserve((MO.truncate ? 0u : O.bound) + n, O.capacity);
     O.fill_table(a.msg_out, /*use_swap=*/true);  // functions write the swap list at their thread index
+    const bool plain = !fn.message_output_optional && MO.truncate;  // every executing agent writes one message into an emptied list
     if (fn.message_output_optional) {
       f.msg_flag.reserve(n);
       a.msg_out_flag = f.msg_flag.p;
-    } else if (f.msg_out->truncate) {
+    } else if (MO.truncate) {
       a.d_msg_out_count = slot_ptr(O.count_slot);  // published by the function kernel itself (step 5)
+    }
+    if (plain && MO.spatial && !MO.bucket) {
+      // bin-ordered output: thread t writes slot t for agent perm[t], perm = bin order of the list's last spatial reader.
+      // Positions have moved a little since, so the list arrives NEARLY bin-grouped: every tile takes the direct scatter.
+      if (cuda_config.binOrderedOutput && !bin_order && !conditional && !f.out_agent && L.perm_valid()) {
+        a.exec_perm = L.cached_perm;
+        a.slot_by_thread = 1u;
+      }
+      if (cuda_config.fusedIndexBuild) {
+        if (MO.hist_dirty)  // keyed by an earlier writer but never built: start from a clean histogram
+          FGB_ABI_THROW(fgb_spatial_clear_histogram(MO.spatial, st));
+        unsigned int *keys = nullptr, *hist = nullptr;
+        FGB_ABI_THROW(fgb_spatial_writer_args(MO.spatial, n, &keys, &hist));
+        a.out_keys = keys;
+        a.out_hist = hist;
+        for (int k = 0; k < 3; ++k) {
+          a.out_min[k] = MO.md.min[k];
+          a.out_grid_dim[k] = static_cast<int>(MO.md.grid_dim[k]);
+        }
+        a.out_radius = MO.md.radius;
+        a.out_win_begin = MO.win_begin;
+        a.out_win_count = MO.win_count;
+        a.d_keyed = slot_ptr(MO.keyed_slot);
+      }
     }
   }
   if (f.out_agent) {
@@ -676,7 +740,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     if (index_pending && f.msg_in && f.msg_in->spatial) FGB_CUDA_THROW(cudaStreamWaitEvent(st, index_done, 0));
     prof_begin("function:" + fn.name, st);
     // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
-    const bool filtered = f.msg_in && f.msg_in->spatial && !f.msg_in->bucket && cuda_config.spatialIterationMode != 0 && fn.func_filtered;
+    const bool filtered = filtered_iteration(f);
     const size_t smem = filtered ? sizeof(uint32_t) * detail::kFilterQueueWords * bs : 0;
     FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(filtered ? fn.func_filtered : fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, smem, st));
     prof_end(st);
@@ -696,11 +760,20 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     } else if (O.truncate) {
       O.list.swap_buffers();  // the count word was written by the function kernel (FunctionArgs::d_msg_out_count)
       O.list.bound = n;
+      if (a.out_keys) {
+        O.keyed_by_writer = true;
+        O.appended_after_keyed = false;
+        O.hist_dirty = true;
+      }
     } else {
       std::vector<fgb_var> vars = O.list.vars(false);
       FGB_ABI_THROW(fgb_compact(ctx, sid, nullptr, 0, n, d_exec, n, 0, d_mc, vars.data(), static_cast<unsigned int>(vars.size()), nullptr,
                                 d_mc, st));
       O.list.bound += n;
+    }
+    if (!a.out_keys) {
+      if (O.truncate) O.keyed_by_writer = false;      // a plain (unfused) rewrite of the list
+      else if (O.keyed_by_writer) O.appended_after_keyed = true;  // the appended items are keyed by the build
     }
     O.truncate = false;
     O.pbm_dirty = true;  // reference CUDASimulation.cu:1057-1059
@@ -724,7 +797,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     }
   } else {
     detail::DevList &E = f.agent->states.at(fn.end_state);
-    E.reserve(E.bound + n, E.capacity);
+    E.reserve(std::min(E.bound + n, std::max(f.agent->pop_bound, 1u)), E.capacity);
     std::vector<fgb_var> vars(L.names.size());
     for (size_t v = 0; v < vars.size(); ++v) {
       vars[v].type_len = L.meta[v].bytes();
@@ -742,12 +815,15 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       FGB_ABI_THROW(fgb_compact(ctx, sid, fn.has_agent_death ? f.death_flag.p : nullptr, 0, n, d_n, fn.has_agent_death ? 0u : n, 0, d_ec,
                                 vars.data(), static_cast<unsigned int>(vars.size()), nullptr, d_ec, st));
     }
-    E.bound += n;
+    E.bound = std::min(E.bound + n, std::max(f.agent->pop_bound, 1u));  // a transition creates no agents
+    E.touch();
+    L.touch();
   }
 
   // 7. births appended after the survivors, in parent order (reference CUDAAgentStateList.cu:189-250)
   bool births_into_vacated = false;
   if (births) {
+    f.out_agent->pop_bound += n;
     T->reserve(T->bound + n, T->capacity);
     std::vector<fgb_var> vars(f.scratch_new.names.size());
     for (size_t v = 0; v < vars.size(); ++v) {
@@ -760,13 +836,16 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     if (T == &L && same_state) {
       FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, fn.has_agent_death ? d_tmp : d_n, vars.data(), nv, nullptr, d_n, st));
       L.bound += n;
+      L.touch();
     } else if (T == &L) {  // the initial state was vacated by the transition: children start at 0
       FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
       births_into_vacated = true;
       L.bound = n;
+      L.touch();
     } else {
       FGB_ABI_THROW(fgb_compact(ctx, sid, f.birth_flag.p, 0, n, d_exec, 0, 0, d_tc, vars.data(), nv, nullptr, d_tc, st));
       T->bound += n;
+      T->touch();
       if (same_state && fn.has_agent_death) {
         detail::k_copy_word<<<1, 1, 0, st>>>(d_n, d_tmp);
         ++own_launches;
@@ -783,6 +862,13 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     }
   }
   prof_end(st);
+}
+
+// which iterator variant a function runs with (CUDAConfig().spatialIterationMode)
+inline bool CUDASimulation::filtered_iteration(const detail::FunctionRT &f) const {
+  if (!(f.msg_in && f.msg_in->spatial && !f.msg_in->bucket && f.fn->func_filtered)) return false;
+  const int mode = cuda_config.spatialIterationMode;
+  return mode > 0 || (mode < 0 && f.fn->radius_filtered_input);
 }
 
 inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream_t st) {
@@ -803,14 +889,19 @@ inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream
     prof_begin("build_index", st);
     std::vector<fgb_var> vars = M.list.vars(true);
     const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
-    FGB_ABI_THROW(fgb_build_index(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
-                                  reinterpret_cast<const float *>(M.list.data[iy]),
-                                  iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
-                                  static_cast<unsigned int>(vars.size()),
-                                  cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT, st));
+    unsigned int flags = cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT;
+    if (M.keyed_by_writer) flags |= FGB_BUILD_KEYS_READY;
+    FGB_ABI_THROW(fgb_build_index_ex(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
+                                     reinterpret_cast<const float *>(M.list.data[iy]),
+                                     iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
+                                     static_cast<unsigned int>(vars.size()), flags,
+                                     (M.keyed_by_writer && M.appended_after_keyed) ? slot_ptr(M.keyed_slot) : nullptr, nullptr, st));
     M.list.swap_buffers();
     prof_end(st);
   }
+  M.keyed_by_writer = false;  // the sorted list has new slots; the histogram was consumed (and re-zeroed) by the scan
+  M.appended_after_keyed = false;
+  M.hist_dirty = false;
   M.pbm_dirty = false;
 }
 
@@ -835,7 +926,7 @@ inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_
       FGB_CUDA_THROW(cudaEventRecord(index_done, index_stream));
       index_pending = true;
     }
-    const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty();
+    const bool fork = cuda_config.inLayerConcurrency && layer.size() > 1 && !side_streams.empty() && !layer_serial[li];
     if (fork) FGB_CUDA_THROW(cudaEventRecord(fork_event, main));
     for (size_t i = 0; i < layer.size(); ++i) {
       cudaStream_t st = fork ? side_streams[i] : main;
@@ -867,6 +958,8 @@ inline void CUDASimulation::record_end_of_step(cudaStream_t main) {
     if (!m.second.desc->persistent) {
       m.second.truncate = true;
       m.second.pbm_dirty = true;
+      m.second.keyed_by_writer = false;  // (hist_dirty stays: an unbuilt histogram is cleared by the next fused writer)
+      m.second.appended_after_keyed = false;
     }
 }
 
@@ -916,8 +1009,10 @@ inline void CUDASimulation::endStepPipelined() {
         l.bound = std::max(l.bound, 1u);
       }
   }
-  for (auto &a : agents)
+  for (auto &a : agents) {
     for (auto &s : a.second.states) s.second.appended_this_step = 0;
+    a.second.recompute_pop_bound();
+  }
   for (auto &m : messages) m.second.list.appended_this_step = 0;
   ++pipelined_steps;
 }
@@ -997,7 +1092,9 @@ inline void CUDASimulation::listAppend(bool is_message, const std::string &name,
   FGB_ABI_THROW(fgb_compact(ctx, xslot, nullptr, 0, n_max, d_n_src, n_max, 0, d_n, vars.data(), static_cast<unsigned int>(vars.size()),
                             nullptr, d_n, xs));
   l.bound += n_max;
+  l.touch();
   l.appended_this_step += n_max;
+  if (!is_message) agent_rt(name).pop_bound += n_max;
   if (is_message) messages.at(name).pbm_dirty = true;
 }
 
@@ -1023,6 +1120,7 @@ inline void CUDASimulation::refresh_bounds() {
   for (auto &a : agents) {
     a.second.host_next_id = h[a.second.next_id_slot];
     for (auto &s : a.second.states) s.second.bound = quantise(h[s.second.count_slot]);
+    a.second.recompute_pop_bound();
   }
 }
 
@@ -1037,6 +1135,16 @@ inline bool CUDASimulation::step() {
     FGB_CUDA_THROW(cudaEventRecord(e0, main_stream));
   }
   if (cuda_config.useCUDAGraphs && !model_has_host_layers && !cuda_config.profile) {
+    // the key covers list pointers, bounds and capacities; grow-only scratch (scan flags, exec_perm, the kernel
+    // library's per-stream scratch and per-list index buffers) is covered by the allocation generation: any
+    // reallocation since the capture invalidates every cached graph (they hold the freed pointers)
+    const unsigned long long gen = alloc_gen + fgb_alloc_generation(ctx);
+    if (gen != graphs_generation) {
+      for (auto &g : graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      graphs.clear();
+      graphs_generation = gen;
+    }
     const std::vector<unsigned long long> key = graph_key();
     GraphEntry *hit = nullptr;
     for (auto &g : graphs)
@@ -1056,6 +1164,7 @@ inline bool CUDASimulation::step() {
         throw;
       }
       FGB_CUDA_THROW(cudaStreamEndCapture(main_stream, &graph));
+      last_graph_width = graph_width(graph);
       GraphEntry g;
       g.key = key;
       FGB_CUDA_THROW(cudaGraphInstantiate(&g.exec, graph, 0));
@@ -1092,6 +1201,40 @@ inline bool CUDASimulation::step() {
     if (ec(&host_api)) go_on = false;
   }
   return go_on;
+}
+
+// Widest level of a captured graph: nodes are levelled by their longest path from a root; the width is the largest
+// number of KERNEL nodes on one level.  1 = a chain; functions of one layer on their own streams show up as > 1.
+inline unsigned int CUDASimulation::graph_width(cudaGraph_t graph) {
+  size_t nn = 0, ne = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &nn) != cudaSuccess || nn == 0) return 0;
+  std::vector<cudaGraphNode_t> nodes(nn);
+  cudaGraphGetNodes(graph, nodes.data(), &nn);
+  cudaGraphGetEdges(graph, nullptr, nullptr, &ne);
+  std::vector<cudaGraphNode_t> from(ne), to(ne);
+  if (ne) cudaGraphGetEdges(graph, from.data(), to.data(), &ne);
+  std::map<cudaGraphNode_t, size_t> id;
+  for (size_t i = 0; i < nn; ++i) id[nodes[i]] = i;
+  std::vector<unsigned int> depth(nn, 0);
+  for (size_t pass = 0; pass < nn; ++pass) {  // longest-path relaxation (graphs of a step have tens of nodes)
+    bool changed = false;
+    for (size_t e = 0; e < ne; ++e) {
+      const size_t a = id[from[e]], b = id[to[e]];
+      if (depth[b] < depth[a] + 1) {
+        depth[b] = depth[a] + 1;
+        changed = true;
+      }
+    }
+    if (!changed) break;
+  }
+  std::map<unsigned int, unsigned int> per_level;
+  unsigned int width = 0;
+  for (size_t i = 0; i < nn; ++i) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    width = std::max(width, ++per_level[depth[i]]);
+  }
+  return width;
 }
 
 inline void CUDASimulation::simulate() {

@@ -128,7 +128,10 @@ enum fgb_build_flags {
   FGB_BUILD_STABLE = 1,
   /* fgb_bin_permutation only: group equal bins inside tiles of 2048 consecutive points instead of globally
    * (one pass, the PBM is not written).  For lists that are already coarsely ordered. */
-  FGB_BUILD_TILE_LOCAL = 2
+  FGB_BUILD_TILE_LOCAL = 2,
+  /* fgb_build_index_ex only: the bin key of the leading items and their histogram contribution were already written
+   * by the list's writer (fgb_spatial_writer_args); see fgb_build_index_ex */
+  FGB_BUILD_KEYS_READY = 4
 };
 
 /* MessageSpatial3D::CUDAModelHandler::buildIndex (MessageSpatial3D.cu:113-146) and
@@ -147,6 +150,22 @@ fgb_status fgb_build_index(fgb_spatial *sp, unsigned int n, const unsigned int *
  * MessageBucket::CUDAModelHandler (src/flamegpu/runtime/messaging/MessageBucket.cu:36-78): keys
  * lower_bound..upper_bound (inclusive), bucketCount = upper_bound - lower_bound + 1, PBM of bucketCount + 1 words,
  * zeroed (:69).  The handle is an fgb_spatial (destroy / read_pbm / reserve apply); positional entry points reject it. */
+/* b200 extension: the fused form of buildIndex.  The reference's atomicHistogram3D (MessageSpatial3D.cu:54-72) re-reads
+ * the location of every message right after the output function wrote it; here the kernel that WRITES a list can
+ * publish, per message slot i, keys[i] = bin of the message (getGridPosition3D + getHash3D arithmetic, window-rebased)
+ * and add 1 to hist[keys[i]] (fgb_spatial_writer_args returns both device arrays, sized for n_max items; hist must
+ * only be touched between two builds).  fgb_build_index_ex(FGB_BUILD_KEYS_READY) then starts at the scan:
+ *   d_keyed == NULL : every item of the list was keyed by its writer;
+ *   d_keyed != NULL : only the first *d_keyed items were (device word); the items behind them -- e.g. ghost messages
+ *                     appended by the slab exchange -- are keyed and counted here, the others are not read again.
+ * src_slot_out (may be NULL): src_slot_out[j] = slot the message at sorted position j came from. */
+fgb_status fgb_spatial_writer_args(fgb_spatial *sp, unsigned int n_max, unsigned int **d_keys, unsigned int **d_hist);
+/* zeroes the histogram: only needed when a writer published counts that no fgb_build_index_ex consumed */
+fgb_status fgb_spatial_clear_histogram(fgb_spatial *sp, void *stream);
+fgb_status fgb_build_index_ex(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const float *x, const float *y,
+                              const float *z, const fgb_var *vars, unsigned int nvars, unsigned int flags,
+                              const unsigned int *d_keyed, unsigned int *src_slot_out, void *stream);
+
 fgb_status fgb_bucket_create(fgb_ctx *ctx, int lower_bound, int upper_bound, fgb_spatial **out);
 /* MessageBucket::MetaData {min, max (exclusive), PBM} (include/flamegpu/runtime/messaging/MessageBucket.h:40-55) */
 fgb_status fgb_bucket_get_bounds(const fgb_spatial *sp, int *min_key, int *max_key_exclusive, const unsigned int **d_pbm);
@@ -265,6 +284,13 @@ fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max);
 
 /* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
 unsigned long long fgb_launch_count(const fgb_ctx *ctx);
+
+/* Allocation generation of `ctx`: incremented whenever scratch owned by the context or by one of its
+ * fgb_spatial handles is (re)allocated.  Kernels captured into a CUDA graph hold the old pointers, so a
+ * caller that replays graphs compares this value before each replay and re-captures when it moved (the
+ * reference keeps its scratch in CubTemporaryMemory / CUDAScanCompaction, which it resizes between
+ * launches, never under a graph: src/flamegpu/simulation/detail/CubTemporaryMemory.cu:23-32). */
+unsigned long long fgb_alloc_generation(const fgb_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -107,9 +107,11 @@ unsigned int getu(const std::map<std::string, std::string> &kv, const char *k, u
   return it == kv.end() ? d : static_cast<unsigned int>(std::strtoul(it->second.c_str(), nullptr, 10));
 }
 
-void dump_agents(flamegpu::CUDASimulation &sim, flamegpu::ModelDescription &model, const std::string &agent, const std::string &prefix) {
+void dump_agents(flamegpu::CUDASimulation &sim, flamegpu::ModelDescription &model, const std::string &agent, const std::string &prefix,
+                 const std::string &state = "") {
   flamegpu::AgentVector pop(model.Agent(agent));
-  sim.getPopulationData(pop);
+  if (state.empty()) sim.getPopulationData(pop);
+  else sim.getPopulationData(pop, state);
   const flamegpu::AgentVector &cpop = pop;
   std::vector<Column> cols;
   for (const auto &v : cpop.getVariableMetaData()) {
@@ -122,7 +124,7 @@ void dump_agents(flamegpu::CUDASimulation &sim, flamegpu::ModelDescription &mode
     if (src && !c.data.empty()) std::memcpy(c.data.data(), src, c.data.size());
     cols.push_back(std::move(c));
   }
-  write_state(prefix + "." + agent + ".bin", cpop.size(), cols);
+  write_state(prefix + "." + agent + (state.empty() ? "" : "." + state) + ".bin", cpop.size(), cols);
 }
 
 // PBM + the bin-sorted message list of a spatial message, straight from the reference's device buffers
@@ -172,8 +174,10 @@ void dump_messages(flamegpu::CUDASimulation &sim, const std::string &message, in
 
 int main(int argc, const char **argv) {
   std::string model_name = "circles", params, in_path, out_prefix = "ref_out", dump_msg;
+  std::vector<std::string> pops;   // --pop agent:state:path (state may be empty = the agent's initial state), repeatable
+  std::vector<std::string> dumps;  // --dump agent:state, repeatable: <out>.<agent>.<state>.bin
   unsigned int steps = 1, warmup = 0;
-  bool quiet = false;
+  bool quiet = false, dump_steps = false;  // --dump-steps: <out>.s<k>.<agent>.bin after every step (teacher-forced parity)
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> std::string { return i + 1 < argc ? argv[++i] : ""; };
@@ -185,6 +189,9 @@ int main(int argc, const char **argv) {
     else if (a == "--warmup") warmup = static_cast<unsigned int>(std::strtoul(next().c_str(), nullptr, 10));
     else if (a == "--dump-messages") dump_msg = next();
     else if (a == "--quiet") quiet = true;
+    else if (a == "--dump-steps") dump_steps = true;
+    else if (a == "--pop") pops.push_back(next());
+    else if (a == "--dump") dumps.push_back(next());
   }
   try {
     flamegpu::io::Telemetry::disable();
@@ -198,6 +205,7 @@ int main(int argc, const char **argv) {
       p.radius = getf(kv, "radius", p.radius);
       p.repulse = getf(kv, "repulse", p.repulse);
       p.sort_period = getu(kv, "sort_period", p.sort_period);
+      p.validation = getu(kv, "validation", p.validation);
       fgb_examples::define_circles(model, p);
     } else if (model_name == "boids3d" || model_name == "boids2d") {
       fgb_examples::BoidsParams p;
@@ -224,6 +232,11 @@ int main(int argc, const char **argv) {
       p.radius = getf(kv, "radius", 1.f);
       p.sort_period = getu(kv, "sort_period", 1);
       p.bucket_upper = static_cast<int>(getu(kv, "bucket_upper", 12 + 512));
+      p.birth_optional = static_cast<int>(getu(kv, "birth_optional", 0));
+      p.birth_death = static_cast<int>(getu(kv, "birth_death", 0));
+      p.birth_condition = static_cast<int>(getu(kv, "birth_condition", 0));
+      p.birth_target = static_cast<int>(getu(kv, "birth_target", 0));
+      p.append_optional = static_cast<int>(getu(kv, "append_optional", 0));
       msg_dims = (p.which == fgb_examples::TM_COUNT2D || p.which == fgb_examples::TM_WRAP2D) ? 2 : 3;
       if (p.which >= fgb_examples::TM_BUCKET && p.which <= fgb_examples::TM_BUCKET_RANGE) msg_dims = 0;
       fgb_examples::define_test_model(model, p);
@@ -237,7 +250,23 @@ int main(int argc, const char **argv) {
     sim.SimulationConfig().telemetry = false;
     sim.applyConfig();
     uint32_t n = 0;
-    {
+    for (const std::string &spec : pops) {
+      const size_t c1 = spec.find(':'), c2 = spec.find(':', c1 + 1);
+      if (c1 == std::string::npos || c2 == std::string::npos) throw std::runtime_error("--pop expects agent:state:path");
+      const std::string an = spec.substr(0, c1), st = spec.substr(c1 + 1, c2 - c1 - 1), path = spec.substr(c2 + 1);
+      uint32_t m = 0;
+      std::vector<Column> cols = read_state(path, &m);
+      flamegpu::AgentVector pop(model.Agent(an), m);
+      for (const auto &c : cols) {
+        if (!c.name.empty() && c.name[0] == '_') continue;  // "_n": carries only the population size
+        void *dst = pop.data(c.name);
+        if (dst && !c.data.empty()) std::memcpy(dst, c.data.data(), c.data.size());
+      }
+      if (st.empty()) sim.setPopulationData(pop);
+      else sim.setPopulationData(pop, st);
+      n += m;
+    }
+    if (!in_path.empty()) {
       std::vector<Column> cols = read_state(in_path, &n);
       flamegpu::AgentVector pop(model.Agent(agent_name), n);
       for (const auto &c : cols) {
@@ -246,11 +275,20 @@ int main(int argc, const char **argv) {
       }
       sim.setPopulationData(pop);
     }
-    for (unsigned int i = 0; i < warmup + steps; ++i) sim.step();
+    for (unsigned int i = 0; i < warmup + steps; ++i) {
+      sim.step();
+      if (dump_steps) dump_agents(sim, model, agent_name, out_prefix + ".s" + std::to_string(i + 1));
+    }
     cudaDeviceSynchronize();
     const std::vector<double> t = sim.getElapsedTimeSteps();
-    dump_agents(sim, model, agent_name, out_prefix);
-    if (model_name == "test" && getu(kv, "which", 0) == fgb_examples::TM_BIRTH_OTHER_AGENT) dump_agents(sim, model, "agent2", out_prefix);
+    if (dumps.empty()) {
+      dump_agents(sim, model, agent_name, out_prefix);
+      if (model_name == "test" && getu(kv, "which", 0) == fgb_examples::TM_BIRTH_OTHER_AGENT) dump_agents(sim, model, "agent2", out_prefix);
+    }
+    for (const std::string &spec : dumps) {
+      const size_t c1 = spec.find(':');
+      dump_agents(sim, model, spec.substr(0, c1), out_prefix, c1 == std::string::npos ? "" : spec.substr(c1 + 1));
+    }
     if (!dump_msg.empty()) dump_messages(sim, dump_msg, msg_dims, out_prefix);
     // per-step seconds of the timed steps (after warm-up) as one JSON line
     std::printf("{\"impl\": \"flamegpu2-reference-cuda\", \"model\": \"%s\", \"n\": %u, \"steps\": %u, \"warmup\": %u, \"step_seconds\": [",

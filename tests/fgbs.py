@@ -46,10 +46,21 @@ def have_ref():
     return os.path.exists(REF_SIM) and os.access(REF_SIM, os.X_OK)
 
 
-def run_ref(model, params, in_state, out_prefix, steps=1, warmup=0, dump_messages=None, timeout=600):
-    """Runs the reference's CUDA build; returns the parsed JSON line it prints."""
-    cmd = [REF_SIM, "--model", model, "--params", ",".join(f"{k}={v}" for k, v in params.items()), "--in", in_state, "--out",
+def run_ref(model, params, in_state, out_prefix, steps=1, warmup=0, dump_messages=None, timeout=600, pops=None, dumps=None,
+            dump_steps=False):
+    """Runs the reference's CUDA build; returns the parsed JSON line it prints.
+    in_state: state file of the model's main agent (or None); pops: [(agent, state, path)] further populations;
+    dumps: [(agent, state)] -> <out_prefix>.<agent>.<state>.bin; dump_steps: <out_prefix>.s<k>.<agent>.bin after each step."""
+    cmd = [REF_SIM, "--model", model, "--params", ",".join(f"{k}={v}" for k, v in params.items()), "--out",
            out_prefix, "--steps", str(steps), "--warmup", str(warmup), "--quiet"]
+    if in_state:
+        cmd += ["--in", in_state]
+    for a, st, path in pops or []:
+        cmd += ["--pop", f"{a}:{st}:{path}"]
+    for a, st in dumps or []:
+        cmd += ["--dump", f"{a}:{st}" if st else a]
+    if dump_steps:
+        cmd += ["--dump-steps"]
     if dump_messages:
         cmd += ["--dump-messages", dump_messages]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
