@@ -13,6 +13,7 @@
 #include "fgb_radix.cuh"
 #include "fgb_reduce.cuh"
 #include "fgb_scan.cuh"
+#include "fgb_slab.cuh"
 
 using namespace fgb;
 
@@ -117,16 +118,16 @@ int scatter_from_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, 
   k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
   if (!stable) {
     if (vec) {
-      k_bin_scatter_direct<true, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state);
+      k_bin_scatter_direct<false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state, sp->d_ctrl);
       k_bin_scatter_staged<true, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
     } else {
-      k_bin_scatter_direct<false, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state);
+      k_bin_scatter_direct<false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state, sp->d_ctrl);
       k_bin_scatter_staged<false, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
     }
     ctx->launches += 3;
     return launch_ok();
   }
-  k_bin_scatter_direct<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm, sp->d_state, sp->n_state);
+  k_bin_scatter_direct<true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm, sp->d_state, sp->n_state, sp->d_ctrl);
   k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm);
   ctx->launches += 3;
   r = stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars, st);
@@ -196,7 +197,7 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   VarTable none{};
   none.n = 0;
   k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-  k_bin_scatter_direct<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm, sp->d_state, sp->n_state);
+  k_bin_scatter_direct<true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm, sp->d_state, sp->n_state, sp->d_ctrl);
   k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm);
   ctx->launches += 3;
   if (stable) return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
@@ -489,6 +490,57 @@ fgb_status fgb_plane_flags(fgb_ctx *ctx, const float *pos, unsigned int n, const
   if (n == 0) return FGB_OK;
   k_plane_flags<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(pos, n, d_n, env_min, radius, grid_dim, lo, hi,
                                                                               flag_lo, flag_mid, flag_hi);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_signal(fgb_ctx *ctx, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, const unsigned int *d_epoch,
+                           void *stream) {
+  if (!ctx || !d_epoch) return FGB_ERR_INVALID_ARG;
+  if (!peer_flag_lo && !peer_flag_hi) return FGB_OK;
+  k_slab_signal<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(peer_flag_lo, peer_flag_hi, d_epoch);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const unsigned long long *flag_hi, const unsigned int *count_lo,
+                         const unsigned int *count_hi, unsigned int capacity, const unsigned int *d_epoch, unsigned int *d_err,
+                         unsigned int timeout_ms, void *stream) {
+  if (!ctx || !d_epoch || !d_err || (flag_lo && !count_lo) || (flag_hi && !count_hi)) return FGB_ERR_INVALID_ARG;
+  if (!flag_lo && !flag_hi) return FGB_OK;
+  k_slab_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flag_lo, flag_hi, count_lo, count_hi, capacity, d_epoch, d_err,
+                                                              static_cast<unsigned long long>(timeout_ms) * 1000000ull);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_check_bound(fgb_ctx *ctx, const unsigned int *d_count, unsigned int bound, unsigned int *d_err, void *stream) {
+  if (!ctx || !d_count || !d_err) return FGB_ERR_INVALID_ARG;
+  k_slab_check_bound<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_count, bound, d_err);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_allreduce(fgb_ctx *ctx, int op, int dtype, void *d_value_inout, void *const *mailboxes, int rank, int world,
+                              unsigned long long epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream) {
+  if (!ctx || !d_value_inout || !mailboxes || !d_err || world < 1 || world > kSlabMaxWorld || rank < 0 || rank >= world ||
+      op < FGB_REDUCE_SUM || op > FGB_REDUCE_MAX || dtype < FGB_F32 || dtype > FGB_U64)
+    return FGB_ERR_INVALID_ARG;
+  SlabMailboxes mb{};
+  for (int r = 0; r < world; ++r) {
+    if (!mailboxes[r]) return FGB_ERR_INVALID_ARG;
+    mb.box[r] = static_cast<SlabMailSlot *>(mailboxes[r]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned long long to = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
+  switch (dtype) {
+    case FGB_F32: k_slab_allreduce<float><<<1, 32, 0, st>>>(static_cast<float *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    case FGB_F64: k_slab_allreduce<double><<<1, 32, 0, st>>>(static_cast<double *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    case FGB_I32: k_slab_allreduce<int><<<1, 32, 0, st>>>(static_cast<int *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    case FGB_U32: k_slab_allreduce<unsigned int><<<1, 32, 0, st>>>(static_cast<unsigned int *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    case FGB_I64: k_slab_allreduce<long long><<<1, 32, 0, st>>>(static_cast<long long *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    default: k_slab_allreduce<unsigned long long><<<1, 32, 0, st>>>(static_cast<unsigned long long *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+  }
   ctx->launches += 1;
   return launch_ok();
 }

@@ -206,84 +206,119 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_keys(KeySrc<DIMS> src, uint
 // shared memory (the table is indexed by the low key bits, so x-adjacent bins -- adjacent in the
 // output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
 // items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
-// Grouped tiles.  Reads the stored keys (8 per thread, one 256-bit load), classifies its 2048-item tile by the number
-// of runs of equal keys -- a tile of a bin-ordered list has few, any other order one per item -- and records the
-// choice for k_bin_scatter_staged, which runs next and takes the ungrouped tiles.  No shared-memory table: one
-// global atomic per run claims its output range, the items of a run land on consecutive addresses.
+// Grouped tiles.  A warp owns 256 consecutive items of its block's 2048-item tile and walks them in 8 rounds of 32:
+// lane l of round r holds item w0 + 32 r + l, so consecutive lanes hold consecutive items -- in a bin-ordered list
+// mostly the same bin.  Runs of equal keys inside a round are found with one shuffle and one ballot; the first lane
+// of a run claims the run's output range with ONE global atomic and the lanes of the run store to consecutive
+// addresses: every load is a coalesced 128-byte warp access and every store instruction writes whole runs (with one
+// item per thread-owned 8-item strip instead, each store instruction touched 32 different sectors, 4 bytes each).
+// The block first classifies its tile by the number of runs -- a bin-ordered tile has few, any other order one per
+// item -- and records the choice for k_bin_scatter_staged, which runs next and takes the ungrouped tiles.
 // Also re-zeroes the scan's look-back words (the scan is complete by now) for the next build.
-template <bool VEC, bool IDX_ONLY>
+template <bool IDX_ONLY>
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter_direct(const uint32_t *__restrict__ keys, uint32_t n_max,
                                                                     const unsigned int *d_n, uint32_t *cursor,
                                                                     const __grid_constant__ VarTable vt, uint32_t *perm,
                                                                     uint32_t *tile_mode, unsigned long long *state,
-                                                                    uint32_t n_state) {
+                                                                    uint32_t n_state, uint32_t *ctrl) {
   __shared__ uint32_t s_runs;
   for (uint32_t s = blockIdx.x * kBinThreads + threadIdx.x; s < n_state; s += gridDim.x * kBinThreads) state[s] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ctrl) ctrl[0] = 0u;  // big-bin counter of the stable fix-up that may follow
   const uint32_t n = load_count(d_n, n_max);
   const uint32_t tile0 = blockIdx.x * kTile;
   if (tile0 >= n) return;
-  const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
-  const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
+  if (threadIdx.x == 0) s_runs = 0u;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t w0 = tile0 + warp * (32u * kTileItems);
   const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
-  uint32_t k[kTileItems];
-  if (cnt == kTileItems && VEC) {
-    ld_nc_u8(keys + i0, k);
-  } else {
+  uint32_t k[kTileItems], head[kTileItems];  // head: ballot of the lanes that start a run (bit 0 always set)
+  uint32_t runs = 0;
 #pragma unroll
-    for (int t = 0; t < kTileItems; ++t) k[t] = t < cnt ? __ldg(keys + i0 + t) : 0xFFFFFFFFu;
+  for (int r = 0; r < kTileItems; ++r) {
+    const uint32_t i = w0 + r * 32u + lane;
+    k[r] = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k[r], 1);
+    head[r] = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev != k[r]);
+    runs += __popc(head[r] & __ballot_sync(0xFFFFFFFFu, i < n));
   }
-  const bool grouped = block_run_count(k, cnt, &s_runs) * 2u <= tile_n;
+  if (lane == 0) atomicAdd(&s_runs, runs);
+  __syncthreads();
+  const bool grouped = s_runs * 2u <= tile_n;
   if (threadIdx.x == 0) tile_mode[blockIdx.x] = grouped ? 1u : 0u;
-  if (!grouped || cnt == 0) return;
-  // one atomic per run (all of a thread's atomics are in flight together)
+  if (!grouped) return;
+  // claim: the first lane of every run adds the run's length to the bin's cursor (all atomics of a warp in flight)
   uint32_t dst[kTileItems];
-  {
-    int j = 0;
 #pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
-      if (r == j && j < cnt) {
-        int e = j + 1;
-#pragma unroll
-        for (int t = 1; t < kTileItems; ++t)
-          if (t < kTileItems - r && r + t < cnt && e == r + t && k[(r + t) & (kTileItems - 1)] == k[r]) e = r + t + 1;
-        const uint32_t b = atomicAdd(cursor + k[r] + 1, static_cast<uint32_t>(e - j));
-#pragma unroll
-        for (int t = 0; t < kTileItems; ++t)
-          if (r + t < e && t < kTileItems - r) dst[r + t] = b + t;
-        j = e;
-      }
+  for (int r = 0; r < kTileItems; ++r) {
+    const uint32_t i = w0 + r * 32u + lane;
+    const uint32_t below = head[r] & ((2u << lane) - 1u);            // run heads at or below this lane
+    const int first = 31 - __clz(static_cast<int>(below));           // lane that starts this lane's run
+    const uint32_t above = head[r] & ~((2u << lane) - 1u);           // run heads above this lane
+    const int next = above ? __ffs(static_cast<int>(above)) - 1 : 32;  // first lane of the next run
+    uint32_t base = 0;
+    if (static_cast<int>(lane) == first && i < n) {
+      // the run ends at the next head or at the end of the list
+      const uint32_t last_valid = (n - (w0 + r * 32u)) < 32u ? n - (w0 + r * 32u) : 32u;
+      const uint32_t len = (static_cast<uint32_t>(next) < last_valid ? static_cast<uint32_t>(next) : last_valid) - lane;
+      base = atomicAdd(cursor + k[r] + 1, len);
     }
+    base = __shfl_sync(0xFFFFFFFFu, base, first);
+    dst[r] = base + (lane - static_cast<uint32_t>(first));
   }
   if constexpr (IDX_ONLY) {
 #pragma unroll
-    for (int t = 0; t < kTileItems; ++t)
-      if (t < cnt) perm[dst[t]] = i0 + t;
+    for (int r = 0; r < kTileItems; ++r) {
+      const uint32_t i = w0 + r * 32u + lane;
+      if (i < n) perm[dst[r]] = i;
+    }
   } else {
-    for (uint32_t v = 0; v < vt.n; ++v) {
-      if (vt.len[v] == 4) {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v]);
-        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
-        uint32_t w[kTileItems];
-        if (VEC && cnt == kTileItems && (reinterpret_cast<uintptr_t>(in + i0) & 31u) == 0) {
-          ld_nc_u8(in + i0, w);
-        } else {
+    // software pipeline over the variables: the loads of variable v+1 are in flight while v is stored
+    uint32_t cur[kTileItems];
+    bool cur4 = vt.n > 0 && vt.len[0] == 4;
+    if (cur4) {
+      const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[0]);
 #pragma unroll
-          for (int t = 0; t < kTileItems; ++t)
-            if (t < cnt) w[t] = __ldg(in + i0 + t);
-        }
-#pragma unroll
-        for (int t = 0; t < kTileItems; ++t)
-          if (t < cnt) o[dst[t]] = w[t];
-      } else {
-#pragma unroll
-        for (int t = 0; t < kTileItems; ++t)
-          if (t < cnt) copy_item(vt, v, i0 + t, dst[t]);
+      for (int r = 0; r < kTileItems; ++r) {
+        const uint32_t i = w0 + r * 32u + lane;
+        if (i < n) cur[r] = ld_stream_u32(in + i);
       }
     }
-    if (perm) {  // source slot of every sorted item (the scheduler derives the readers' bin-ordered execution from it)
+    for (uint32_t v = 0; v < vt.n; ++v) {
+      const bool next4 = v + 1 < vt.n && vt.len[v + 1] == 4;
+      uint32_t nxt[kTileItems];
+      if (next4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 1]);
 #pragma unroll
-      for (int t = 0; t < kTileItems; ++t)
-        if (t < cnt) perm[dst[t]] = i0 + t;
+        for (int r = 0; r < kTileItems; ++r) {
+          const uint32_t i = w0 + r * 32u + lane;
+          if (i < n) nxt[r] = ld_stream_u32(in + i);
+        }
+      }
+      if (cur4) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+          const uint32_t i = w0 + r * 32u + lane;
+          if (i < n) o[dst[r]] = cur[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+          const uint32_t i = w0 + r * 32u + lane;
+          if (i < n) copy_item(vt, v, i, dst[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kTileItems; ++r) cur[r] = nxt[r];
+      cur4 = next4;
+    }
+    if (perm) {  // source slot of every sorted item
+#pragma unroll
+      for (int r = 0; r < kTileItems; ++r) {
+        const uint32_t i = w0 + r * 32u + lane;
+        if (i < n) perm[dst[r]] = i;
+      }
     }
   }
 }

@@ -117,6 +117,13 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
     s->sim = std::make_unique<flamegpu::CUDASimulation>(*s->model);
     s->sim->CUDAConfig().device_id = device;
     s->sim->CUDAConfig().inLayerConcurrency = getu(kv, "concurrency", 1) != 0;
+    if (getu(kv, "slab_world", 1) > 1)
+      s->sim->configureSlabs(static_cast<int>(getu(kv, "slab_rank", 0)), static_cast<int>(getu(kv, "slab_world", 1)),
+                             kv.count("slab_message") ? kv.at("slab_message") : std::string("location"), getu(kv, "halo_cap", 65536),
+                             getu(kv, "mig_cap", 16384));
+    s->sim->CUDAConfig().slabRefreshPeriod = getu(kv, "slab_refresh", 16);
+    s->sim->CUDAConfig().fusedIndexBuild = getu(kv, "fused_index", 1) != 0;
+    s->sim->CUDAConfig().binOrderedOutput = getu(kv, "ordered_output", 1) != 0;
     if (kv.count("win_count")) s->sim->setMessageWindow("location", static_cast<int>(getu(kv, "win_begin", 0)), static_cast<int>(getu(kv, "win_count", 0)));
     s->sim->CUDAConfig().useCUDAGraphs = getu(kv, "graphs", 1) != 0;
     s->sim->CUDAConfig().stableMessageOrder = getu(kv, "stable", 0) != 0;
@@ -282,7 +289,23 @@ int fgbm_step_times(void *h, double *out, unsigned int cap, unsigned int *n) {
   });
 }
 
-// ---- multi-GPU slab driver hooks (flamegpu2_b200/slab.py) ------------------------------------------
+// ---- multi-GPU slab decomposition behind step() (CUDASimulation::configureSlabs) -----------------------
+// The harness (flamegpu2_b200/slab.py) only moves the 64-byte staging handles between the ranks.
+unsigned int fgbm_slab_handle_bytes(void *h) { return static_cast<unsigned int>(static_cast<Sim *>(h)->sim->slabHandleBytes()); }
+int fgbm_slab_export(void *h, void *out) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->slabExportHandle(out); });
+}
+int fgbm_slab_connect(void *h, const void *all_handles) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->slabConnect(all_handles); });
+}
+int fgbm_slab_planes(void *h, int *z0, int *z1) {
+  return guarded([&] { static_cast<Sim *>(h)->sim->slabPlanes(z0, z1); });
+}
+int fgbm_slab_error(void *h, unsigned int *bits) {
+  return guarded([&] { *bits = static_cast<Sim *>(h)->sim->slabError(); });
+}
+
+// ---- phase-wise multi-GPU driver hooks (round-1 path, kept for A/B) ------------------------------------
 int fgbm_run_layers(void *h, unsigned int first, unsigned int last) {
   return guarded([&] { static_cast<Sim *>(h)->sim->runLayers(first, last); });
 }
@@ -380,10 +403,17 @@ int fgbm_circles_step_host(void *h, unsigned int n, const float *x, const float 
     const char *names[4] = {"x", "y", "z", "drift"};
     const void *ptrs[4] = {x, y, z, drift};
     s->sim->setPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, n, 4, names, ptrs);
-    for (unsigned int i = 0; i < steps; ++i) s->sim->step();
     const char *onames[5] = {"x", "y", "z", "drift", "_id"};
     void *optrs[5] = {x_out, y_out, z_out, drift_out, id_out};
-    s->sim->getPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, id_out ? 5 : 4, onames, optrs, n);
+    for (unsigned int i = 0; i + 1 < steps; ++i) s->sim->step();
+    // the download rides on the last step: finished chunks of `move` are copied while the rest still computes
+    if (steps > 0) s->sim->streamPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, id_out ? 5 : 4, onames, optrs, 8);
+    if (steps > 0) {
+      s->sim->step();
+      if (s->sim->finishStreamedPopulation() > n) throw std::runtime_error("population grew beyond the caller's buffers");
+    } else {
+      s->sim->getPopulationDataSoA("Circle", flamegpu::DEFAULT_STATE, id_out ? 5 : 4, onames, optrs, n);
+    }
   });
 }
 

@@ -26,7 +26,8 @@ typedef void(AgentFunctionConditionWrapper)(const detail::FunctionArgs);
 // lock-step walk); it reaches the iterator as a constant, so each instance contains one variant only
 template <typename AgentFunction, typename MessageIn, typename MessageOut, int ITER_MODE = 0>
 __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionArgs args) {
-  const unsigned int index = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int index = args.first_thread + blockIdx.x * blockDim.x + threadIdx.x;
+  if (args.last_thread && index >= args.last_thread) return;
   unsigned int n = args.bound;
   if (args.d_count) {
     const unsigned int c = __ldg(args.d_count);

@@ -63,6 +63,8 @@ struct FunctionArgs {
   const unsigned int *exec_perm; // thread t runs agent exec_perm[t] (bin order); NULL: agent t
   const unsigned int *d_agent_offset;  // function condition: agents [0, *d_agent_offset) are disabled (NULL: 0)
   unsigned int bound;           // launch bound
+  unsigned int first_thread;    // this launch covers threads [first_thread, last_thread) of the function (a function may be
+  unsigned int last_thread;     // launched in several thread-range chunks, CUDASimulation::streamPopulationDataSoA); 0,0 = all
   DevVars agent;                // variables of the executing agent's state list
   DevVars msg_in;               // input message list (bin-sorted for spatial messages)
   DevVars msg_out;              // output message list

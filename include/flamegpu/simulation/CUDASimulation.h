@@ -58,8 +58,10 @@ namespace detail {
 #if defined(__CUDACC__)
 // end-of-step bookkeeping on the device: ++step, reset the counts of non-persistent message lists
 // (reference CUDASimulation.cu:619-625 does this on the host)
-__global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const unsigned int *zero_slots, unsigned int n_zero) {
+__global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const unsigned int *zero_slots, unsigned int n_zero,
+                              unsigned int epoch_slot) {
   if (threadIdx.x == 0) ctrl[step_slot] += 1u;
+  if (threadIdx.x == 1 && epoch_slot) ctrl[epoch_slot] += 1u;  // slab exchange epoch (one halo + one migration per step)
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
@@ -324,6 +326,8 @@ class CUDASimulation {
     bool tileLocalExecOrder = true;   // b200: bin-order execution groups inside 2048-agent tiles when the list was just sorted
     bool overlapIndexBuild = true;    // b200: build the input list's PBM on a second stream while the agents are sorted
     bool profile = false;             // b200: eager execution with CUDA events around every phase (getProfile())
+    unsigned int slabRefreshPeriod = 16;  // b200 slabs: steps between host re-reads of the list counts (launch bounds)
+    unsigned int slabTimeoutMs = 20000;   // b200 slabs: a wait for a neighbour gives up (error word) after this long
     bool fusedIndexBuild = true;      // b200: mandatory spatial output publishes bin keys + histogram (buildIndex starts at the scan)
     bool binOrderedOutput = true;     // b200: mandatory spatial output writes its messages in the bin order of the last reader
     bool trueSpatialSortKey = false;  // b200: sort 3D agents by the intended x,y,z key (the reference's
@@ -371,6 +375,26 @@ class CUDASimulation {
     if (initialised) throw exception::InvalidArgument("setMessageWindow must be called before the simulation is initialised");
     windows[message_name] = std::make_pair(plane_begin, plane_count);
   }
+  // Slab decomposition BEHIND step(): this process is rank `rank` of `world` (one process per GPU) and owns a contiguous
+  // range of bin planes of `message`'s slowest grid axis.  Call before the first step / setPopulationData, upload only
+  // the agents whose position lies in slabPlanes(), exchange the staging handles (slabExportHandle on every rank, an
+  // all-gather by the caller -- torch.distributed / MPI: plumbing -- then slabConnect) and call step() as usual:
+  //   * before `message` is indexed for its first reader, the messages of the two boundary planes are packed straight
+  //     into the neighbours' staging buffers (peer memory over NVLink), the neighbours' halos are appended;
+  //   * at the end of the step agents whose position left the slab are packed to the neighbour the same way, removed
+  //     here and the arriving ones appended;
+  //   * HostAgentAPI reductions (step functions) are all-reduced over per-rank mailboxes.
+  // Everything is kernel launches on the step's streams: the slab step is captured in the same CUDA graphs, nothing
+  // returns to the host (list bounds are re-read every CUDAConfig().slabRefreshPeriod steps).
+  void configureSlabs(int rank, int world, const std::string &message, unsigned int halo_capacity, unsigned int migrate_capacity);
+  size_t slabHandleBytes() const { return sizeof(cudaIpcMemHandle_t); }
+  void slabExportHandle(void *out);
+  void slabConnect(const void *all_handles);
+  void slabPlanes(int *z0, int *z1) const {
+    if (z0) *z0 = slab.z0;
+    if (z1) *z1 = slab.z1;
+  }
+  unsigned int slabError();  // FGB_SLAB_ERR_* bits raised on the device so far (synchronises)
   // run layers [first, last) of the model eagerly (no end-of-step bookkeeping); endStep() finishes the step
   void runLayers(unsigned int first, unsigned int last);
   void endStep();
@@ -405,6 +429,15 @@ class CUDASimulation {
   // through pageable host vectors.  Variables not listed are reset to their defaults; ids restart at 1.
   void setPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int n, unsigned int nvars,
                             const char *const *names, const void *const *host_ptrs);
+  // Streamed download: arms the NEXT step() to copy the listed variables of a state list into the caller's (pinned) host
+  // buffers WHILE the step's last function on that list is still running -- the function is launched in `chunks`
+  // thread-range chunks and every finished chunk is copied on a second stream, so only the last chunk's copy is exposed
+  // (the reference's getPopulationData copies after the step, CUDASimulation.cu:1417-1440).  Falls back to one copy at
+  // the end of the step when the list's last function can die / birth / change state, has a condition, or runs in a
+  // global (not tile-local) bin order.  finishStreamedPopulation() waits for the copies and returns the agent count.
+  void streamPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars, const char *const *names,
+                               void *const *host_ptrs, unsigned int chunks = 8);
+  unsigned int finishStreamedPopulation();
   // Returns the agent count; copies the listed variables (device order) into the caller's buffers.
   unsigned int getPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars,
                                     const char *const *names, void *const *host_ptrs, unsigned int capacity);
@@ -462,6 +495,51 @@ class CUDASimulation {
   }
   void write_slot(unsigned int s, unsigned int v) { FGB_CUDA_THROW(cudaMemcpy(d_ctrl + s, &v, 4, cudaMemcpyHostToDevice)); }
 
+  // ---- slab decomposition state --------------------------------------------------------------------------------
+  struct SlabStaging {  // receive buffer for one (list, side) inside the arena: variables back to back, count, flag
+    std::vector<size_t> var_off;
+    size_t count_off = 0, flag_off = 0;
+  };
+  struct SlabList {
+    bool is_message = false;
+    detail::DevList *list = nullptr;
+    detail::CUDAAgent *agent = nullptr;
+    int pos_var = -1;           // index of the position variable along the decomposed axis
+    unsigned int capacity = 0;  // items per staging buffer
+    SlabStaging st[2];          // [0]: data arriving from rank-1, [1]: from rank+1
+  };
+  struct Slab {
+    bool enabled = false, connected = false;
+    int rank = 0, world = 1;
+    std::string message;
+    int planes = 0, z0 = 0, z1 = 0;
+    unsigned int halo_cap = 0, mig_cap = 0;
+    char *arena = nullptr;  // every staging buffer + the reduction mailboxes of THIS rank, one IPC-exported allocation
+    size_t arena_bytes = 0, mail_off = 0;
+    std::vector<char *> peer;  // arena of every rank as mapped here (peer[rank] == arena)
+    std::vector<SlabList> lists;  // [0] = the halo message list, then every agent state list that carries the position
+    unsigned int epoch_slot = 0, err_slot = 0;
+    unsigned long long reduce_epoch = 0;
+  } slab;
+  struct Streamed {
+    bool armed = false, chunked = false;
+    detail::DevList *list = nullptr;
+    const detail::FunctionRT *function = nullptr;  // the step's last function on the list (chunked launch), or NULL
+    std::vector<int> vars;
+    std::vector<void *> host;
+    unsigned int chunks = 8, n = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t chunk_done = nullptr;
+  } streamed;
+  unsigned int *h_words = nullptr;  // pinned staging for small host -> device control words
+  unsigned int soa_uploads = 0;
+  cudaStream_t stream_copy = nullptr;        // streamed downloads
+  cudaEvent_t stream_chunk_done = nullptr;
+  static constexpr unsigned int kSlabScratchSlot = 127;  // fgb_ctx scratch slot of the exchange (FGB_MAX_STREAMS - 1)
+  void slab_setup();  // arena layout + allocation (initialise)
+  void slab_exchange(SlabList &S, int lo_plane, int hi_plane, bool remove, cudaStream_t st);
+  void slab_refresh_bounds();
+  void slab_allreduce(void *d_value, int dtype, int op);
   void upload_environment();
   void plan_step();                         // reserve capacities for the coming step (may allocate)
   void record_step(cudaStream_t main);      // enqueue one whole step

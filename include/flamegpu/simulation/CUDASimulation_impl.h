@@ -193,6 +193,8 @@ inline void CUDASimulation::initialise() {
   FGB_CUDA_THROW(cudaMalloc(&d_env, env_host.size()));
   env_table.buffer = d_env;
   env_dirty = true;
+  for (auto &f : slab_flags) f.gen = &alloc_gen;
+  if (slab.enabled) slab_setup();
   initialised = true;
 }
 
@@ -225,10 +227,23 @@ inline void CUDASimulation::destroy() {
     if (m.second.spatial) fgb_spatial_destroy(m.second.spatial);
   }
   for (auto &f : slab_flags) f.release();
+  if (slab.enabled) {
+    for (int r = 0; r < static_cast<int>(slab.peer.size()); ++r)
+      if (r != slab.rank && slab.peer[r]) cudaIpcCloseMemHandle(slab.peer[r]);
+    slab.peer.clear();
+    if (slab.arena) cudaFree(slab.arena);
+    slab.arena = nullptr;
+  }
   for (int i = 0; i < 2; ++i) {
     if (h_ctrl_pinned[i]) cudaFreeHost(h_ctrl_pinned[i]);
     if (ctrl_events[i]) cudaEventDestroy(ctrl_events[i]);
   }
+  if (stream_copy) cudaStreamDestroy(stream_copy);
+  if (stream_chunk_done) cudaEventDestroy(stream_chunk_done);
+  stream_copy = nullptr;
+  stream_chunk_done = nullptr;
+  if (h_words) cudaFreeHost(h_words);
+  h_words = nullptr;
   if (d_env) cudaFree(d_env);
   if (d_zero_slots) cudaFree(d_zero_slots);
   if (d_ctrl) cudaFree(d_ctrl);
@@ -362,10 +377,66 @@ inline void CUDASimulation::setPopulationDataSoA(const std::string &agent_name, 
     }
   }
   a.host_next_id = n + 1;
-  const unsigned int words[2] = {n, n + 1};
-  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + l.count_slot, &words[0], 4, cudaMemcpyHostToDevice, main_stream));
-  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + a.next_id_slot, &words[1], 4, cudaMemcpyHostToDevice, main_stream));
-  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));  // `words` lives on this stack frame
+  // control words travel through pinned staging (two slots per call parity), so the call returns without draining the stream
+  if (!h_words) FGB_CUDA_THROW(cudaMallocHost(&h_words, 16 * sizeof(unsigned int)));
+  static_assert(sizeof(unsigned int) == 4, "");
+  unsigned int *w = h_words + 2 * (soa_uploads++ & 7u);
+  w[0] = n;
+  w[1] = n + 1;
+  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + l.count_slot, &w[0], 4, cudaMemcpyHostToDevice, main_stream));
+  FGB_CUDA_THROW(cudaMemcpyAsync(d_ctrl + a.next_id_slot, &w[1], 4, cudaMemcpyHostToDevice, main_stream));
+}
+
+inline void CUDASimulation::streamPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars,
+                                                    const char *const *names, void *const *host_ptrs, unsigned int chunks) {
+  initialise();
+  detail::DevList &l = state_list(agent_name, state);
+  streamed = Streamed{};
+  streamed.list = &l;
+  for (unsigned int k = 0; k < nvars; ++k) {
+    const int v = l.index_of(names[k]);
+    if (v < 0) throw exception::InvalidAgentVar(std::string("agent has no variable '") + names[k] + "'");
+    streamed.vars.push_back(v);
+    streamed.host.push_back(host_ptrs[k]);
+  }
+  streamed.chunks = std::max(1u, chunks);
+  if (!stream_copy) {
+    FGB_CUDA_THROW(cudaStreamCreateWithFlags(&stream_copy, cudaStreamNonBlocking));
+    FGB_CUDA_THROW(cudaEventCreateWithFlags(&stream_chunk_done, cudaEventDisableTiming));
+  }
+  streamed.stream = stream_copy;
+  streamed.chunk_done = stream_chunk_done;
+  // the step's last function that executes on the list; chunkable only if the list's membership and order are final once it ran
+  for (auto &layer : layers)
+    for (auto &f : layer) {
+      const AgentFunctionData &fn = *f.fn;
+      const bool touches = &f.agent->states.at(fn.initial_state) == &l || &f.agent->states.at(fn.end_state) == &l ||
+                           (f.out_agent && &f.out_agent->states.at(fn.agent_output_state) == &l);
+      if (!touches) continue;
+      const bool simple = &f.agent->states.at(fn.initial_state) == &l && fn.initial_state == fn.end_state && !fn.has_agent_death &&
+                          !fn.condition && !f.out_agent;
+      streamed.function = simple ? &f : nullptr;
+    }
+  streamed.armed = true;
+}
+
+inline unsigned int CUDASimulation::finishStreamedPopulation() {
+  if (!streamed.list) throw exception::InvalidArgument("finishStreamedPopulation without streamPopulationDataSoA");
+  detail::DevList &l = *streamed.list;
+  if (!streamed.chunked) {  // fallback: the copies could not ride on a chunked launch
+    const unsigned int n = read_slot(l.count_slot);
+    for (size_t k = 0; k < streamed.vars.size(); ++k)
+      if (n) FGB_CUDA_THROW(cudaMemcpyAsync(streamed.host[k], l.data[streamed.vars[k]], static_cast<size_t>(n) * l.meta[streamed.vars[k]].bytes(),
+                                            cudaMemcpyDeviceToHost, main_stream));
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    streamed = Streamed{};
+    return n;
+  }
+  FGB_CUDA_THROW(cudaStreamSynchronize(streamed.stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  const unsigned int n = streamed.n;
+  streamed = Streamed{};
+  return n;
 }
 
 inline unsigned int CUDASimulation::getPopulationDataSoA(const std::string &agent_name, const std::string &state, unsigned int nvars,
@@ -560,6 +631,21 @@ inline void CUDASimulation::plan_step() {
       }
       for (unsigned int sid = 0; sid < std::max<size_t>(1, side_streams.size()); ++sid) FGB_ABI_THROW(fgb_ctx_reserve(ctx, sid, std::max(n, 1u), 0));
     }
+  if (slab.enabled) {
+    unsigned int most = 1;
+    for (SlabList &S : slab.lists) {
+      // room for what the neighbours may append (halo ghosts / arriving agents)
+      const unsigned int b = S.is_message ? bound_of(*S.list) : S.list->bound;
+      S.list->reserve(b + 2u * S.capacity, S.list->capacity);
+      most = std::max(most, b + 2u * S.capacity);
+      if (S.is_message) {
+        for (auto &m : messages)
+          if (&m.second.list == S.list && m.second.spatial) FGB_ABI_THROW(fgb_spatial_reserve(m.second.spatial, b + 2u * S.capacity));
+      }
+    }
+    for (auto &f : slab_flags) f.reserve(most);
+    FGB_ABI_THROW(fgb_ctx_reserve(ctx, kSlabScratchSlot, most, 0));
+  }
   // reserving may have raised list bounds' capacity only; bounds themselves are untouched
 }
 
@@ -691,7 +777,9 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     if (plain && MO.spatial && !MO.bucket) {
       // bin-ordered output: thread t writes slot t for agent perm[t], perm = bin order of the list's last spatial reader.
       // Positions have moved a little since, so the list arrives NEARLY bin-grouped: every tile takes the direct scatter.
-      if (cuda_config.binOrderedOutput && !bin_order && !conditional && !f.out_agent && L.perm_valid()) {
+      // (Not with stableMessageOrder: the permutation's order inside a bin is atomic-arrival order, and the stable
+      // build orders a bin by message slot.)
+      if (cuda_config.binOrderedOutput && !cuda_config.stableMessageOrder && !bin_order && !conditional && !f.out_agent && L.perm_valid()) {
         a.exec_perm = L.cached_perm;
         a.slot_by_thread = 1u;
       }
@@ -742,9 +830,34 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     // radius-filtered iterator: kFilterQueueWords words of chunk queue per thread (FunctionArgs.h)
     const bool filtered = filtered_iteration(f);
     const size_t smem = filtered ? sizeof(uint32_t) * detail::kFilterQueueWords * bs : 0;
-    FGB_CUDA_THROW(cudaLaunchKernel(reinterpret_cast<const void *>(filtered ? fn.func_filtered : fn.func), dim3((n + bs - 1) / bs), dim3(bs), kargs, smem, st));
+    const void *kernel = reinterpret_cast<const void *>(filtered ? fn.func_filtered : fn.func);
+    // thread range == agent range only without a permutation or with the tile-local one (groups stay inside 2048-agent tiles)
+    const bool chunkable = streamed.armed && streamed.function == &f && n > 0 && (!a.exec_perm || (bin_order && sorted_now));
+    if (chunkable) {
+      // streamed download: the function runs in thread-range chunks, every finished chunk of the requested variables is
+      // copied to the host on the copy stream while the next chunk computes
+      const unsigned int per = ((n + streamed.chunks - 1) / streamed.chunks + 2047u) & ~2047u;
+      for (unsigned int c0 = 0; c0 < n; c0 += per) {
+        const unsigned int c1 = std::min(n, c0 + per);
+        a.first_thread = c0;
+        a.last_thread = c1;
+        FGB_CUDA_THROW(cudaLaunchKernel(kernel, dim3((c1 - c0 + bs - 1) / bs), dim3(bs), kargs, smem, st));
+        ++own_launches;
+        FGB_CUDA_THROW(cudaEventRecord(streamed.chunk_done, st));
+        FGB_CUDA_THROW(cudaStreamWaitEvent(streamed.stream, streamed.chunk_done, 0));
+        for (size_t k = 0; k < streamed.vars.size(); ++k) {
+          const size_t b = L.meta[streamed.vars[k]].bytes();
+          FGB_CUDA_THROW(cudaMemcpyAsync(static_cast<char *>(streamed.host[k]) + static_cast<size_t>(c0) * b, L.data[streamed.vars[k]] + static_cast<size_t>(c0) * b,
+                                         static_cast<size_t>(c1 - c0) * b, cudaMemcpyDeviceToHost, streamed.stream));
+        }
+      }
+      streamed.chunked = true;
+      streamed.n = n;
+    } else {
+      FGB_CUDA_THROW(cudaLaunchKernel(kernel, dim3((n + bs - 1) / bs), dim3(bs), kargs, smem, st));
+      ++own_launches;
+    }
     prof_end(st);
-    ++own_launches;
   }
 
   // 5. output message list (reference CUDAMessage::swap, CUDAMessage.cu:171-208)
@@ -885,6 +998,13 @@ inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream
     M.pbm_dirty = false;
     return;
   }
+  if (slab.enabled && slab.connected && !slab.lists.empty() && slab.lists[0].list == &M.list) {
+    // halo: the messages of the boundary planes z0 and z1-1 go to rank-1 / rank+1, theirs are appended as ghosts
+    prof_begin("slab_halo", st);
+    slab_exchange(slab.lists[0], slab.z0 + 1, slab.z1 - 1, /*remove=*/false, st);
+    if (M.keyed_by_writer) M.appended_after_keyed = true;  // the ghosts are keyed by the build
+    prof_end(st);
+  }
   if (M.list.bound > 0) {
     prof_begin("build_index", st);
     std::vector<fgb_var> vars = M.list.vars(true);
@@ -952,7 +1072,17 @@ inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_
 
 inline void CUDASimulation::record_end_of_step(cudaStream_t main) {
   // end of step on the device: ++step counter, non-persistent lists emptied (reference :619-625)
-  detail::k_end_of_step<<<1, 32, 0, main>>>(d_ctrl, kStepSlot, d_zero_slots, n_zero_slots);
+  if (slab.enabled) {
+    // migration: agents whose position left the slab go to the neighbour that owns their plane
+    prof_begin("slab_migrate", main);
+    for (size_t k = 1; k < slab.lists.size(); ++k) {
+      SlabList &S = slab.lists[k];
+      slab_exchange(S, slab.z0, slab.z1, /*remove=*/true, main);
+      FGB_ABI_THROW(fgb_slab_check_bound(ctx, slot_ptr(S.list->count_slot), S.list->bound, slot_ptr(slab.err_slot), main));
+    }
+    prof_end(main);
+  }
+  detail::k_end_of_step<<<1, 32, 0, main>>>(d_ctrl, kStepSlot, d_zero_slots, n_zero_slots, slab.enabled ? slab.epoch_slot : 0u);
   ++own_launches;
   for (auto &m : messages)
     if (!m.second.desc->persistent) {
@@ -1113,6 +1243,204 @@ inline void CUDASimulation::endMessageExchange(const std::string &message) {
   exchange_active = false;
 }
 
+// ================================================================================================================
+// multi-GPU: z-slab decomposition behind step()
+// ================================================================================================================
+inline void CUDASimulation::configureSlabs(int rank, int world, const std::string &message, unsigned int halo_capacity,
+                                           unsigned int migrate_capacity) {
+  if (initialised) throw exception::InvalidArgument("configureSlabs must be called before the simulation is initialised");
+  if (world < 1 || rank < 0 || rank >= world || world > 32) throw exception::InvalidArgument("configureSlabs: bad rank / world");
+  auto it = model->messages.find(message);
+  if (it == model->messages.end() || it->second->dims() == 0) throw exception::InvalidMessageName("configureSlabs: '" + message + "' is not a spatial message list");
+  const MessageData &md = *it->second;
+  const int slow = md.dims() - 1;
+  const int planes = static_cast<int>(std::ceil((md.max[slow] - md.min[slow]) / md.radius));
+  if (world > planes) throw exception::InvalidArgument("configureSlabs: more ranks than bin planes");
+  slab.enabled = world > 1;
+  slab.rank = rank;
+  slab.world = world;
+  slab.message = message;
+  slab.planes = planes;
+  slab.z0 = static_cast<int>((static_cast<long long>(planes) * rank) / world);         // contiguous, as even as possible
+  slab.z1 = static_cast<int>((static_cast<long long>(planes) * (rank + 1)) / world);
+  slab.halo_cap = halo_capacity;
+  slab.mig_cap = migrate_capacity;
+  if (slab.enabled) {
+    const int w0 = std::max(slab.z0 - 1, 0), w1 = std::min(slab.z1 + 1, planes);  // own planes + one ghost plane per side
+    windows[message] = std::make_pair(w0, w1 - w0);
+  }
+}
+
+inline void CUDASimulation::slab_setup() {
+  detail::CUDAMessage &M = messages.at(slab.message);
+  const char *axis = M.desc->dims() == 3 ? "z" : "y";
+  auto add = [&](bool is_message, detail::DevList &l, detail::CUDAAgent *agent, unsigned int cap) {
+    const int pv = l.index_of(axis);
+    if (pv < 0 || l.meta[pv].type != std::type_index(typeid(float)) || l.meta[pv].elements != 1) return;
+    SlabList S;
+    S.is_message = is_message;
+    S.list = &l;
+    S.agent = agent;
+    S.pos_var = pv;
+    S.capacity = cap;
+    slab.lists.push_back(S);
+  };
+  add(true, M.list, nullptr, slab.halo_cap);
+  if (slab.lists.empty()) throw exception::InvalidMessageVar("slab message has no float position variable");
+  for (auto &a : agents)
+    for (auto &st : a.second.states) add(false, st.second, &a.second, slab.mig_cap);
+  size_t off = 0;
+  auto align = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  for (SlabList &S : slab.lists)
+    for (int side = 0; side < 2; ++side) {
+      SlabStaging &g = S.st[side];
+      for (size_t v = 0; v < S.list->names.size(); ++v) {
+        g.var_off.push_back(off);
+        off = align(off + static_cast<size_t>(S.capacity) * S.list->meta[v].bytes());
+      }
+      g.count_off = off;
+      g.flag_off = off + 8;
+      off = align(off + 16);
+    }
+  slab.mail_off = off;
+  off = align(off + static_cast<size_t>(2) * slab.world * 16);
+  slab.arena_bytes = off;
+  FGB_CUDA_THROW(cudaMalloc(&slab.arena, slab.arena_bytes));
+  FGB_CUDA_THROW(cudaMemset(slab.arena, 0, slab.arena_bytes));
+  slab.peer.assign(slab.world, nullptr);
+  slab.peer[slab.rank] = slab.arena;
+  slab.epoch_slot = alloc_slot();
+  slab.err_slot = alloc_slot();
+}
+
+inline void CUDASimulation::slabExportHandle(void *out) {
+  initialise();
+  if (!slab.enabled) throw exception::InvalidArgument("slab decomposition is not configured");
+  FGB_CUDA_THROW(cudaDeviceSynchronize());  // the arena is zeroed before any peer can see it
+  cudaIpcMemHandle_t h;
+  FGB_CUDA_THROW(cudaIpcGetMemHandle(&h, slab.arena));
+  std::memcpy(out, &h, sizeof(h));
+}
+
+inline void CUDASimulation::slabConnect(const void *all_handles) {
+  initialise();
+  if (!slab.enabled) throw exception::InvalidArgument("slab decomposition is not configured");
+  const char *p = static_cast<const char *>(all_handles);
+  for (int r = 0; r < slab.world; ++r) {
+    if (r == slab.rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, p + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+    void *mapped = nullptr;
+    FGB_CUDA_THROW(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    slab.peer[r] = static_cast<char *>(mapped);
+  }
+  slab.connected = true;
+}
+
+inline unsigned int CUDASimulation::slabError() {
+  initialise();
+  return slab.enabled ? read_slot(slab.err_slot) : 0u;
+}
+
+// One exchange of a list with both neighbours: items below plane `lo_plane` go to rank-1, items at or above `hi_plane`
+// to rank+1 (the compaction writes them -- and their count -- into the neighbour's staging buffer), optionally removed
+// here; then the neighbours' items are appended.  Every rank runs the same sequence every step (also with an empty
+// list: the neighbours wait for the flag).
+inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plane, bool remove, cudaStream_t st) {
+  detail::DevList &l = *S.list;
+  const detail::CUDAMessage &G = messages.at(slab.message);
+  const int slow = G.desc->dims() - 1;
+  const unsigned int n = l.bound;
+  unsigned int *d_n = slot_ptr(l.count_slot);
+  const unsigned int *d_epoch = slot_ptr(slab.epoch_slot);
+  unsigned int *d_err = slot_ptr(slab.err_slot);
+  const bool has[2] = {slab.rank > 0, slab.rank < slab.world - 1};
+  const unsigned int nv = static_cast<unsigned int>(l.names.size());
+  if (n > 0) {
+    for (auto &f : slab_flags) f.reserve(n);
+    FGB_ABI_THROW(fgb_plane_flags(ctx, reinterpret_cast<const float *>(l.data[S.pos_var]), n, d_n, G.md.min[slow], G.md.radius,
+                                  static_cast<int>(G.md.grid_dim[slow]), lo_plane, hi_plane, slab_flags[0].p, remove ? slab_flags[1].p : nullptr,
+                                  slab_flags[2].p, st));
+  }
+  unsigned long long *peer_flag[2] = {nullptr, nullptr};
+  for (int side = 0; side < 2; ++side) {
+    if (!has[side]) continue;
+    // I am the neighbour's OTHER side: what I send down arrives in rank-1's "from rank+1" buffer and vice versa
+    char *base = slab.peer[slab.rank + (side == 0 ? -1 : 1)];
+    const SlabStaging &g = S.st[side == 0 ? 1 : 0];
+    std::vector<fgb_var> vars(nv);
+    for (unsigned int v = 0; v < nv; ++v) {
+      vars[v].type_len = l.meta[v].bytes();
+      vars[v].in = l.data[v];
+      vars[v].out = base + g.var_off[v];
+    }
+    FGB_ABI_THROW(fgb_compact_limited(ctx, kSlabScratchSlot, slab_flags[side == 0 ? 0 : 2].p, 0, n, d_n, 0, 0, nullptr, S.capacity, vars.data(), nv,
+                                      reinterpret_cast<unsigned int *>(base + g.count_off), nullptr, st));
+    peer_flag[side] = reinterpret_cast<unsigned long long *>(base + g.flag_off);
+  }
+  if (remove && n > 0) {
+    std::vector<fgb_var> vars = l.vars(true);
+    FGB_ABI_THROW(fgb_compact(ctx, kSlabScratchSlot, slab_flags[1].p, 0, n, d_n, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
+    l.swap_buffers();
+  }
+  FGB_ABI_THROW(fgb_slab_signal(ctx, peer_flag[0], peer_flag[1], d_epoch, st));
+  const SlabStaging &from_lo = S.st[0], &from_hi = S.st[1];
+  FGB_ABI_THROW(fgb_slab_wait(ctx, has[0] ? reinterpret_cast<const unsigned long long *>(slab.arena + from_lo.flag_off) : nullptr,
+                              has[1] ? reinterpret_cast<const unsigned long long *>(slab.arena + from_hi.flag_off) : nullptr,
+                              has[0] ? reinterpret_cast<const unsigned int *>(slab.arena + from_lo.count_off) : nullptr,
+                              has[1] ? reinterpret_cast<const unsigned int *>(slab.arena + from_hi.count_off) : nullptr, S.capacity, d_epoch, d_err,
+                              cuda_config.slabTimeoutMs, st));
+  for (int side = 0; side < 2; ++side) {
+    if (!has[side]) continue;
+    const SlabStaging &g = S.st[side];
+    std::vector<fgb_var> vars(nv);
+    for (unsigned int v = 0; v < nv; ++v) {
+      vars[v].type_len = l.meta[v].bytes();
+      vars[v].in = slab.arena + g.var_off[v];
+      vars[v].out = l.data[v];
+    }
+    // copy-all append: keep_front == capacity keeps every item below the received count (clamped to the capacity)
+    FGB_ABI_THROW(fgb_compact(ctx, kSlabScratchSlot, nullptr, 0, S.capacity, reinterpret_cast<const unsigned int *>(slab.arena + g.count_off),
+                              S.capacity, 0, d_n, vars.data(), nv, nullptr, d_n, st));
+  }
+  if (S.is_message) {
+    l.bound += (has[0] ? S.capacity : 0u) + (has[1] ? S.capacity : 0u);
+    for (auto &m : messages)
+      if (&m.second.list == &l) m.second.pbm_dirty = true;
+  }
+  // agent lists keep their (sticky) launch bound: fgb_slab_check_bound raises the error word if the population outgrows
+  // it before the next slab_refresh_bounds()
+  l.touch();
+}
+
+// Re-read the list counts (one small copy + sync every slabRefreshPeriod steps) and re-centre the sticky launch bounds
+// of the decomposed agent lists: generous enough to absorb the net inflow until the next refresh, and unchanged as
+// long as they still fit, so that the captured step graphs are reused.
+inline void CUDASimulation::slab_refresh_bounds() {
+  std::vector<unsigned int> h(kCtrlWords);
+  FGB_CUDA_THROW(cudaMemcpyAsync(h.data(), d_ctrl, next_slot * 4, cudaMemcpyDeviceToHost, main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  if (h[slab.err_slot]) throw exception::CUDAError("slab exchange failed on the device: error bits " + std::to_string(h[slab.err_slot]) +
+                                                   " (1 neighbour timeout, 2 staging overflow, 4 list outgrew its launch bound)");
+  const unsigned int period = std::max(1u, cuda_config.slabRefreshPeriod);
+  for (size_t k = 1; k < slab.lists.size(); ++k) {
+    detail::DevList &l = *slab.lists[k].list;
+    const unsigned int count = h[l.count_slot], cap = slab.lists[k].capacity;
+    const unsigned int want = quantise(count + 8u * cap + count / 32u);
+    const bool too_small = static_cast<unsigned long long>(count) + 2ull * cap * period > l.bound;
+    const bool too_big = l.bound > want + want / 2u;
+    if (too_small || too_big) l.bound = want;
+  }
+  for (auto &a : agents) a.second.recompute_pop_bound();
+}
+
+inline void CUDASimulation::slab_allreduce(void *d_value, int dtype, int op) {
+  std::vector<void *> boxes(slab.world);
+  for (int r = 0; r < slab.world; ++r) boxes[r] = slab.peer[r] + slab.mail_off;
+  FGB_ABI_THROW(fgb_slab_allreduce(ctx, op, dtype, d_value, boxes.data(), slab.rank, slab.world, ++slab.reduce_epoch, slot_ptr(slab.err_slot),
+                                   cuda_config.slabTimeoutMs, main_stream));
+}
+
 inline void CUDASimulation::refresh_bounds() {
   std::vector<unsigned int> h(kCtrlWords);
   FGB_CUDA_THROW(cudaMemcpyAsync(h.data(), d_ctrl, next_slot * 4, cudaMemcpyDeviceToHost, main_stream));
@@ -1127,6 +1455,10 @@ inline void CUDASimulation::refresh_bounds() {
 inline bool CUDASimulation::step() {
   initialise();
   if (env_dirty) upload_environment();
+  if (slab.enabled) {
+    if (!slab.connected) throw exception::InvalidArgument("slab decomposition: slabConnect() must be called before the first step");
+    if (step_count % std::max(1u, cuda_config.slabRefreshPeriod) == 0) slab_refresh_bounds();
+  }
   plan_step();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (config.timing) {
@@ -1134,7 +1466,7 @@ inline bool CUDASimulation::step() {
     FGB_CUDA_THROW(cudaEventCreate(&e1));
     FGB_CUDA_THROW(cudaEventRecord(e0, main_stream));
   }
-  if (cuda_config.useCUDAGraphs && !model_has_host_layers && !cuda_config.profile) {
+  if (cuda_config.useCUDAGraphs && !model_has_host_layers && !cuda_config.profile && !streamed.armed) {
     // the key covers list pointers, bounds and capacities; grow-only scratch (scan flags, exec_perm, the kernel
     // library's per-stream scratch and per-list index buffers) is covered by the allocation generation: any
     // reallocation since the capture invalidates every cached graph (they hold the freed pointers)
@@ -1185,14 +1517,17 @@ inline bool CUDASimulation::step() {
   } else {
     record_step(main_stream);
   }
+  streamed.armed = false;  // a streamed download covers exactly one step
+  ++step_count;
+  if (!model->step_functions.empty()) {
+    // step functions see the finished step (reference CUDASimulation.cu:603-617 runs them inside step(), inside its
+    // per-step timer); their reductions are launched on the step's stream
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    for (auto sf : model->step_functions) sf(&host_api);
+  }
   if (config.timing) {
     FGB_CUDA_THROW(cudaEventRecord(e1, main_stream));
     step_events.emplace_back(e0, e1);
-  }
-  ++step_count;
-  if (!model->step_functions.empty()) {
-    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
-    for (auto sf : model->step_functions) sf(&host_api);
   }
   if (model_has_births) refresh_bounds();
   bool go_on = true;
@@ -1280,7 +1615,16 @@ inline std::map<std::string, std::pair<double, unsigned int>> CUDASimulation::ge
 
 // ---- minimal HostAPI -------------------------------------------------------------------------
 inline unsigned int HostAPI::getStepCounter() const { return sim->getStepCounter(); }
-inline unsigned int HostAgentAPI::count() { return sim->getAgentCount(agent, state); }
+inline unsigned int HostAgentAPI::count() {
+  const unsigned int local = sim->getAgentCount(agent, state);
+  if (!sim->slab.enabled) return local;
+  unsigned long long v = local;  // global population: all-reduce of the per-slab counts
+  FGB_CUDA_THROW(cudaMemcpyAsync(sim->d_reduce_out, &v, 8, cudaMemcpyHostToDevice, sim->main_stream));
+  sim->slab_allreduce(sim->d_reduce_out, FGB_U64, FGB_REDUCE_SUM);
+  FGB_CUDA_THROW(cudaMemcpyAsync(&v, sim->d_reduce_out, 8, cudaMemcpyDeviceToHost, sim->main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
+  return static_cast<unsigned int>(v);
+}
 namespace detail {
 template <typename T> struct reduce_dtype;
 template <> struct reduce_dtype<float> { static constexpr int value = FGB_F32; using sum_t = double; };
@@ -1290,6 +1634,9 @@ template <> struct reduce_dtype<unsigned int> { static constexpr int value = FGB
 template <> struct reduce_dtype<long long> { static constexpr int value = FGB_I64; using sum_t = long long; };
 template <> struct reduce_dtype<unsigned long long> { static constexpr int value = FGB_U64; using sum_t = unsigned long long; };
 }  // namespace detail
+// under a slab decomposition every rank holds a part of the population: fold the per-rank results (8 bytes each)
+#define FGB_SLAB_FOLD(R, op)                                                                                  \
+  if (sim->slab.enabled) sim->slab_allreduce(sim->d_reduce_out, detail::reduce_dtype<R>::value, (op))
 
 // one reduction kernel over the state list's variable (device-resident count), then 8 bytes to the host
 template <typename T, typename R>
@@ -1301,6 +1648,7 @@ inline R HostAgentAPI::reduce(const std::string &variable, int op) {
   if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
   FGB_ABI_THROW(fgb_reduce(sim->ctx, 0, op, detail::reduce_dtype<T>::value, l.data[i], l.bound, sim->slot_ptr(l.count_slot),
                            sim->d_reduce_out, sim->main_stream));
+  FGB_SLAB_FOLD(R, op);
   R r{};
   FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(R), cudaMemcpyDeviceToHost, sim->main_stream));
   FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
@@ -1315,6 +1663,7 @@ inline R HostAgentAPI::transform_reduce(const std::string &variable, int transfo
   if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
   FGB_ABI_THROW(fgb_transform_reduce(sim->ctx, 0, transform, detail::reduce_dtype<T>::value, l.data[i], l.bound,
                                      sim->slot_ptr(l.count_slot), param, sim->d_reduce_out, sim->main_stream));
+  FGB_SLAB_FOLD(R, FGB_REDUCE_SUM);
   R r{};
   FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(R), cudaMemcpyDeviceToHost, sim->main_stream));
   FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));

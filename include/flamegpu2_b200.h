@@ -282,6 +282,31 @@ fgb_status fgb_sort_spatial(fgb_ctx *ctx, unsigned int stream_id, const float *x
 fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_max, int max_bit);
 fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max);
 
+/* ---- multi-GPU z-slab exchange (b200 extension; the reference has no multi-GPU simulation) -----------
+ * One process per GPU.  Halo messages / migrating agents are packed by fgb_compact_limited straight into the
+ * NEIGHBOUR's staging buffer (peer memory mapped with cudaIpcOpenMemHandle: vars[v].out and d_out_count are peer
+ * pointers), so the pack is the transfer.  These entry points are the synchronisation around it; epochs advance by one
+ * per simulation step and are read from a device word, so every launch is CUDA-graph replayable.
+ *   fgb_slab_signal : peer_flag_{lo,hi} (peer memory, NULL = no neighbour) <- *d_epoch + 1, ordered after all earlier
+ *                     writes of the stream (system-scope release)
+ *   fgb_slab_wait   : waits until the LOCAL flag words reach *d_epoch + 1; then *count_{lo,hi} > capacity raises
+ *                     FGB_SLAB_ERR_OVERFLOW in *d_err; gives up after timeout_ms with FGB_SLAB_ERR_TIMEOUT (a dead
+ *                     peer must not wedge the GPU)
+ *   fgb_slab_check_bound : *d_count > bound raises FGB_SLAB_ERR_BOUND (agents beyond a launch bound would not execute)
+ *   fgb_slab_allreduce   : all-reduce (op: fgb_reduce_op, dtype: fgb_dtype of the 4/8-byte value) over per-rank
+ *                     mailboxes (mailboxes[r] = rank r's array of 2 * world 16-byte slots, peer memory for r != rank);
+ *                     folded in rank order, so every rank obtains the identical value; `epoch` must increase by one
+ *                     per call on every rank */
+enum { FGB_SLAB_ERR_TIMEOUT = 1, FGB_SLAB_ERR_OVERFLOW = 2, FGB_SLAB_ERR_BOUND = 4 };
+fgb_status fgb_slab_signal(fgb_ctx *ctx, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, const unsigned int *d_epoch,
+                           void *stream);
+fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const unsigned long long *flag_hi, const unsigned int *count_lo,
+                         const unsigned int *count_hi, unsigned int capacity, const unsigned int *d_epoch, unsigned int *d_err,
+                         unsigned int timeout_ms, void *stream);
+fgb_status fgb_slab_check_bound(fgb_ctx *ctx, const unsigned int *d_count, unsigned int bound, unsigned int *d_err, void *stream);
+fgb_status fgb_slab_allreduce(fgb_ctx *ctx, int op, int dtype, void *d_value_inout, void *const *mailboxes, int rank, int world,
+                              unsigned long long epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream);
+
 /* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
 unsigned long long fgb_launch_count(const fgb_ctx *ctx);
 

@@ -206,6 +206,7 @@ int main(int argc, const char **argv) {
       p.repulse = getf(kv, "repulse", p.repulse);
       p.sort_period = getu(kv, "sort_period", p.sort_period);
       p.validation = getu(kv, "validation", p.validation);
+      p.env_max_z = getf(kv, "env_max_z", p.env_max_z);
       fgb_examples::define_circles(model, p);
     } else if (model_name == "boids3d" || model_name == "boids2d") {
       fgb_examples::BoidsParams p;

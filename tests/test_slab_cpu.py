@@ -71,40 +71,34 @@ def test_neighbour_exchange_gloo(world):
     assert dict(out) == {r: 1 for r in range(world)}
 
 
-def _flat_worker(rank, world, port, out):
+def _handle_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # the staging layout of one list (message {id,x,y,z} plus an odd-sized variable): one flat buffer per side,
-        # variables back to back (16-byte aligned), count word behind them; exchanged with ONE send/recv per neighbour
-        layout = [("id", 4), ("v3", 12), ("x", 4)]
-        cap = 37
-        b = slab._Buffers(layout, cap, "cpu")
-        assert b.count_off % 16 == 0 and b.nbytes == b.count_off + 16
-        for side in ("lo", "hi"):
-            offs = [v.data_ptr() - b.send_flat[side].data_ptr() for v in b.send[side]]
-            assert offs[0] == 0 and all(o % 16 == 0 for o in offs) and offs == sorted(offs)
-            assert [v.numel() for v in b.send[side]] == [cap * bytes_ for _, bytes_ in layout]
-            assert b.send_count[side].data_ptr() - b.send_flat[side].data_ptr() == b.count_off
-            for k, v in enumerate(b.send[side]):
-                v.fill_(16 * rank + (0 if side == "lo" else 8) + k + 1)
-            b.send_count[side].fill_(1000 * rank + (1 if side == "lo" else 2))
-        slab.exchange_with_neighbours([b.send_flat["lo"]], [b.send_flat["hi"]], [b.recv_flat["lo"]], [b.recv_flat["hi"]], rank, world)
-        ok = True
-        if rank > 0:
-            ok &= int(b.recv_counts["lo"]) == 1000 * (rank - 1) + 2
-            ok &= all(bool((v == 16 * (rank - 1) + 8 + k + 1).all()) for k, v in enumerate(b.recv["lo"]))
-        if rank < world - 1:
-            ok &= int(b.recv_counts["hi"]) == 1000 * (rank + 1) + 1
-            ok &= all(bool((v == 16 * (rank + 1) + k + 1).all()) for k, v in enumerate(b.recv["hi"]))
+        # what SlabSimulation does once at start-up: every rank contributes its 64-byte staging handle and receives all
+        # of them in rank order (the C++ side maps rank r's arena from bytes [64 r, 64 r + 64))
+        blob = bytes([(17 * rank + k) % 251 for k in range(64)])
+        everyone = slab.all_gather_bytes(blob, world)
+        ok = len(everyone) == 64 * world
+        for r in range(world):
+            ok &= everyone[64 * r:64 * (r + 1)] == bytes([(17 * r + k) % 251 for k in range(64)])
         out[rank] = 1 if ok else 0
     finally:
         dist.destroy_process_group()
 
 
-def test_flat_staging_buffers_exchange_gloo():
+@pytest.mark.parametrize("world", [2, 3])
+def test_staging_handles_all_gather_gloo(world):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_flat_worker, args=(3, _free_port(), out), nprocs=3, join=True)
-    assert dict(out) == {r: 1 for r in range(3)}
+    mp.spawn(_handle_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: 1 for r in range(world)}
+
+
+def test_slab_arithmetic_matches_the_cpp_layer():
+    # CUDASimulation::configureSlabs computes z0 = planes * rank / world (integer division); the host helper must agree
+    for planes in (8, 50, 51, 256):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                assert slab.slab_planes(planes, world, r) == ((planes * r) // world, (planes * (r + 1)) // world)
