@@ -169,7 +169,7 @@ def make_sim(box, rank, world, local, **cfg):
 
     per_plane = box.n_per_rank // box.planes_per_rank
     halo_cap = int(3 * per_plane + 8192)   # a boundary plane holds ~n/planes messages (3x: clustering)
-    mig_cap = int(per_plane // 2 + 4096)   # a few percent of a plane changes slab per step
+    mig_cap = int(min(per_plane // 2 + 4096, 131072))   # a few percent of a plane changes slab per step
     sl = slab.SlabSimulation("circles", "Circle", "location", rank, world, local, box.planes, halo_capacity=halo_cap,
                              migrate_capacity=mig_cap, **box.model_params(), **cfg)
     return sl.sim, sl

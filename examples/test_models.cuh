@@ -350,6 +350,20 @@ FLAMEGPU_AGENT_FUNCTION_CONDITION(t_tr_step_parity) {
   return (FLAMEGPU->getVariable<unsigned int>("y") + FLAMEGPU->getStepCounter()) % 3 == 0;
 }
 
+// ---- test_host_agent_creation.cu:19-43 (BasicOutput from init and step functions, OutputMultiAgent) ---------------
+FLAMEGPU_STEP_FUNCTION(t_host_basic_output) {
+  auto t = FLAMEGPU->agent("agent");
+  for (unsigned int i = 0; i < 512; ++i) t.newAgent().setVariable<float>("x", 1.0f);
+}
+FLAMEGPU_STEP_FUNCTION(t_host_multi_output) {
+  auto t = FLAMEGPU->agent("agent", "b");
+  auto t2 = FLAMEGPU->agent("agent2");
+  for (unsigned int i = 0; i < 512; ++i) {
+    t.newAgent().setVariable<float>("x", 1.0f);
+    t2.newAgent().setVariable<float>("y", 2.0f);
+  }
+}
+
 enum TestModel {
   TM_COUNT3D = 0,        // Spatial3DMessageTest.Mandatory
   TM_OPTIONAL3D = 1,     // Spatial3DMessageTest.Optional
@@ -374,7 +388,8 @@ enum TestModel {
   TM_TRANSITION_COND = 19,      // TestAgentStateTransitions.Src_10_Dest_10 (conditional transition)
   TM_UNIQUE_IDS = 20,           // DeviceAgentCreationTest.AgentID_MultipleStatesUniqueIDs (two functions in one layer)
   TM_CONCURRENT_SPATIAL = 21,   // TestCUDASimulationConcurrency.ConcurrentMessageOutputInputSpatial3D (4 agent types)
-  TM_TRANSITION_PINGPONG = 22   // conditional transitions both ways, many steps (list bounds must stay bounded)
+  TM_TRANSITION_PINGPONG = 22,  // conditional transitions both ways, many steps (list bounds must stay bounded)
+  TM_HOST_CREATION = 23         // HostAgentCreationTest.FromInit / FromStep / FromStepMultiAgent (host_init: 1 init, 0 step, 2 multi)
 };
 
 struct TestParams {
@@ -388,6 +403,7 @@ struct TestParams {
   int birth_optional = 0, birth_death = 0, birth_condition = 0;
   int birth_target = 0;  // 0 same state, 1 different state, 2 different agent
   int append_optional = 0;  // TM_APPEND
+  int host_init = 0;        // TM_HOST_CREATION
 };
 
 constexpr int kConcurrentAgents = 4;  // TM_CONCURRENT_SPATIAL: agent_0..3, location_0..3
@@ -691,6 +707,22 @@ inline void define_test_model(flamegpu::ModelDescription &model, const TestParam
       ba.setFunctionCondition(t_tr_step_parity);
       model.newLayer().addAgentFunction(ab);
       model.newLayer().addAgentFunction(ba);
+      break;
+    }
+    case TM_HOST_CREATION: {
+      agent.newVariable<float>("x");
+      agent.newVariable<float>("default", 15.0f);  // test_host_agent_creation.cu DefaultVariableValue
+      if (p.host_init == 2) {
+        agent.newState("a");
+        agent.newState("b");
+        flamegpu::AgentDescription agent2 = model.newAgent("agent2");
+        agent2.newVariable<float>("y");
+        model.addStepFunction(t_host_multi_output);
+      } else if (p.host_init == 1) {
+        model.addInitFunction(t_host_basic_output);
+      } else {
+        model.addStepFunction(t_host_basic_output);
+      }
       break;
     }
     case TM_UNIQUE_IDS: {

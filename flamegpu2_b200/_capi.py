@@ -57,15 +57,25 @@ SIGNATURES = {
     "fgb_spatial_get_window": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fgb_plane_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fgb_array_reorder": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "fgb_scatter_new_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]),
+    "fgb_histogram_even": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_double, C.c_double, C.c_void_p,
+                                     C.c_void_p]),
     "fgb_slab_signal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_slab_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint,
                                 C.c_void_p]),
+    "fgb_slab_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint]),
+    "fgb_slab_migrate_out": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "fgb_slab_check_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
     "fgb_slab_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong,
                                      C.c_void_p, C.c_uint, C.c_void_p]),
     "fgb_spatial_destroy": (C.c_int, [C.c_void_p]),
     "fgb_spatial_get_metadata": (C.c_int, [C.c_void_p, C.POINTER(fgb_spatial_metadata), C.POINTER(C.c_uint)]),
     "fgb_spatial_metadata_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "fgb_spatial_bin_count": (C.c_uint, [C.c_void_p]),
     "fgb_spatial_read_pbm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_spatial_reserve": (C.c_int, [C.c_void_p, C.c_uint]),
     "fgb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_uint, C.c_uint, C.c_int]),

@@ -13,6 +13,7 @@
 #include "fgb_radix.cuh"
 #include "fgb_reduce.cuh"
 #include "fgb_scan.cuh"
+#include "fgb_scatter_misc.cuh"
 #include "fgb_slab.cuh"
 
 using namespace fgb;
@@ -357,6 +358,7 @@ fgb_status fgb_ctx_destroy(fgb_ctx *ctx) {
     for (auto &b : s.rs_keys) b.release();
     for (auto &b : s.rs_idx) b.release();
     s.red.release();
+    s.slab.release();
   }
   delete ctx;
   return FGB_OK;
@@ -474,6 +476,8 @@ fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata 
   return FGB_OK;
 }
 
+unsigned int fgb_spatial_bin_count(const fgb_spatial *sp) { return sp ? sp->bin_count : 0u; }
+
 const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp) { return sp ? sp->d_md : nullptr; }
 
 fgb_status fgb_spatial_get_window(const fgb_spatial *sp, int *plane_begin, int *plane_count) {
@@ -511,6 +515,54 @@ fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const 
   k_slab_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flag_lo, flag_hi, count_lo, count_hi, capacity, d_epoch, d_err,
                                                               static_cast<unsigned long long>(timeout_ms) * 1000000ull);
   ctx->launches += 1;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int capacity) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS) return FGB_ERR_INVALID_ARG;
+  return reserve_zeroed(ctx->slot[stream_id].slab, 256 + static_cast<size_t>(capacity) * 4 * 6);
+}
+
+fgb_status fgb_slab_migrate_out(fgb_ctx *ctx, unsigned int stream_id, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                                float radius, int grid_dim, int lo_plane, int hi_plane, unsigned int capacity, const fgb_var *list_vars,
+                                unsigned int nvars, void *const *peer_lo, void *const *peer_hi, unsigned int *peer_count_lo,
+                                unsigned int *peer_count_hi, unsigned int *d_n_inout, unsigned int *d_err, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || !d_n_inout || !d_err || (n && !pos) || capacity == 0 ||
+      2ull * capacity > static_cast<unsigned long long>(kSlabHoleBits) || (peer_lo && !peer_count_lo) || (peer_hi && !peer_count_hi))
+    return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const size_t head = 256;
+  int r = reserve_zeroed(s.slab, head + static_cast<size_t>(capacity) * 4 * 6);
+  if (r) return r;
+  char *base = static_cast<char *>(s.slab.p);
+  SlabSel *sel = reinterpret_cast<SlabSel *>(base);
+  unsigned int *done = reinterpret_cast<unsigned int *>(base + 64);
+  uint32_t *idx_lo = reinterpret_cast<uint32_t *>(base + head);
+  uint32_t *idx_hi = idx_lo + capacity;
+  uint32_t *to = idx_hi + capacity;
+  uint32_t *from = to + 2 * static_cast<size_t>(capacity);
+  VarTable vt_list, vt_lo{}, vt_hi{};
+  r = make_var_table(list_vars, nvars, &vt_list);
+  if (r) return r;
+  vt_lo.n = vt_hi.n = 0;
+  for (int side = 0; side < 2; ++side) {
+    void *const *peer = side == 0 ? peer_lo : peer_hi;
+    if (!peer) continue;
+    VarTable &vt = side == 0 ? vt_lo : vt_hi;
+    vt = vt_list;
+    for (unsigned int v = 0; v < nvars; ++v) vt.out[v] = static_cast<char *>(peer[v]);
+  }
+  if (n) k_slab_select<<<(n + 255) / 256, 256, 0, st>>>(pos, n, d_n, env_min, radius, grid_dim, lo_plane, hi_plane, capacity, sel, idx_lo, idx_hi);
+  const unsigned int pgrid = std::max(1u, std::min((capacity + 255u) / 256u, 4u * kNumSMs));
+  k_slab_pack<<<dim3(pgrid, 2), 256, 0, st>>>(sel, idx_lo, idx_hi, capacity, vt_lo, vt_hi, peer_count_lo, peer_count_hi);
+  k_slab_holes<<<1, 1024, 0, st>>>(sel, idx_lo, idx_hi, capacity, n, d_n, to, from, d_err);
+  // in == out == the list's own columns: tail agents move into the holes
+  VarTable vt_move = vt_list;
+  for (unsigned int v = 0; v < nvars; ++v) vt_move.out[v] = const_cast<char *>(vt_list.in[v]);
+  const unsigned int fgrid = std::max(1u, std::min((2u * capacity + 255u) / 256u, 2u * kNumSMs));
+  k_slab_fill<<<fgrid, 256, 0, st>>>(sel, to, from, vt_move, d_n_inout, done);
+  ctx->launches += n ? 4 : 3;
   return launch_ok();
 }
 
@@ -815,6 +867,74 @@ fgb_status fgb_broadcast_init(fgb_ctx *ctx, const fgb_var *vars, unsigned int nv
   if (r) return r;
   k_broadcast_init<<<(n + 255) / 256, 256, 0, st>>>(n, out_offset, vt);
   ctx->launches += 1;
+  return launch_ok();
+}
+
+/* CUDAScatter::arrayMessageReorder (CUDAScatter.cu:567-655) */
+fgb_status fgb_array_reorder(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *index, unsigned int array_length, const fgb_var *vars,
+                             unsigned int nvars, unsigned int n, const unsigned int *d_n, unsigned int *d_write_count,
+                             unsigned int *d_max_writes, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || (n && !index) || (d_max_writes && !d_write_count)) return FGB_ERR_INVALID_ARG;
+  if (n > array_length) return FGB_ERR_INVALID_ARG;  // "Too many messages output for array message structure" (:579-581)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  if (n) {
+    k_array_reorder<<<(n + 255) / 256, 256, 0, st>>>(index, array_length, n, d_n, vt, d_write_count);
+    ctx->launches += 1;
+  }
+  if (d_max_writes) {
+    fgb_stream_scratch &s = ctx->slot[stream_id];
+    r = reserve_zeroed(s.red, static_cast<size_t>(kRedMaxBlocks) * 8 + 8);
+    if (r) return r;
+    uint32_t *partial = static_cast<uint32_t *>(s.red.p);
+    uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(s.red.p) + static_cast<size_t>(kRedMaxBlocks) * 8);
+    unsigned int blocks = (array_length + 2047) / 2048;
+    blocks = blocks < 1u ? 1u : (blocks > static_cast<unsigned int>(kRedMaxBlocks) ? static_cast<unsigned int>(kRedMaxBlocks) : blocks);
+    k_array_conflicts<<<blocks, 256, 0, st>>>(d_write_count, array_length, partial, done, d_max_writes);
+    ctx->launches += 1;
+  }
+  return launch_ok();
+}
+
+/* CUDAScatter::scatterNewAgents (CUDAScatter.cu:367-395) */
+fgb_status fgb_scatter_new_agents(fgb_ctx *ctx, const void *d_aos, unsigned int agent_size, const fgb_var *vars, unsigned int nvars,
+                                  unsigned int n, unsigned int out_offset, const unsigned int *d_out_offset, void *stream) {
+  if (!ctx || (n && !d_aos) || agent_size == 0) return FGB_ERR_INVALID_ARG;
+  if (n == 0 || nvars == 0) return FGB_OK;
+  VarTable vt;
+  int r = make_var_table(vars, nvars, &vt);
+  if (r) return r;
+  const char *base = static_cast<const char *>(d_aos);
+  for (unsigned int v = 0; v < nvars; ++v)
+    if (vt.in[v] < base || vt.in[v] + vt.len[v] > base + agent_size) return FGB_ERR_INVALID_ARG;  // every variable lies inside the struct
+  const size_t tile_bytes = static_cast<size_t>(kNaTile) * agent_size;
+  const int staged = tile_bytes <= 48 * 1024 ? 1 : 0;
+  k_new_agents<<<(n + kNaTile - 1) / kNaTile, 256, staged ? tile_bytes : 0, static_cast<cudaStream_t>(stream)>>>(n, agent_size, out_offset, d_out_offset,
+                                                                                                                  base, vt, staged);
+  ctx->launches += 1;
+  return launch_ok();
+}
+
+/* cub::DeviceHistogram::HistogramEven as called by HostAgentAPI::histogramEven (HostAgentAPI.cuh:720-745) */
+fgb_status fgb_histogram_even(fgb_ctx *ctx, int dtype, const void *in, unsigned int n, const unsigned int *d_n, unsigned int bins,
+                              double lower, double upper, unsigned int *d_counts, void *stream) {
+  if (!ctx || !d_counts || (n && !in) || bins == 0 || !(upper > lower) || dtype < FGB_F32 || dtype > FGB_U64) return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FGB_CHECK(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(bins) * 4, st));
+  if (n == 0) return FGB_OK;
+  unsigned int blocks = (n + 2047) / 2048;
+  blocks = blocks > 4u * kNumSMs ? 4u * kNumSMs : blocks;
+  ctx->launches += 1;
+  switch (dtype) {
+    case FGB_F32: k_histogram_even<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(in), n, d_n, bins, static_cast<float>(lower), static_cast<float>(upper), d_counts); break;
+    case FGB_F64: k_histogram_even<double><<<blocks, 256, 0, st>>>(static_cast<const double *>(in), n, d_n, bins, lower, upper, d_counts); break;
+    case FGB_I32: k_histogram_even<int><<<blocks, 256, 0, st>>>(static_cast<const int *>(in), n, d_n, bins, static_cast<int>(lower), static_cast<int>(upper), d_counts); break;
+    case FGB_U32: k_histogram_even<unsigned int><<<blocks, 256, 0, st>>>(static_cast<const unsigned int *>(in), n, d_n, bins, static_cast<unsigned int>(lower), static_cast<unsigned int>(upper), d_counts); break;
+    case FGB_I64: k_histogram_even<long long><<<blocks, 256, 0, st>>>(static_cast<const long long *>(in), n, d_n, bins, static_cast<long long>(lower), static_cast<long long>(upper), d_counts); break;
+    default: k_histogram_even<unsigned long long><<<blocks, 256, 0, st>>>(static_cast<const unsigned long long *>(in), n, d_n, bins, static_cast<unsigned long long>(lower), static_cast<unsigned long long>(upper), d_counts); break;
+  }
   return launch_ok();
 }
 

@@ -240,6 +240,7 @@ struct fgb_stream_scratch {
   fgb::DevBuf rs_keys[2];   // radix sort: key ping-pong
   fgb::DevBuf rs_idx[2];    // radix sort: index ping-pong
   fgb::DevBuf red;          // reductions: per-block partials (8 B each) + done counter
+  fgb::DevBuf slab;         // slab migration: control block, leaver index lists, hole / tail pairing
 };
 
 #define FGB_MAX_STREAMS 128
@@ -254,7 +255,7 @@ struct fgb_ctx {
   fgb_ctx() {
     for (auto &s : slot) {
       fgb::DevBuf *all[] = {&s.tile_state, &s.sort_hist, &s.sort_cursor, &s.perm, &s.worklist, &s.ctrl, &s.rs_state,
-                            &s.rs_keys[0], &s.rs_keys[1], &s.rs_idx[0], &s.rs_idx[1], &s.red};
+                            &s.rs_keys[0], &s.rs_keys[1], &s.rs_idx[0], &s.rs_idx[1], &s.red, &s.slab};
       for (fgb::DevBuf *b : all) b->gen = &generation;
     }
   }

@@ -130,3 +130,154 @@ __global__ void k_slab_allreduce(A *value_inout, const __grid_constant__ SlabMai
 
 #endif  // __CUDACC__
 }  // namespace fgb
+
+// ------------------------------------------------------------------------------------------------------------------
+// Migration without rewriting the list.  Only a few agents per step leave a slab (those that crossed one of its two
+// boundary planes), so instead of a stable compaction of EVERY variable of EVERY agent (read + write of the whole list)
+//   k_slab_select : one read of the position along the decomposed axis; the indices of the leavers are collected in
+//                   two small lists (warp-aggregated atomics; order is arrival order)
+//   k_slab_pack   : gathers the leavers' variables straight into the neighbours' staging buffers (peer memory) + counts
+//   k_slab_holes  : ONE block pairs every hole below the new list end with a surviving agent of the tail
+//   k_slab_fill   : moves those tail agents into the holes; the list's count becomes n - leavers
+// The list stays dense; the relative order of the agents that stay changes only for the few moved tail agents (the
+// order of a state list is observable, but a slab's list has no single-GPU counterpart to match; the order inside a
+// PBM bin is unspecified in the reference).
+// ------------------------------------------------------------------------------------------------------------------
+namespace fgb {
+#ifdef __CUDACC__
+
+struct SlabSel {           // device-resident control block of one exchange (zeroed by k_slab_fill for the next one)
+  unsigned int cnt[2];     // leavers towards rank-1 / rank+1 (may exceed the list capacity: overflow is reported)
+  unsigned int pairs;      // holes below the new end == tail agents to move
+  unsigned int new_n;
+};
+
+__global__ void __launch_bounds__(256) k_slab_select(const float *__restrict__ p, uint32_t n_max, const unsigned int *d_n, float mn, float radius,
+                                                     int dim, int lo, int hi, uint32_t cap, SlabSel *sel, uint32_t *idx_lo, uint32_t *idx_hi) {
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  int side = -1;
+  if (i < n) {
+    int c = static_cast<int>(floorf(__fdiv_rn(__ldg(p + i) - mn, radius)));
+    c = c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+    side = c < lo ? 0 : (c >= hi ? 1 : -1);
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, side == s);
+    if (!m) continue;
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int base = 0;
+    if (lane == static_cast<unsigned int>(__ffs(m) - 1)) base = atomicAdd(&sel->cnt[s], static_cast<unsigned int>(__popc(m)));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    if (side == s) {
+      const unsigned int at = base + __popc(m & ((1u << lane) - 1u));
+      if (at < cap) (s == 0 ? idx_lo : idx_hi)[at] = i;
+    }
+  }
+}
+
+// blockIdx.y = side.  vt_lo / vt_hi: in = the list's columns, out = the neighbour's staging columns (NULL table n == 0:
+// no neighbour on that side; its leavers are still removed -- they left the global domain's decomposition range never
+// happens with clamped planes, so the lists are empty there).
+__global__ void __launch_bounds__(256) k_slab_pack(const SlabSel *sel, const uint32_t *__restrict__ idx_lo, const uint32_t *__restrict__ idx_hi,
+                                                   uint32_t cap, const __grid_constant__ VarTable vt_lo, const __grid_constant__ VarTable vt_hi,
+                                                   unsigned int *peer_count_lo, unsigned int *peer_count_hi) {
+  const int s = blockIdx.y;
+  const VarTable &vt = s == 0 ? vt_lo : vt_hi;
+  const uint32_t *idx = s == 0 ? idx_lo : idx_hi;
+  unsigned int *peer_count = s == 0 ? peer_count_lo : peer_count_hi;
+  const unsigned int total = sel->cnt[s];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && peer_count) *peer_count = total;  // the receiver flags total > cap as an overflow
+  if (vt.n == 0) return;
+  const unsigned int m = total < cap ? total : cap;
+  for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < m; j += gridDim.x * 256) {
+    const uint32_t src = idx[j];
+    for (uint32_t v = 0; v < vt.n; ++v) copy_item(vt, v, src, j);
+  }
+}
+
+// One block.  holes = idx_lo[0..c0) U idx_hi[0..c1); new_n = n - (c0 + c1).  to[k] = k-th hole below new_n,
+// from[k] = k-th surviving index in [new_n, n).  Tail membership is a bitmap in shared memory (tail length == #holes).
+constexpr int kSlabHoleBits = 1 << 18;  // up to 262144 leavers per step and rank (32 KB bitmap)
+__global__ void __launch_bounds__(1024) k_slab_holes(SlabSel *sel, const uint32_t *__restrict__ idx_lo, const uint32_t *__restrict__ idx_hi,
+                                                     uint32_t cap, uint32_t n_max, const unsigned int *d_n, uint32_t *to, uint32_t *from,
+                                                     unsigned int *d_err) {
+  __shared__ uint32_t s_bits[kSlabHoleBits / 32];
+  __shared__ uint32_t s_scan[33];
+  __shared__ uint32_t s_cursor;
+  const uint32_t n = load_count_coherent(d_n, n_max);
+  uint32_t c0 = sel->cnt[0], c1 = sel->cnt[1];
+  if (c0 > cap || c1 > cap) {
+    if (threadIdx.x == 0) atomicOr(d_err, kSlabErrOverflow);
+    c0 = c0 < cap ? c0 : cap;
+    c1 = c1 < cap ? c1 : cap;
+  }
+  uint32_t h = c0 + c1;
+  if (h > static_cast<uint32_t>(kSlabHoleBits)) {  // cannot happen with capacities below the bitmap size; keep memory safe regardless
+    if (threadIdx.x == 0) atomicOr(d_err, kSlabErrOverflow);
+    h = kSlabHoleBits;
+    c1 = h > c0 ? h - c0 : 0u;
+    c0 = h - c1;
+  }
+  const uint32_t new_n = n - h;
+  for (uint32_t w = threadIdx.x; w < (h + 31u) / 32u; w += 1024) s_bits[w] = 0u;
+  if (threadIdx.x == 0) s_cursor = 0u;
+  __syncthreads();
+  // holes below the new end need filling; holes in the tail are simply cut off (marked in the bitmap)
+  for (uint32_t k = threadIdx.x; k < h; k += 1024) {
+    const uint32_t i = k < c0 ? idx_lo[k] : idx_hi[k - c0];
+    if (i >= new_n) atomicOr(&s_bits[(i - new_n) >> 5], 1u << ((i - new_n) & 31u));
+    else to[atomicAdd(&s_cursor, 1u)] = i;
+  }
+  __syncthreads();
+  const uint32_t pairs = s_cursor;
+  // survivors of the tail, in index order: thread t owns bitmap words [t*W, (t+1)*W)
+  const uint32_t words = (h + 31u) / 32u;
+  const uint32_t W = (words + 1023u) / 1024u;
+  uint32_t mine = 0;
+  for (uint32_t w = threadIdx.x * W; w < (threadIdx.x + 1) * W && w < words; ++w) {
+    const uint32_t valid = (w + 1u) * 32u <= h ? 0xFFFFFFFFu : ((1u << (h - w * 32u)) - 1u);
+    mine += __popc(~s_bits[w] & valid);
+  }
+  uint32_t total;
+  uint32_t at = block_exclusive_scan(mine, s_scan, &total);
+  for (uint32_t w = threadIdx.x * W; w < (threadIdx.x + 1) * W && w < words; ++w) {
+    const uint32_t valid = (w + 1u) * 32u <= h ? 0xFFFFFFFFu : ((1u << (h - w * 32u)) - 1u);
+    uint32_t live = ~s_bits[w] & valid;
+    while (live) {
+      const int b = __ffs(static_cast<int>(live)) - 1;
+      live &= live - 1u;
+      from[at++] = new_n + w * 32u + static_cast<uint32_t>(b);
+    }
+  }
+  if (threadIdx.x == 0) {
+    sel->pairs = pairs;  // == total by construction
+    sel->new_n = new_n;
+  }
+}
+
+// moves from[k] -> to[k] for every variable, publishes the new count and clears the control block for the next exchange
+__global__ void __launch_bounds__(256) k_slab_fill(SlabSel *sel, const uint32_t *__restrict__ to, const uint32_t *__restrict__ from,
+                                                   const __grid_constant__ VarTable vt, unsigned int *d_n, unsigned int *done) {
+  __shared__ unsigned int s_last;
+  const unsigned int pairs = sel->pairs;
+  for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < pairs; k += gridDim.x * 256) {
+    const uint32_t a = to[k], b = from[k];
+    for (uint32_t v = 0; v < vt.n; ++v) copy_item(vt, v, b, a);  // in == out == the list's columns
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *d_n = sel->new_n;
+    sel->cnt[0] = sel->cnt[1] = sel->pairs = 0u;
+    *done = 0u;
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace fgb

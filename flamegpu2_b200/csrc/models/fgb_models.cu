@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -16,6 +17,12 @@
 #include "../../../examples/circles_model.cuh"
 #include "../../../examples/stress_model.cuh"
 #include "../../../examples/test_models.cuh"
+
+// user functors of the reference's own host-reduction tests (tests/test_cases/runtime/agent/host_reduction/
+// test_transform_reduce.cu:8-13, test_reduce.cu) for fgbm_agent_custom_reduce
+FLAMEGPU_CUSTOM_REDUCTION(fgbm_custom_sum, a, b) { return a + b; }
+FLAMEGPU_CUSTOM_REDUCTION(fgbm_custom_max, a, b) { return a > b ? a : b; }
+FLAMEGPU_CUSTOM_TRANSFORM(fgbm_custom_nonpositive, a) { return a <= 0 ? 1 : 0; }
 
 namespace {
 
@@ -110,6 +117,7 @@ int fgbm_create(const char *model_name, const char *params, int device, void **o
       p.birth_condition = static_cast<int>(getu(kv, "birth_condition", 0));
       p.birth_target = static_cast<int>(getu(kv, "birth_target", 0));
       p.append_optional = static_cast<int>(getu(kv, "append_optional", 0));
+      p.host_init = static_cast<int>(getu(kv, "host_init", 0));
       fgb_examples::define_test_model(*s->model, p);
     } else {
       throw std::runtime_error("unknown model '" + name + "'");
@@ -243,6 +251,31 @@ int fgbm_agent_reduce(void *h, const char *agent, const char *var, int op, char 
   });
 }
 
+// HostAgentAPI::histogramEven (kind 'f' float, 'i' int, 'u' unsigned) into out[bins]
+int fgbm_agent_histogram(void *h, const char *agent, const char *var, char kind, unsigned int bins, double lower, double upper, unsigned int *out) {
+  return guarded([&] {
+    flamegpu::HostAgentAPI api = static_cast<Sim *>(h)->sim->hostAPI().agent(agent);
+    std::vector<unsigned int> r = kind == 'f' ? api.histogramEven<float>(var, bins, static_cast<float>(lower), static_cast<float>(upper))
+                                  : (kind == 'i' ? api.histogramEven<int>(var, bins, static_cast<int>(lower), static_cast<int>(upper))
+                                                 : api.histogramEven<unsigned int>(var, bins, static_cast<unsigned int>(lower), static_cast<unsigned int>(upper)));
+    for (unsigned int b = 0; b < bins; ++b) out[b] = r[b];
+  });
+}
+// HostAgentAPI::reduce / transformReduce with user functors: which 0 = reduce(customSum, 0), 1 = reduce(customMax, lowest),
+// 2 = transformReduce(customTransform "a <= 0 ? 1 : 0", customSum, 0) as in the reference's CustomTransformReduce tests
+int fgbm_agent_custom_reduce(void *h, const char *agent, const char *var, int which, char kind, double *out) {
+  return guarded([&] {
+    flamegpu::HostAgentAPI api = static_cast<Sim *>(h)->sim->hostAPI().agent(agent);
+    auto run = [&](auto tag) -> double {
+      using T = decltype(tag);
+      if (which == 0) return static_cast<double>(api.reduce<T>(var, fgbm_custom_sum, static_cast<T>(0)));
+      if (which == 1) return static_cast<double>(api.reduce<T>(var, fgbm_custom_max, std::numeric_limits<T>::lowest()));
+      return static_cast<double>(api.transformReduce<T, int>(var, fgbm_custom_nonpositive, fgbm_custom_sum, 0));
+    };
+    *out = kind == 'f' ? run(float{}) : (kind == 'i' ? run(int{}) : run(static_cast<unsigned int>(0)));
+  });
+}
+
 // Copy one variable of a state list to host memory (bytes = count * type_len, checked).
 int fgbm_get_variable(void *h, const char *agent, const char *state, const char *var, void *host_out, size_t bytes) {
   return guarded([&] {
@@ -262,6 +295,15 @@ int fgbm_step(void *h, unsigned int steps) {
   return guarded([&] {
     Sim *s = static_cast<Sim *>(h);
     for (unsigned int i = 0; i < steps; ++i) s->sim->step();
+  });
+}
+
+// CUDASimulation::simulate(): init functions, `steps` steps, exit functions
+int fgbm_simulate(void *h, unsigned int steps) {
+  return guarded([&] {
+    Sim *s = static_cast<Sim *>(h);
+    s->sim->SimulationConfig().steps = steps;
+    s->sim->simulate();
   });
 }
 

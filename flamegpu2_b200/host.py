@@ -129,6 +129,31 @@ class Context:
                 _capi.FGB_I64: np.int64, _capi.FGB_U64: np.uint64}[dt]
         return raw.view(view)[0].item()
 
+    # -- CUDAScatter::arrayMessageReorder replacement: out[index[i]] = in[i]; returns nothing, max writes per element -> d_max
+    def array_reorder(self, index, array_length: int, ins, outs, n: int, write_count=None, d_max=None, d_n=None, stream_id: int = 0):
+        arr, nv = make_vars(ins, outs)
+        _check(lib().fgb_array_reorder(self.h, stream_id, _ptr(index), array_length, arr, nv, n, _ptr(d_n), _ptr(write_count), _ptr(d_max),
+                                       _stream_ptr()), "fgb_array_reorder")
+
+    # -- CUDAScatter::scatterNewAgents replacement: n structs of agent_size bytes (device) -> SoA columns at out_offset
+    def scatter_new_agents(self, aos: torch.Tensor, agent_size: int, offsets, lens, outs, n: int, out_offset: int = 0, d_out_offset=None):
+        arr = (_capi.fgb_var * max(len(outs), 1))()
+        for i, (off, ln, o) in enumerate(zip(offsets, lens, outs)):
+            arr[i].type_len = ln
+            arr[i].in_ = aos.data_ptr() + off
+            arr[i].out = o.data_ptr()
+        _check(lib().fgb_scatter_new_agents(self.h, _ptr(aos), agent_size, arr, len(outs), n, out_offset, _ptr(d_out_offset), _stream_ptr()),
+               "fgb_scatter_new_agents")
+
+    def histogram_even(self, inp: torch.Tensor, n: int, bins: int, lower: float, upper: float, *, unsigned=False, d_n=None):
+        dt = self._DTYPES[inp.dtype]
+        if unsigned:
+            dt = {_capi.FGB_I32: _capi.FGB_U32, _capi.FGB_I64: _capi.FGB_U64}[dt]
+        out = torch.zeros(bins, dtype=torch.int32, device=inp.device)
+        _check(lib().fgb_histogram_even(self.h, dt, _ptr(inp), n, _ptr(d_n), bins, float(lower), float(upper), _ptr(out), _stream_ptr()),
+               "fgb_histogram_even")
+        return out
+
     def sort_keys(self, x, y, z, env_min, env_width, grid_dim, n: int, keys_out: torch.Tensor, d_n=None):
         mn = (C.c_float * 3)(*[float(v) for v in (list(env_min) + [0.0] * 3)[:3]])
         w = (C.c_float * 3)(*[float(v) for v in (list(env_width) + [1.0] * 3)[:3]])

@@ -118,8 +118,28 @@ class Simulation:
                "fgbm_agent_reduce")
         return float(out.value)
 
+    def agent_histogram(self, agent: str, var: str, kind: str, bins: int, lower: float, upper: float) -> np.ndarray:
+        """HostAgentAPI::histogramEven of an agent variable (kind: 'f' float, 'i' int, 'u' unsigned int)"""
+        out = np.zeros(bins, np.uint32)
+        lib().fgbm_agent_histogram.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char, C.c_uint, C.c_double, C.c_double, C.c_void_p]
+        _check(lib().fgbm_agent_histogram(self.h, agent.encode(), var.encode(), kind.encode(), bins, lower, upper, out.ctypes.data_as(C.c_void_p)),
+               "fgbm_agent_histogram")
+        return out
+
+    def agent_custom_reduce(self, agent: str, var: str, which: int, kind: str) -> float:
+        """HostAgentAPI::reduce / transformReduce with user functors (0 custom sum, 1 custom max, 2 count of a <= 0)"""
+        out = C.c_double(0.0)
+        lib().fgbm_agent_custom_reduce.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char, C.POINTER(C.c_double)]
+        _check(lib().fgbm_agent_custom_reduce(self.h, agent.encode(), var.encode(), which, kind.encode(), C.byref(out)), "fgbm_agent_custom_reduce")
+        return float(out.value)
+
     def step(self, steps: int = 1):
         _check(lib().fgbm_step(self.h, steps), "fgbm_step")
+
+    def simulate(self, steps: int):
+        """CUDASimulation::simulate(): init functions, `steps` steps, exit functions"""
+        lib().fgbm_simulate.argtypes = [C.c_void_p, C.c_uint]
+        _check(lib().fgbm_simulate(self.h, steps), "fgbm_simulate")
 
     def sync(self):
         _check(lib().fgbm_sync(self.h), "fgbm_sync")

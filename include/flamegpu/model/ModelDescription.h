@@ -38,6 +38,7 @@ struct FLAMEGPUException : public std::runtime_error {
   }
 FGB_DEF_EXC(InvalidVarName);
 FGB_DEF_EXC(InvalidVarType);
+FGB_DEF_EXC(UnsupportedVarType);
 FGB_DEF_EXC(InvalidAgentName);
 FGB_DEF_EXC(InvalidAgentFunc);
 FGB_DEF_EXC(InvalidAgentVar);

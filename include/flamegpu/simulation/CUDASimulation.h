@@ -56,6 +56,63 @@ namespace flamegpu {
 namespace detail {
 
 #if defined(__CUDACC__)
+// HostAgentAPI::reduce / transformReduce with user functors: grid-stride accumulation in thread order, block partials
+// in shared memory folded by thread 0, the last block to arrive folds the partials in block order (reproducible)
+constexpr unsigned int kUserRedBlocks = 592;  // 4 blocks per SM
+template <typename InT, typename OutT, typename Transform, typename Reduce>
+__global__ void __launch_bounds__(256) k_user_transform_reduce(const InT *in, unsigned int bound, const unsigned int *d_n, OutT init, OutT *partial,
+                                                               unsigned int *done, OutT *out) {
+  __shared__ OutT s_val[256];
+  __shared__ unsigned int s_last;
+  unsigned int n = bound;
+  if (d_n) {
+    const unsigned int c = *d_n;
+    n = c < n ? c : n;
+  }
+  Transform tr;
+  Reduce rd;
+  OutT acc = init;
+  bool any = false;
+  for (unsigned int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const OutT v = tr(in[i]);
+    acc = any ? rd(acc, v) : v;
+    any = true;
+  }
+  // fold the threads that saw data, in thread order (init is applied once, at the very end)
+  s_val[threadIdx.x] = acc;
+  __shared__ unsigned char s_any[256];
+  s_any[threadIdx.x] = any ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool have = false;
+    OutT b = init;
+    for (int t = 0; t < 256; ++t)
+      if (s_any[t]) {
+        b = have ? rd(b, s_val[t]) : s_val[t];
+        have = true;
+      }
+    partial[blockIdx.x] = b;
+    reinterpret_cast<unsigned int *>(partial + kUserRedBlocks)[blockIdx.x] = have ? 1u : 0u;
+    __threadfence();
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __threadfence();
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    OutT all = init;
+    const volatile unsigned int *have = reinterpret_cast<const volatile unsigned int *>(partial + kUserRedBlocks);
+    for (unsigned int b = 0; b < gridDim.x; ++b)
+      if (have[b]) {
+        OutT p;
+        const volatile unsigned char *src = reinterpret_cast<const volatile unsigned char *>(partial + b);
+        unsigned char *dst = reinterpret_cast<unsigned char *>(&p);
+        for (unsigned int k = 0; k < sizeof(OutT); ++k) dst[k] = src[k];
+        all = rd(all, p);
+      }
+    *out = all;
+    *done = 0u;
+  }
+}
 // end-of-step bookkeeping on the device: ++step, reset the counts of non-persistent message lists
 // (reference CUDASimulation.cu:619-625 does this on the host)
 __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const unsigned int *zero_slots, unsigned int n_zero,
@@ -252,6 +309,54 @@ struct FunctionRT {
 
 class CUDASimulation;
 
+// Host agent creation (reference include/flamegpu/runtime/agent/HostNewAgentAPI.h): an agent made by a host function lives
+// in a host-side array of structs (defaults pre-filled) until the host function returns; CUDASimulation then uploads the
+// structs and fgb_scatter_new_agents transposes them behind the state list (reference CUDAAgent::scatterHostCreation,
+// CUDAScatter.cu:348-395).
+namespace detail {
+struct HostNewAgents {
+  std::vector<std::string> names;
+  std::vector<Variable> meta;
+  std::vector<size_t> offset;  // of every variable inside one struct
+  size_t agent_size = 0;
+  std::vector<char> defaults;  // one struct holding the default values
+  std::vector<char> data;      // count structs
+  unsigned int count = 0;
+};
+}  // namespace detail
+class HostNewAgentAPI {
+ public:
+  HostNewAgentAPI(detail::HostNewAgents *b, unsigned int i) : buf(b), index(i) {}
+  template <typename T>
+  void setVariable(const std::string &name, T value) {
+    *reinterpret_cast<T *>(slot<T>(name, 1)) = value;
+  }
+  template <typename T, flamegpu::size_type N>
+  void setVariable(const std::string &name, unsigned int i, T value) {
+    if (i >= N) throw exception::OutOfBoundsException("array index out of bounds in HostNewAgentAPI::setVariable()");
+    reinterpret_cast<T *>(slot<T>(name, N))[i] = value;
+  }
+  template <typename T>
+  T getVariable(const std::string &name) const {
+    return *reinterpret_cast<const T *>(const_cast<HostNewAgentAPI *>(this)->slot<T>(name, 1));
+  }
+
+ private:
+  template <typename T>
+  char *slot(const std::string &name, unsigned int elements) {
+    if (name == ID_VARIABLE_NAME) throw exception::ReservedName("agent ids are assigned by the simulation");
+    for (size_t v = 0; v < buf->names.size(); ++v)
+      if (buf->names[v] == name) {
+        if (buf->meta[v].type != std::type_index(typeid(T)) || buf->meta[v].elements != elements)
+          throw exception::InvalidVarType("wrong type for variable '" + name + "' in HostNewAgentAPI");
+        return buf->data.data() + static_cast<size_t>(index) * buf->agent_size + buf->offset[v];
+      }
+    throw exception::InvalidAgentVar("new agent has no variable '" + name + "'");
+  }
+  detail::HostNewAgents *buf;
+  unsigned int index;
+};
+
 // Host-side API handed to init/step/exit functions (subset of the reference's HostAPI).
 // sum / min / max run on the device (fgb_reduce: one kernel, 8 bytes come back) instead of the reference's
 // cub::DeviceReduce + copy (HostAgentAPI.cuh:540-700).
@@ -259,6 +364,7 @@ class HostAgentAPI {
  public:
   HostAgentAPI(CUDASimulation *s, std::string a, std::string st) : sim(s), agent(std::move(a)), state(std::move(st)) {}
   inline unsigned int count();
+  inline HostNewAgentAPI newAgent();  // reference HostAgentAPI.cuh:138-142
   template <typename T>
   inline T sum(const std::string &variable);
   template <typename T>
@@ -270,6 +376,21 @@ class HostAgentAPI {
   inline unsigned int count(const std::string &variable, T value);
   template <typename T>
   inline std::pair<double, double> meanStandardDeviation(const std::string &variable);
+  // reference HostAgentAPI.cuh:241,417,720-760 (cub::DeviceHistogram::HistogramEven): counts of lower <= v < upper in even bins
+  template <typename InT, typename OutT = unsigned int>
+  inline std::vector<OutT> histogramEven(const std::string &variable, unsigned int histogramBins, InT lowerBound, InT upperBound);
+#if defined(__CUDACC__)
+  // reference HostAgentAPI.cuh:255-268,776-850 (thrust::reduce / thrust::transform_reduce with user functors declared by
+  // FLAMEGPU_CUSTOM_REDUCTION / FLAMEGPU_CUSTOM_TRANSFORM): one kernel, block partials folded by the last block in block order
+  template <typename InT, typename reductionOperatorT>
+  inline InT reduce(const std::string &variable, reductionOperatorT reductionOperator, InT init);
+  template <typename InT, typename OutT, typename transformOperatorT, typename reductionOperatorT>
+  inline OutT transformReduce(const std::string &variable, transformOperatorT transformOperator, reductionOperatorT reductionOperator, OutT init);
+  template <typename InT, typename transformOperatorT, typename reductionOperatorT>
+  inline InT transformReduce(const std::string &variable, transformOperatorT t, reductionOperatorT r, InT init) {
+    return transformReduce<InT, InT, transformOperatorT, reductionOperatorT>(variable, t, r, init);
+  }
+#endif
 
  private:
   template <typename T, typename R>
@@ -531,6 +652,11 @@ class CUDASimulation {
     cudaStream_t stream = nullptr;
     cudaEvent_t chunk_done = nullptr;
   } streamed;
+  std::map<std::pair<std::string, std::string>, detail::HostNewAgents> host_new_agents;  // (agent, state) -> agents made by host functions
+  detail::HostNewAgents &host_new_buffer(const std::string &agent_name, const std::string &state);
+  void flush_host_agents();  // uploads + transposes them behind their state lists (after every host function phase)
+  char *d_new_aos = nullptr;
+  size_t new_aos_bytes = 0;
   unsigned int *h_words = nullptr;  // pinned staging for small host -> device control words
   unsigned int soa_uploads = 0;
   cudaStream_t stream_copy = nullptr;        // streamed downloads
@@ -570,6 +696,9 @@ class CUDASimulation {
   std::vector<cudaEvent_t> join_events;
   cudaEvent_t fork_event = nullptr;
   void *d_reduce_out = nullptr;          // 8-byte result word of HostAgentAPI reductions
+  void *d_user_reduce = nullptr;         // block partials + arrival counter of the user-functor reductions
+  unsigned int *d_hist_out = nullptr;    // histogramEven counts
+  unsigned int hist_cap = 0;
   cudaStream_t index_stream = nullptr;   // PBM builds of a layer's input lists (overlapIndexBuild)
   cudaEvent_t index_fork = nullptr, index_done = nullptr;
   bool index_pending = false;
@@ -636,6 +765,30 @@ class CUDASimulation {
 };
 
 }  // namespace flamegpu
+
+// reference include/flamegpu/runtime/agent/HostAgentAPI.cuh:69-79,104-114: user functors for HostAgentAPI::reduce / transformReduce
+#define FLAMEGPU_CUSTOM_REDUCTION(funcName, a, b)                                                              \
+  struct funcName##_impl {                                                                                     \
+   public:                                                                                                     \
+    template <typename OutT>                                                                                   \
+    struct binary_function {                                                                                   \
+      __host__ __device__ __forceinline__ OutT operator()(const OutT &a, const OutT &b) const;                 \
+    };                                                                                                         \
+  };                                                                                                           \
+  funcName##_impl funcName;                                                                                    \
+  template <typename OutT>                                                                                     \
+  __host__ __device__ __forceinline__ OutT funcName##_impl::binary_function<OutT>::operator()(const OutT &a, const OutT &b) const
+#define FLAMEGPU_CUSTOM_TRANSFORM(funcName, a)                                                                 \
+  struct funcName##_impl {                                                                                     \
+   public:                                                                                                     \
+    template <typename InT, typename OutT>                                                                     \
+    struct unary_function {                                                                                    \
+      __host__ __device__ OutT operator()(const InT &a) const;                                                 \
+    };                                                                                                         \
+  };                                                                                                           \
+  funcName##_impl funcName;                                                                                    \
+  template <typename InT, typename OutT>                                                                       \
+  __host__ __device__ __forceinline__ OutT funcName##_impl::unary_function<InT, OutT>::operator()(const InT &a) const
 
 #include "flamegpu/simulation/CUDASimulation_impl.h"
 

@@ -242,6 +242,9 @@ inline void CUDASimulation::destroy() {
   if (stream_chunk_done) cudaEventDestroy(stream_chunk_done);
   stream_copy = nullptr;
   stream_chunk_done = nullptr;
+  if (d_new_aos) cudaFree(d_new_aos);
+  d_new_aos = nullptr;
+  new_aos_bytes = 0;
   if (h_words) cudaFreeHost(h_words);
   h_words = nullptr;
   if (d_env) cudaFree(d_env);
@@ -255,6 +258,11 @@ inline void CUDASimulation::destroy() {
   if (index_stream) cudaStreamDestroy(index_stream);
   if (d_reduce_out) cudaFree(d_reduce_out);
   d_reduce_out = nullptr;
+  if (d_user_reduce) cudaFree(d_user_reduce);
+  d_user_reduce = nullptr;
+  if (d_hist_out) cudaFree(d_hist_out);
+  d_hist_out = nullptr;
+  hist_cap = 0;
   fork_event = index_fork = index_done = nullptr;
   index_stream = nullptr;
   if (main_stream) cudaStreamDestroy(main_stream);
@@ -645,6 +653,7 @@ inline void CUDASimulation::plan_step() {
     }
     for (auto &f : slab_flags) f.reserve(most);
     FGB_ABI_THROW(fgb_ctx_reserve(ctx, kSlabScratchSlot, most, 0));
+    FGB_ABI_THROW(fgb_slab_reserve(ctx, kSlabScratchSlot, std::max(slab.mig_cap, 1u)));
   }
   // reserving may have raised list bounds' capacity only; bounds themselves are untouched
 }
@@ -660,7 +669,20 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
   // 1. automatic spatial sort of the executing agents (reference CUDASimulation.cu:463-573)
   const unsigned int period = f.agent->desc->sort_period;
   // after the auto sort the list is in the sort key's order: grouping inside tiles is enough for step 2b
-  const bool sorted_now = f.sortable && period != 0 && step_count % period == 0 && cuda_config.tileLocalExecOrder;
+  // ... unless the grid is deep along the slowest axis.  The sorted list is in (x,y)-column order (sort_geometry), so the
+  // agents of a 2048-agent tile span EVERY plane of a few columns, and the ~110 tiles in flight (148 SMs) together touch
+  // planes x 9 strips x 3 bins of messages each: at 256 planes that is ~100 MB, the whole L2, and `move` ran 3.5x slower
+  // than at 32 planes (profiles/r02_move_depth.jsonl).  The global bin order keeps the blocks in flight inside ~3 planes.
+  bool tile_local_fits = true;
+  if (f.msg_in && f.msg_in->spatial && !f.msg_in->bucket && f.sort_dims == 3 && !cuda_config.trueSpatialSortKey) {
+    size_t msg_bytes = 0;
+    for (const auto &m : f.msg_in->list.meta) msg_bytes += m.bytes();
+    const double per_bin = L.bound > 0 ? std::max(1.0, static_cast<double>(f.msg_in->list.bound) / std::max(1u, f.msg_in->spatial ? fgb_spatial_bin_count(f.msg_in->spatial) : 1u)) : 1.0;
+    const int planes = f.msg_in->win_count > 0 ? f.msg_in->win_count : static_cast<int>(f.msg_in->md.grid_dim[f.msg_in->desc->dims() - 1]);
+    const double footprint = 110.0 * planes * 27.0 * per_bin * static_cast<double>(msg_bytes);
+    tile_local_fits = footprint < 32.0 * 1024 * 1024;  // a quarter of the 126 MB L2
+  }
+  const bool sorted_now = f.sortable && period != 0 && step_count % period == 0 && cuda_config.tileLocalExecOrder && tile_local_fits;
   if (f.sortable && period != 0 && step_count % period == 0) {
     float mn[3], width[3];
     unsigned int gd[3];
@@ -1065,6 +1087,7 @@ inline void CUDASimulation::record_layers(cudaStream_t main, size_t first, size_
     if (!model->layers[li]->host_functions.empty()) {
       FGB_CUDA_THROW(cudaStreamSynchronize(main));
       for (auto hf : model->layers[li]->host_functions) hf(&host_api);
+      flush_host_agents();
       if (env_dirty) upload_environment();
     }
   }
@@ -1264,7 +1287,7 @@ inline void CUDASimulation::configureSlabs(int rank, int world, const std::strin
   slab.z0 = static_cast<int>((static_cast<long long>(planes) * rank) / world);         // contiguous, as even as possible
   slab.z1 = static_cast<int>((static_cast<long long>(planes) * (rank + 1)) / world);
   slab.halo_cap = halo_capacity;
-  slab.mig_cap = migrate_capacity;
+  slab.mig_cap = std::min(migrate_capacity, 131072u);  // fgb_slab_migrate_out pairs holes in a 262144-bit shared-memory bitmap
   if (slab.enabled) {
     const int w0 = std::max(slab.z0 - 1, 0), w1 = std::min(slab.z1 + 1, planes);  // own planes + one ghost plane per side
     windows[message] = std::make_pair(w0, w1 - w0);
@@ -1356,14 +1379,37 @@ inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plan
   unsigned int *d_err = slot_ptr(slab.err_slot);
   const bool has[2] = {slab.rank > 0, slab.rank < slab.world - 1};
   const unsigned int nv = static_cast<unsigned int>(l.names.size());
-  if (n > 0) {
+  if (n > 0 && !remove) {
     for (auto &f : slab_flags) f.reserve(n);
     FGB_ABI_THROW(fgb_plane_flags(ctx, reinterpret_cast<const float *>(l.data[S.pos_var]), n, d_n, G.md.min[slow], G.md.radius,
-                                  static_cast<int>(G.md.grid_dim[slow]), lo_plane, hi_plane, slab_flags[0].p, remove ? slab_flags[1].p : nullptr,
-                                  slab_flags[2].p, st));
+                                  static_cast<int>(G.md.grid_dim[slow]), lo_plane, hi_plane, slab_flags[0].p, nullptr, slab_flags[2].p, st));
   }
   unsigned long long *peer_flag[2] = {nullptr, nullptr};
-  for (int side = 0; side < 2; ++side) {
+  if (remove) {
+    // migration: only a few agents leave per step, so the list is not rewritten: the leavers are gathered by index into the
+    // neighbours' staging buffers and their holes are filled from the tail (fgb_slab_migrate_out)
+    std::vector<void *> peer_cols[2];
+    unsigned int *peer_count[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side) {
+      if (!has[side]) continue;
+      char *base = slab.peer[slab.rank + (side == 0 ? -1 : 1)];
+      const SlabStaging &g = S.st[side == 0 ? 1 : 0];
+      for (unsigned int v = 0; v < nv; ++v) peer_cols[side].push_back(base + g.var_off[v]);
+      peer_count[side] = reinterpret_cast<unsigned int *>(base + g.count_off);
+      peer_flag[side] = reinterpret_cast<unsigned long long *>(base + g.flag_off);
+    }
+    std::vector<fgb_var> cols(nv);
+    for (unsigned int v = 0; v < nv; ++v) {
+      cols[v].type_len = l.meta[v].bytes();
+      cols[v].in = l.data[v];
+      cols[v].out = l.data[v];
+    }
+    FGB_ABI_THROW(fgb_slab_migrate_out(ctx, kSlabScratchSlot, reinterpret_cast<const float *>(l.data[S.pos_var]), n, d_n, G.md.min[slow], G.md.radius,
+                                       static_cast<int>(G.md.grid_dim[slow]), lo_plane, hi_plane, S.capacity, cols.data(), nv,
+                                       has[0] ? peer_cols[0].data() : nullptr, has[1] ? peer_cols[1].data() : nullptr, peer_count[0], peer_count[1],
+                                       d_n, d_err, st));
+  }
+  for (int side = 0; side < 2 && !remove; ++side) {
     if (!has[side]) continue;
     // I am the neighbour's OTHER side: what I send down arrives in rank-1's "from rank+1" buffer and vice versa
     char *base = slab.peer[slab.rank + (side == 0 ? -1 : 1)];
@@ -1377,11 +1423,6 @@ inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plan
     FGB_ABI_THROW(fgb_compact_limited(ctx, kSlabScratchSlot, slab_flags[side == 0 ? 0 : 2].p, 0, n, d_n, 0, 0, nullptr, S.capacity, vars.data(), nv,
                                       reinterpret_cast<unsigned int *>(base + g.count_off), nullptr, st));
     peer_flag[side] = reinterpret_cast<unsigned long long *>(base + g.flag_off);
-  }
-  if (remove && n > 0) {
-    std::vector<fgb_var> vars = l.vars(true);
-    FGB_ABI_THROW(fgb_compact(ctx, kSlabScratchSlot, slab_flags[1].p, 0, n, d_n, 0, 0, nullptr, vars.data(), nv, nullptr, d_n, st));
-    l.swap_buffers();
   }
   FGB_ABI_THROW(fgb_slab_signal(ctx, peer_flag[0], peer_flag[1], d_epoch, st));
   const SlabStaging &from_lo = S.st[0], &from_hi = S.st[1];
@@ -1524,6 +1565,7 @@ inline bool CUDASimulation::step() {
     // per-step timer); their reductions are launched on the step's stream
     FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
     for (auto sf : model->step_functions) sf(&host_api);
+    flush_host_agents();
   }
   if (config.timing) {
     FGB_CUDA_THROW(cudaEventRecord(e1, main_stream));
@@ -1534,6 +1576,16 @@ inline bool CUDASimulation::step() {
   for (auto ec : model->exit_conditions) {
     FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
     if (ec(&host_api)) go_on = false;
+  }
+  if (!model->exit_conditions.empty()) {
+    if (go_on) {
+      flush_host_agents();
+    } else {  // reference test_host_agent_creation.cu:24-29: agents made alongside an EXIT verdict are not created
+      for (auto &kv : host_new_agents) {
+        kv.second.count = 0;
+        kv.second.data.clear();
+      }
+    }
   }
   return go_on;
 }
@@ -1576,6 +1628,7 @@ inline void CUDASimulation::simulate() {
   initialise();
   const auto t0 = std::chrono::steady_clock::now();
   for (auto f : model->init_functions) f(&host_api);
+  flush_host_agents();
   for (unsigned int i = 0; config.steps == 0 || i < config.steps; ++i)
     if (!step()) break;
   FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
@@ -1611,6 +1664,77 @@ inline std::map<std::string, std::pair<double, unsigned int>> CUDASimulation::ge
   }
   prof.clear();
   return out;
+}
+
+// ---- host agent creation ---------------------------------------------------------------------
+inline detail::HostNewAgents &CUDASimulation::host_new_buffer(const std::string &agent_name, const std::string &state) {
+  initialise();
+  auto key = std::make_pair(agent_name, state);
+  auto it = host_new_agents.find(key);
+  if (it != host_new_agents.end()) return it->second;
+  detail::DevList &l = state_list(agent_name, state);
+  detail::HostNewAgents b;
+  size_t off = 0;
+  for (size_t v = 0; v < l.names.size(); ++v) {
+    const size_t bytes = l.meta[v].bytes();
+    const size_t align = std::min<size_t>(16, bytes & (~bytes + 1));  // largest power of two dividing the size, at most 16
+    off = (off + align - 1) / align * align;
+    b.names.push_back(l.names[v]);
+    b.meta.push_back(l.meta[v]);
+    b.offset.push_back(off);
+    off += bytes;
+  }
+  b.agent_size = (off + 15) & ~static_cast<size_t>(15);
+  b.defaults.assign(b.agent_size, 0);
+  for (size_t v = 0; v < b.names.size(); ++v)
+    if (!b.meta[v].default_value.empty()) std::memcpy(b.defaults.data() + b.offset[v], b.meta[v].default_value.data(), b.meta[v].bytes());
+  return host_new_agents.emplace(key, std::move(b)).first->second;
+}
+
+inline void CUDASimulation::flush_host_agents() {
+  for (auto &kv : host_new_agents) {
+    detail::HostNewAgents &b = kv.second;
+    if (b.count == 0) continue;
+    detail::CUDAAgent &a = agent_rt(kv.first.first);
+    detail::DevList &l = state_list(kv.first.first, kv.first.second);
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    // ids: the next free ones of the agent type (device counter: device births may have advanced it)
+    id_t next = read_slot(a.next_id_slot);
+    const int iv = l.index_of(ID_VARIABLE_NAME);
+    for (unsigned int i = 0; i < b.count; ++i) *reinterpret_cast<id_t *>(b.data.data() + static_cast<size_t>(i) * b.agent_size + b.offset[iv]) = next++;
+    a.host_next_id = next;
+    write_slot(a.next_id_slot, next);
+    const unsigned int have = read_slot(l.count_slot);
+    l.reserve(have + b.count, have);
+    const size_t bytes = static_cast<size_t>(b.count) * b.agent_size;
+    if (bytes > new_aos_bytes) {
+      if (d_new_aos) cudaFree(d_new_aos);
+      FGB_CUDA_THROW(cudaMalloc(&d_new_aos, bytes + bytes / 2));
+      new_aos_bytes = bytes + bytes / 2;
+    }
+    FGB_CUDA_THROW(cudaMemcpyAsync(d_new_aos, b.data.data(), bytes, cudaMemcpyHostToDevice, main_stream));
+    std::vector<fgb_var> vars(l.names.size());
+    for (size_t v = 0; v < vars.size(); ++v) {
+      vars[v].type_len = l.meta[v].bytes();
+      vars[v].in = d_new_aos + b.offset[v];
+      vars[v].out = l.data[v];
+    }
+    FGB_ABI_THROW(fgb_scatter_new_agents(ctx, d_new_aos, static_cast<unsigned int>(b.agent_size), vars.data(), static_cast<unsigned int>(vars.size()),
+                                         b.count, have, nullptr, main_stream));
+    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));  // host creation is not a hot path: the staging vector is reused below
+    write_slot(l.count_slot, have + b.count);
+    l.bound = std::max(l.bound, model_has_births ? quantise(have + b.count) : have + b.count);
+    l.touch();
+    a.recompute_pop_bound();
+    b.count = 0;
+    b.data.clear();
+  }
+}
+
+inline HostNewAgentAPI HostAgentAPI::newAgent() {
+  detail::HostNewAgents &b = sim->host_new_buffer(agent, state);
+  b.data.insert(b.data.end(), b.defaults.begin(), b.defaults.end());
+  return HostNewAgentAPI(&b, b.count++);
 }
 
 // ---- minimal HostAPI -------------------------------------------------------------------------
@@ -1681,6 +1805,75 @@ inline std::pair<double, double> HostAgentAPI::meanStandardDeviation(const std::
   const double ss = transform_reduce<T, double>(variable, FGB_TRANSFORM_SUM_SQ_DEV, &mean);
   return std::make_pair(mean, std::sqrt(ss / static_cast<double>(n)));
 }
+template <typename InT, typename OutT>
+inline std::vector<OutT> HostAgentAPI::histogramEven(const std::string &variable, unsigned int histogramBins, InT lowerBound, InT upperBound) {
+  sim->initialise();
+  if (!(lowerBound < upperBound)) throw exception::InvalidArgument("lowerBound must be lower than upperBound in HostAgentAPI::histogramEven()");
+  if (sim->slab.enabled) throw exception::UnsupportedFeature("histogramEven under a slab decomposition");
+  detail::DevList &l = sim->state_list(agent, state);
+  const int i = l.index_of(variable);
+  if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
+  if (l.meta[i].elements != 1) throw exception::UnsupportedVarType("HostAgentAPI::histogramEven() does not support agent array variables");
+  if (l.meta[i].type != std::type_index(typeid(InT))) throw exception::InvalidVarType("wrong type for '" + variable + "'");
+  if (histogramBins > sim->hist_cap) {
+    if (sim->d_hist_out) cudaFree(sim->d_hist_out);
+    FGB_CUDA_THROW(cudaMalloc(&sim->d_hist_out, static_cast<size_t>(histogramBins) * 4));
+    sim->hist_cap = histogramBins;
+  }
+  FGB_ABI_THROW(fgb_histogram_even(sim->ctx, detail::reduce_dtype<InT>::value, l.data[i], l.bound, sim->slot_ptr(l.count_slot), histogramBins,
+                                   static_cast<double>(lowerBound), static_cast<double>(upperBound), sim->d_hist_out, sim->main_stream));
+  std::vector<unsigned int> h(histogramBins);
+  FGB_CUDA_THROW(cudaMemcpyAsync(h.data(), sim->d_hist_out, static_cast<size_t>(histogramBins) * 4, cudaMemcpyDeviceToHost, sim->main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
+  return std::vector<OutT>(h.begin(), h.end());
+}
+#if defined(__CUDACC__)
+namespace detail {
+template <typename InT>
+struct identity_transform {  // reduce() == transformReduce() with the identity
+  template <typename A, typename B>
+  struct unary_function {
+    __host__ __device__ B operator()(const A &a) const { return static_cast<B>(a); }
+  };
+};
+}  // namespace detail
+template <typename InT, typename OutT, typename transformOperatorT, typename reductionOperatorT>
+inline OutT HostAgentAPI::transformReduce(const std::string &variable, transformOperatorT, reductionOperatorT, OutT init) {
+  static_assert(sizeof(OutT) <= 8, "reduction results are at most 8 bytes");
+  sim->initialise();
+  if (sim->slab.enabled) throw exception::UnsupportedFeature("user-functor reductions under a slab decomposition");
+  detail::DevList &l = sim->state_list(agent, state);
+  const int i = l.index_of(variable);
+  if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
+  if (l.meta[i].elements != 1) throw exception::UnsupportedVarType("HostAgentAPI::transformReduce() does not support agent array variables");
+  if (l.meta[i].type != std::type_index(typeid(InT))) throw exception::InvalidVarType("wrong type for '" + variable + "'");
+  if (!sim->d_user_reduce) {
+    const size_t bytes = static_cast<size_t>(detail::kUserRedBlocks) * 8 + static_cast<size_t>(detail::kUserRedBlocks) * 4 + 16;
+    FGB_CUDA_THROW(cudaMalloc(&sim->d_user_reduce, bytes));
+    FGB_CUDA_THROW(cudaMemset(sim->d_user_reduce, 0, bytes));
+  }
+  OutT *partial = static_cast<OutT *>(sim->d_user_reduce);
+  // layout: kUserRedBlocks partials of sizeof(OutT) <= 8 bytes, kUserRedBlocks "has data" words right behind the partials
+  // (as the kernel addresses them), the arrival counter at the very end
+  unsigned int *done = reinterpret_cast<unsigned int *>(static_cast<char *>(sim->d_user_reduce) + static_cast<size_t>(detail::kUserRedBlocks) * 12 + 8);
+  unsigned int blocks = (l.bound + 2047u) / 2048u;
+  blocks = std::max(1u, std::min(blocks, detail::kUserRedBlocks));
+  using Tr = typename transformOperatorT::template unary_function<InT, OutT>;
+  using Rd = typename reductionOperatorT::template binary_function<OutT>;
+  detail::k_user_transform_reduce<InT, OutT, Tr, Rd><<<blocks, 256, 0, sim->main_stream>>>(
+      reinterpret_cast<const InT *>(l.data[i]), l.bound, sim->slot_ptr(l.count_slot), init, partial, done, static_cast<OutT *>(sim->d_reduce_out));
+  FGB_CUDA_THROW(cudaPeekAtLastError());
+  ++sim->own_launches;
+  OutT r{};
+  FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(OutT), cudaMemcpyDeviceToHost, sim->main_stream));
+  FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
+  return r;
+}
+template <typename InT, typename reductionOperatorT>
+inline InT HostAgentAPI::reduce(const std::string &variable, reductionOperatorT r, InT init) {
+  return transformReduce<InT, InT, detail::identity_transform<InT>, reductionOperatorT>(variable, detail::identity_transform<InT>(), r, init);
+}
+#endif
 template <typename T>
 inline T HostAgentAPI::sum(const std::string &variable) {
   return static_cast<T>(reduce<T, typename detail::reduce_dtype<T>::sum_t>(variable, FGB_REDUCE_SUM));

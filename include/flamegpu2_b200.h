@@ -115,6 +115,7 @@ fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata 
 /* MessageSpecialisationHandler::getMetaDataDevicePtr
  * (include/flamegpu/runtime/messaging/MessageSpecialisationHandler.h:44) */
 const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp);
+unsigned int fgb_spatial_bin_count(const fgb_spatial *sp);  /* bins of the (windowed) PBM */
 
 /* Inspection helper (no reference counterpart: "The PBM is never stored on the host",
  * MessageSpatial3D.h:55-58): copies the bin_count+1 PBM entries to host memory after
@@ -282,6 +283,27 @@ fgb_status fgb_sort_spatial(fgb_ctx *ctx, unsigned int stream_id, const float *x
 fgb_status fgb_ctx_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int n_max, int max_bit);
 fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max);
 
+/* ---- the remaining CUDAScatter kernels and the histogram behind HostAgentAPI::histogramEven ------------- */
+/* CUDAScatter::arrayMessageReorder + reorder_array_messages (CUDAScatter.cu:540-655): array messages (MessageArray /
+ * MessageArray2D / MessageArray3D) are written at the sender's thread index together with their target element
+ * (`index`, the "___INDEX" variable); this moves every variable to out[index[i]].  An index >= array_length is dropped
+ * (:553-554); n > array_length is an error (:579-581, FGB_ERR_INVALID_ARG).  d_write_count (array_length words, all-zero
+ * on entry, re-zeroed by the call; may be NULL) counts the writes per element; d_max_writes (may be NULL) receives their
+ * maximum -- > 1 is the reference's ArrayMessageWriteConflict (:629-651), left to the caller to raise, so nothing here
+ * synchronises. */
+fgb_status fgb_array_reorder(fgb_ctx *ctx, unsigned int stream_id, const unsigned int *index, unsigned int array_length, const fgb_var *vars,
+                             unsigned int nvars, unsigned int n, const unsigned int *d_n, unsigned int *d_write_count,
+                             unsigned int *d_max_writes, void *stream);
+/* CUDAScatter::scatterNewAgents + scatter_new_agents (CUDAScatter.cu:348-395): host-created agents arrive as `n` structs
+ * of `agent_size` bytes at d_aos (device memory); vars[v].in points at variable v inside the FIRST struct, vars[v].out is
+ * the state list's SoA column; agent i lands at out[out_offset + i] (offset optionally from a device word). */
+fgb_status fgb_scatter_new_agents(fgb_ctx *ctx, const void *d_aos, unsigned int agent_size, const fgb_var *vars, unsigned int nvars,
+                                  unsigned int n, unsigned int out_offset, const unsigned int *d_out_offset, void *stream);
+/* cub::DeviceHistogram::HistogramEven as HostAgentAPI::histogramEven calls it (include/flamegpu/runtime/agent/HostAgentAPI.cuh:
+ * 720-745): d_counts[b] (bins words, overwritten) = number of items with lower <= v < upper in even bin b. */
+fgb_status fgb_histogram_even(fgb_ctx *ctx, int dtype, const void *in, unsigned int n, const unsigned int *d_n, unsigned int bins,
+                              double lower, double upper, unsigned int *d_counts, void *stream);
+
 /* ---- multi-GPU z-slab exchange (b200 extension; the reference has no multi-GPU simulation) -----------
  * One process per GPU.  Halo messages / migrating agents are packed by fgb_compact_limited straight into the
  * NEIGHBOUR's staging buffer (peer memory mapped with cudaIpcOpenMemHandle: vars[v].out and d_out_count are peer
@@ -296,8 +318,21 @@ fgb_status fgb_spatial_reserve(fgb_spatial *sp, unsigned int n_max);
  *   fgb_slab_allreduce   : all-reduce (op: fgb_reduce_op, dtype: fgb_dtype of the 4/8-byte value) over per-rank
  *                     mailboxes (mailboxes[r] = rank r's array of 2 * world 16-byte slots, peer memory for r != rank);
  *                     folded in rank order, so every rank obtains the identical value; `epoch` must increase by one
- *                     per call on every rank */
+ *                     per call on every rank
+ *   fgb_slab_migrate_out : removes the items of a list whose position `pos` lies in planes < lo_plane / >= hi_plane
+ *                     (plane arithmetic of fgb_plane_flags) and writes them -- and their counts -- into the neighbours'
+ *                     staging columns peer_lo[v] / peer_hi[v] (peer memory; NULL = no neighbour on that side).  Only the
+ *                     position column is read in full: the few leavers are gathered by index, the holes they leave are
+ *                     filled with agents from the tail of the list (list_vars[v].in is the column, .out is ignored), and
+ *                     *d_n_inout becomes the new count.  More than `capacity` leavers on a side (2 * capacity must not
+ *                     exceed 262144) raise FGB_SLAB_ERR_OVERFLOW here and on the receiver. */
 enum { FGB_SLAB_ERR_TIMEOUT = 1, FGB_SLAB_ERR_OVERFLOW = 2, FGB_SLAB_ERR_BOUND = 4 };
+/* scratch of fgb_slab_migrate_out for staging buffers of `capacity` items (call outside stream capture) */
+fgb_status fgb_slab_reserve(fgb_ctx *ctx, unsigned int stream_id, unsigned int capacity);
+fgb_status fgb_slab_migrate_out(fgb_ctx *ctx, unsigned int stream_id, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                                float radius, int grid_dim, int lo_plane, int hi_plane, unsigned int capacity, const fgb_var *list_vars,
+                                unsigned int nvars, void *const *peer_lo, void *const *peer_hi, unsigned int *peer_count_lo,
+                                unsigned int *peer_count_hi, unsigned int *d_n_inout, unsigned int *d_err, void *stream);
 fgb_status fgb_slab_signal(fgb_ctx *ctx, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, const unsigned int *d_epoch,
                            void *stream);
 fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const unsigned long long *flag_hi, const unsigned int *count_lo,

@@ -238,6 +238,7 @@ int main(int argc, const char **argv) {
       p.birth_condition = static_cast<int>(getu(kv, "birth_condition", 0));
       p.birth_target = static_cast<int>(getu(kv, "birth_target", 0));
       p.append_optional = static_cast<int>(getu(kv, "append_optional", 0));
+      p.host_init = static_cast<int>(getu(kv, "host_init", 0));
       msg_dims = (p.which == fgb_examples::TM_COUNT2D || p.which == fgb_examples::TM_WRAP2D) ? 2 : 3;
       if (p.which >= fgb_examples::TM_BUCKET && p.which <= fgb_examples::TM_BUCKET_RANGE) msg_dims = 0;
       fgb_examples::define_test_model(model, p);

@@ -8,8 +8,8 @@ seeded state (both sides start from identical agents, so nothing is amplified by
     (SURVEY.md 8e), and every rank's ghost planes hold exactly the neighbours' boundary planes;
   * every PBM bin of an owned plane holds the same message ids as the single-GPU list (as a multiset);
   * after migration every agent sits on the rank that owns its plane, no id is lost or duplicated;
-  * ids and integer state (_auto_sort_bin_index) are bit-exact per agent, the agents that stayed on their rank keep
-    the single-GPU list order, floats agree within rtol 1e-5 / atol 2e-6 (summation order over ~33 neighbours).
+  * ids and integer state (_auto_sort_bin_index) are bit-exact per agent, floats agree within rtol 1e-5 / atol 2e-6
+    (summation order over ~33 neighbours).
 A free-running multi-step variant (SLAB_STEPS > 1) is kept as a smoke test of sustained migration with loose tolerances."""
 import os
 import sys
@@ -136,8 +136,8 @@ def run_check(rank, world, local, n_per_rank=100_000, planes_per_rank=23, radius
                 fails.append("per-bin message ids differ")
             if not ints_ok:
                 fails.append("_auto_sort_bin_index differs")
-            if not order_ok:
-                fails.append("list order of the agents that stayed differs from the single-GPU order")
+            # (the agents that stay keep their relative order except for the few tail agents that fill the holes of the
+            #  leavers -- fgb_slab_migrate_out -- so `stayers_keep_list_order` is reported, not required)
         elif not fails:
             # free-running: summation-order differences are amplified by the dynamics; almost all agents must agree
             pos_in_ref = np.empty(n + 1, np.int64)

@@ -402,3 +402,74 @@ def test_agent_sort_2d_and_many_ties(ctx):
     out = torch.zeros(n, dtype=torch.int32, device=DEV)
     ctx.sort_by_key(keys, mb, [t(order)], [out], n)   # ~780 agents per bin: big-bin fix-up path
     assert np.array_equal(as_u32(out), orc.sort_perm(keys_ref, mb))
+
+
+# ---- the remaining CUDAScatter kernels ------------------------------------------------------------
+@pytest.mark.parametrize("n,length", [(1, 1), (1000, 1000), (70001, 100000), (300000, 300000)])
+def test_array_message_reorder(ctx, n, length):
+    """reorder_array_messages (CUDAScatter.cu:540-566): out[index[i]] = in[i]; unique indices -> max writes 1"""
+    rng = np.random.default_rng(n)
+    index = rng.permutation(length)[:n].astype(np.int32)
+    v4 = rng.integers(0, 2**31, n).astype(np.int32)
+    v12 = rng.integers(0, 2**31, (n, 3)).astype(np.int32)
+    ins = [torch.from_numpy(a).to(DEV) for a in (v4, v12)]
+    outs = [torch.full((length,), -1, dtype=torch.int32, device=DEV), torch.full((length, 3), -1, dtype=torch.int32, device=DEV)]
+    wc = torch.zeros(length, dtype=torch.int32, device=DEV)
+    mx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ctx.array_reorder(torch.from_numpy(index).to(DEV), length, ins, outs, n, write_count=wc, d_max=mx)
+    exp4 = np.full(length, -1, np.int32)
+    exp12 = np.full((length, 3), -1, np.int32)
+    exp4[index] = v4
+    exp12[index] = v12
+    assert np.array_equal(outs[0].cpu().numpy(), exp4) and np.array_equal(outs[1].cpu().numpy(), exp12)
+    assert int(mx.item()) == 1 and int(wc.sum().item()) == 0, "write counters are folded to their maximum and re-zeroed"
+
+
+def test_array_message_reorder_conflict_and_out_of_bounds(ctx):
+    """two messages for one element -> max writes 2 (the reference raises ArrayMessageWriteConflict, CUDAScatter.cu:629-651);
+    an index beyond the array is dropped (:553-554); more messages than elements is rejected (:579-581)"""
+    index = torch.tensor([0, 5, 5, 9, 12], dtype=torch.int32, device=DEV)
+    val = torch.arange(5, dtype=torch.int32, device=DEV)
+    out = torch.full((10,), -1, dtype=torch.int32, device=DEV)
+    wc = torch.zeros(10, dtype=torch.int32, device=DEV)
+    mx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ctx.array_reorder(index, 10, [val], [out], 5, write_count=wc, d_max=mx)
+    o = out.cpu().numpy()
+    assert int(mx.item()) == 2 and o[0] == 0 and o[9] == 3 and o[5] in (1, 2) and (o[[1, 2, 3, 4, 6, 7, 8]] == -1).all()
+    with pytest.raises(Exception):
+        ctx.array_reorder(index, 4, [val], [out], 5)
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 1000, 100003])
+def test_scatter_new_agents_aos_to_soa(ctx, n):
+    """scatter_new_agents (CUDAScatter.cu:348-366): structs {f32 x; u32 id; i32 arr[3]; u8 flag; pad} appended after 7 agents"""
+    agent_size = 24
+    rng = np.random.default_rng(n)
+    raw = rng.integers(0, 256, (n, agent_size)).astype(np.uint8)
+    aos = torch.from_numpy(raw).to(DEV)
+    offsets, lens = [0, 4, 8, 20], [4, 4, 12, 1]
+    outs = [torch.zeros(n + 7, dtype=torch.int32, device=DEV), torch.zeros(n + 7, dtype=torch.int32, device=DEV),
+            torch.zeros((n + 7, 3), dtype=torch.int32, device=DEV), torch.zeros(n + 7, dtype=torch.uint8, device=DEV)]
+    off = torch.tensor([7], dtype=torch.int32, device=DEV)
+    ctx.scatter_new_agents(aos, agent_size, offsets, lens, outs, n, d_out_offset=off)
+    for o, ofs, ln in zip(outs, offsets, lens):
+        got = o.cpu().numpy().view(np.uint8).reshape(n + 7, ln)
+        assert not got[:7].any(), "existing agents are untouched"
+        assert np.array_equal(got[7:], raw[:, ofs:ofs + ln])
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 2000003])
+def test_histogram_even(ctx, n):
+    """cub::DeviceHistogram::HistogramEven semantics as HostAgentAPI::histogramEven uses them (test_histogram_even.cu:50-64)"""
+    rng = np.random.default_rng(n + 1)
+    f = rng.uniform(-2, 22, n).astype(np.float32)
+    h = ctx.histogram_even(torch.from_numpy(f).to(DEV), n, 10, 0.0, 20.0).cpu().numpy()
+    inside = f[(f >= 0) & (f < 20)]
+    exp = np.bincount(((inside - np.float32(0)) * (np.float32(10) / np.float32(20))).astype(np.int32), minlength=10)[:10]
+    assert np.array_equal(h, exp)
+    i = rng.integers(-5, 30, n).astype(np.int32)
+    h = ctx.histogram_even(torch.from_numpy(i).to(DEV), n, 10, 0, 20).cpu().numpy()
+    inside = i[(i >= 0) & (i < 20)]
+    assert np.array_equal(h, np.bincount(inside * 10 // 20, minlength=10)[:10])
+    hb = ctx.histogram_even(torch.from_numpy(i).to(DEV), n, 5000, -5, 30).cpu().numpy()  # more bins than the shared-memory path holds
+    assert hb.sum() == n

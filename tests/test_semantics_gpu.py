@@ -1,6 +1,6 @@
 """Restatements of the reference's own tests for list lifecycle and scheduling semantics, run on this repo's CUDA
 path and, where oracle/_ref/ref_sim is present, on the reference's own CUDA build from the same inputs:
-  * message append vs truncate        tests/test_cases/runtime/messaging/test_append_truncate.cu:106-330
+  * message append vs truncate        tests/test_cases/runtime/messaging/test_append_truncate.cu:106-309
   * device agent creation, 20 combos  tests/test_cases/runtime/agent/test_device_agent_creation.cu:53-1107
   * unique ids across states          tests/test_cases/runtime/agent/test_device_agent_creation.cu:1196-1296
   * state transitions                 tests/test_cases/runtime/agent/detail/test_agent_state_transition.cu:67-257
@@ -270,3 +270,37 @@ def test_concurrent_spatial_layers(tmp_path, graphs):
             ref = fgbs.read_state(str(tmp_path / f"ref.agent_{i}.bin"))
             for v in ("_id", "count", "badCount", "idsum"):
                 assert np.array_equal(ours[i][v], ref[v]), (i, v)
+
+
+# ---- host agent creation (scatter_new_agents) -----------------------------------------------------
+@pytest.mark.parametrize("host_init", [1, 0])
+def test_host_agent_creation_from_init_and_step(host_init):
+    """HostAgentCreationTest.FromInit / FromStep (tests/test_cases/runtime/agent/test_host_agent_creation.cu:56-130): 512 agents made
+    by a host function join 512 uploaded ones; values set on the host arrive, untouched variables hold their defaults, ids are unique"""
+    n = 512
+    s = _sim("test", which=23, host_init=host_init)
+    s.set_population("agent", {"x": np.full(n, 12.0, np.float32)})
+    s.simulate(1)
+    x = s.get("agent", "x", np.float32)
+    assert len(x) == 2 * n and (x == 12.0).sum() == n and (x == 1.0).sum() == n
+    assert np.array_equal(x[:n], np.full(n, 12.0, np.float32)), "host-made agents are appended behind the existing ones"
+    assert np.all(s.get("agent", "default", np.float32) == 15.0)
+    ids = s.get("agent", "_id", np.uint32)
+    assert len(np.unique(ids)) == 2 * n and np.all(ids != 0)
+    s.close()
+
+
+def test_host_agent_creation_multi_agent_and_state():
+    """HostAgentCreationTest.FromStepMultiAgent (test_host_agent_creation.cu:36-43): a step function creates agents of two
+    types, one of them into a non-initial state, over two steps"""
+    n = 300
+    s = _sim("test", which=23, host_init=2)
+    s.set_population("agent", {"x": np.full(n, 12.0, np.float32)}, state="a")
+    s.simulate(2)
+    assert s.count("agent", "a") == n
+    xb = s.get("agent", "x", np.float32, state="b")
+    y2 = s.get("agent2", "y", np.float32)
+    assert len(xb) == 1024 and np.all(xb == 1.0) and len(y2) == 1024 and np.all(y2 == 2.0)
+    ids = np.concatenate([s.get("agent", "_id", np.uint32, state="a"), s.get("agent", "_id", np.uint32, state="b")])
+    assert len(np.unique(ids)) == n + 1024
+    s.close()

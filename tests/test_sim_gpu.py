@@ -537,3 +537,19 @@ def test_function_condition_with_death_same_state():
     s.step(1)
     assert s.count("agent") > 0
     s.close()
+
+
+def test_host_agent_histogram_and_custom_reductions():
+    """HostAgentAPI::histogramEven / reduce / transformReduce with user functors (SURVEY.md 8f.3; reference
+    tests/test_cases/runtime/agent/host_reduction/test_histogram_even.cu, test_reduce.cu, test_transform_reduce.cu)"""
+    n = 50000
+    rng = np.random.default_rng(4)
+    x = rng.integers(-100, 100, n).astype(np.int32)
+    s = _sim("test", which=11)  # agent with one int variable "x"
+    s.set_population("agent", {"x": x})
+    h = s.agent_histogram("agent", "x", "i", 10, -100, 100)
+    assert np.array_equal(h, np.bincount((x.astype(np.int64) + 100) * 10 // 200, minlength=10))
+    assert s.agent_custom_reduce("agent", "x", 0, "i") == float(x.sum())
+    assert s.agent_custom_reduce("agent", "x", 1, "i") == float(x.max())
+    assert s.agent_custom_reduce("agent", "x", 2, "i") == float((x <= 0).sum())
+    s.close()
