@@ -102,6 +102,24 @@ int launch_bin_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, co
   return launch_ok();
 }
 
+// scan + scatter of the stored keys in one launch, then the (normally empty) worklist of ungrouped tiles
+static_assert(kFsTile == kScanTile, "k_scan_scatter and scan_num_tiles() must agree on the scan tile size");
+template <bool IDX_ONLY>
+void launch_scan_scatter(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const VarTable &vt, unsigned int *perm, bool vec,
+                         cudaStream_t st) {
+  const unsigned int tiles = tile_grid(n), scan_tiles = scan_num_tiles(sp->bin_count);
+  const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
+  uint32_t *wl = static_cast<uint32_t *>(sp->tile_mode.p);
+  k_scan_scatter<IDX_ONLY><<<scan_tiles + tiles, kBinThreads, 0, st>>>(sp->d_hist, sp->md.PBM, sp->bin_count, sp->d_state, scan_tiles, keys, n,
+                                                                       d_n, vt, perm, wl, sp->d_ctrl);
+  const unsigned int sgrid = std::min<unsigned int>(tiles, 2u * kNumSMs);
+  if (vec)
+    k_bin_scatter_staged<true, IDX_ONLY><<<sgrid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, wl, sp->d_ctrl);
+  else
+    k_bin_scatter_staged<false, IDX_ONLY><<<sgrid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, wl, sp->d_ctrl);
+  sp->ctx->launches += 2;
+}
+
 // scan + scatter from the stored keys (sp->keys, sp->d_hist complete for [0, n))
 int scatter_from_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const fgb_var *vars, unsigned int nvars, unsigned int flags,
                       unsigned int *src_slot_out, cudaStream_t st) {
@@ -110,27 +128,14 @@ int scatter_from_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, 
   int r = make_var_table(vars, nvars, &vt);
   if (r) return r;
   const bool vec = vars_in_aligned(vars, nvars);
-  const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
   const bool stable = (flags & FGB_BUILD_STABLE) != 0;
-  const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
-  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
   uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
-  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
   if (!stable) {
-    if (vec) {
-      k_bin_scatter_direct<false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state, sp->d_ctrl);
-      k_bin_scatter_staged<true, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
-    } else {
-      k_bin_scatter_direct<false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm, sp->d_state, sp->n_state, sp->d_ctrl);
-      k_bin_scatter_staged<false, false><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, src_slot_out, tm);
-    }
-    ctx->launches += 3;
+    launch_scan_scatter<false>(sp, n, d_n, vt, src_slot_out, vec, st);
     return launch_ok();
   }
-  k_bin_scatter_direct<true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm, sp->d_state, sp->n_state, sp->d_ctrl);
-  k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, tm);
-  ctx->launches += 3;
+  launch_scan_scatter<true>(sp, n, d_n, vt, perm, true, st);
   r = stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, vars, nvars, st);
   if (r == 0 && src_slot_out) r = static_cast<int>(cudaMemcpyAsync(src_slot_out, perm, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, st));
   return r;
@@ -191,16 +196,10 @@ int bin_permutation_impl(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   if (r) return r;
   r = launch_bin_keys<DIMS>(sp, n, d_n, nullptr, x, y, z, st);
   if (r) return r;
-  const unsigned int grid = tile_grid(n);
   const unsigned int B = sp->bin_count;
-  const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
-  uint32_t *tm = static_cast<uint32_t *>(sp->tile_mode.p);
   VarTable none{};
   none.n = 0;
-  k_exclusive_scan<true><<<scan_num_tiles(B), kScanThreads, 0, st>>>(sp->d_hist, sp->md.PBM, B, sp->d_state, 1, 1);
-  k_bin_scatter_direct<true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm, sp->d_state, sp->n_state, sp->d_ctrl);
-  k_bin_scatter_staged<true, true><<<grid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, none, perm, tm);
-  ctx->launches += 3;
+  launch_scan_scatter<true>(sp, n, d_n, none, perm, true, st);
   if (stable) return stable_tail(ctx, sp->md.PBM, B, perm, static_cast<uint32_t *>(sp->worklist.p), sp->d_ctrl, n, d_n, nullptr, 0, st);
   return launch_ok();
 }
@@ -298,11 +297,11 @@ int alloc_index_buffers(fgb_spatial *sp) {
   if (e == cudaSuccess) e = cudaMalloc(&md.PBM, words * 4);
   if (e == cudaSuccess) e = cudaMalloc(&sp->d_state, static_cast<size_t>(sp->n_state) * 8);
   if (e == cudaSuccess) e = cudaMalloc(&sp->d_md, sizeof(fgb_spatial_metadata));
-  if (e == cudaSuccess) e = cudaMalloc(&sp->d_ctrl, 16);
+  if (e == cudaSuccess) e = cudaMalloc(&sp->d_ctrl, 64);
   if (e == cudaSuccess) e = cudaMemset(sp->d_hist, 0, words * 4);
   if (e == cudaSuccess) e = cudaMemset(md.PBM, 0, words * 4);  // MessageSpatial3D.cu:77, MessageBucket.cu:69
   if (e == cudaSuccess) e = cudaMemset(sp->d_state, 0, static_cast<size_t>(sp->n_state) * 8);
-  if (e == cudaSuccess) e = cudaMemset(sp->d_ctrl, 0, 16);
+  if (e == cudaSuccess) e = cudaMemset(sp->d_ctrl, 0, 64);
   if (e == cudaSuccess) e = cudaMemcpy(sp->d_md, &md, sizeof(md), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     fgb_spatial_destroy(sp);

@@ -196,148 +196,277 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_keys(KeySrc<DIMS> src, uint
   }
 }
 
-// ---- phase 3: scatter --------------------------------------------------------------------
-// cursor[k+1] holds the next free slot of bin k.  IDX_ONLY: perm[dst] = source index.
+// ---- phases 2 + 3: scan and scatter in ONE launch -------------------------------------------
+// k_scan_scatter: blocks [0, scan_tiles) turn the histogram into the shifted prefix array (cursor[k+1] = start of bin
+// k; single-pass decoupled look-back, the histogram is re-zeroed on the way), blocks [scan_tiles, grid) scatter one
+// 2048-item tile each.  A scatter block loads and classifies its tile and has the first payload variable in flight
+// BEFORE it needs the cursors; only then does it wait for the scan (one acquire-load spin by thread 0 on the count of
+// finished scan tiles).  Blocks are dispatched in index order, so every scan tile is resident or done before the
+// first scatter block exists: the wait cannot deadlock.  Against two launches this removes one kernel boundary and
+// hides the scan behind the scatter's own loads (1 M messages: 8 + 14 us -> one kernel).
 //
-// Grouped tile (the steady state of a bin-sorted list): one global atomic per run, items of a run
-// and of neighbouring threads land on consecutive addresses, payload streamed with 128-bit loads.
-// Ungrouped tile: (1) rank the items per key in the shared-memory table, (2) claim one contiguous
-// output range per distinct key with a single global atomic, (3) lay the tile out in TABLE order in
-// shared memory (the table is indexed by the low key bits, so x-adjacent bins -- adjacent in the
-// output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
-// items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
-// Grouped tiles.  A warp owns 256 consecutive items of its block's 2048-item tile and walks them in 8 rounds of 32:
-// lane l of round r holds item w0 + 32 r + l, so consecutive lanes hold consecutive items -- in a bin-ordered list
-// mostly the same bin.  Runs of equal keys inside a round are found with one shuffle and one ballot; the first lane
-// of a run claims the run's output range with ONE global atomic and the lanes of the run store to consecutive
-// addresses: every load is a coalesced 128-byte warp access and every store instruction writes whole runs (with one
-// item per thread-owned 8-item strip instead, each store instruction touched 32 different sectors, 4 bytes each).
-// The block first classifies its tile by the number of runs -- a bin-ordered tile has few, any other order one per
-// item -- and records the choice for k_bin_scatter_staged, which runs next and takes the ungrouped tiles.
-// Also re-zeroes the scan's look-back words (the scan is complete by now) for the next build.
-template <bool IDX_ONLY>
-__global__ void __launch_bounds__(kBinThreads) k_bin_scatter_direct(const uint32_t *__restrict__ keys, uint32_t n_max,
-                                                                    const unsigned int *d_n, uint32_t *cursor,
-                                                                    const __grid_constant__ VarTable vt, uint32_t *perm,
-                                                                    uint32_t *tile_mode, unsigned long long *state,
-                                                                    uint32_t n_state, uint32_t *ctrl) {
-  __shared__ uint32_t s_runs;
-  for (uint32_t s = blockIdx.x * kBinThreads + threadIdx.x; s < n_state; s += gridDim.x * kBinThreads) state[s] = 0ull;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && ctrl) ctrl[0] = 0u;  // big-bin counter of the stable fix-up that may follow
-  const uint32_t n = load_count(d_n, n_max);
-  const uint32_t tile0 = blockIdx.x * kTile;
-  if (tile0 >= n) return;
-  if (threadIdx.x == 0) s_runs = 0u;
+// Grouped tile (the steady state of a bin-sorted list): a warp owns 256 consecutive items and walks them in 8 rounds
+// of 32; runs of equal keys inside a round are found with one shuffle and one ballot, the first lane of a run claims
+// the run's output range with ONE global atomic (dst = atomicAdd(&cursor[k+1], run); afterwards cursor[] IS the PBM)
+// and the lanes of the run store to consecutive addresses.  Ungrouped tile (any other order: one run per item): its
+// index is queued for k_bin_scatter_staged, which runs next over that worklist.
+// ctrl[]: [0] big-bin counter of the stable fix-up, [1] finished scan tiles, [2] finished scatter blocks,
+//         [3] length of the staged worklist.  The last scatter block re-zeroes [1], [2] and the look-back words.
+constexpr int kFsItems = 16;                          // counters per thread of a scan block
+constexpr int kFsTile = kBinThreads * kFsItems;       // 4096 counters per scan tile (== kScanTile)
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void scan_tile_256x16(uint32_t *hist, uint32_t *out, uint32_t bins, unsigned long long *state,
+                                                 int tile, uint32_t *warp_sums, uint32_t *s_excl) {
+  const uint32_t base = static_cast<uint32_t>(tile) * kFsTile + threadIdx.x * kFsItems;
+  uint32_t v[kFsItems];
+  const bool full = base + kFsItems <= bins;
+  if (full) {
+#pragma unroll
+    for (int q = 0; q < kFsItems / 4; ++q) {
+      const uint4 w = *reinterpret_cast<const uint4 *>(hist + base + 4 * q);
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+      *reinterpret_cast<uint4 *>(hist + base + 4 * q) = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kFsItems; ++j) {
+      v[j] = base + j < bins ? hist[base + j] : 0u;
+      if (base + j < bins) hist[base + j] = 0u;
+    }
+  }
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int j = 0; j < kFsItems; ++j) tsum += v[j];
+  uint32_t agg;
+  const uint32_t texcl = block_exclusive_scan(tsum, warp_sums, &agg);
+  if (threadIdx.x == 0) {
+    st_state(state + tile, (tile == 0 ? kStInclusive : kStAggregate) | agg);
+    if (tile == 0) *s_excl = 0;
+  }
+  if (tile > 0 && threadIdx.x < 32) {
+    const uint32_t e = lookback_exclusive(state, tile);
+    if (threadIdx.x == 0) {
+      st_state(state + tile, kStInclusive | static_cast<unsigned long long>(e + agg));
+      *s_excl = e;
+    }
+  }
   __syncthreads();
+  // out[base + j + 1] = exclusive prefix of item j (shifted by one): o[j] below is the value for out[base + 1 + j]
+  uint32_t run = *s_excl + texcl;
+  uint32_t o[kFsItems];
+#pragma unroll
+  for (int j = 0; j < kFsItems; ++j) {
+    o[j] = run;
+    run += v[j];
+  }
+  if (full) {
+    // out[base+1 .. base+3], three aligned 128-bit stores for out[base+4 .. base+15], out[base+16]
+    out[base + 1] = o[0];
+    out[base + 2] = o[1];
+    out[base + 3] = o[2];
+#pragma unroll
+    for (int q = 1; q < kFsItems / 4; ++q)
+      *reinterpret_cast<uint4 *>(out + base + 4 * q) = make_uint4(o[4 * q - 1], o[4 * q], o[4 * q + 1], o[4 * q + 2]);
+    out[base + kFsItems] = o[kFsItems - 1];
+  } else {
+#pragma unroll
+    for (int j = 0; j < kFsItems; ++j)
+      if (base + j < bins) out[base + j + 1] = o[j];
+  }
+  if (tile == 0 && threadIdx.x == 0) out[0] = 0u;
+}
+
+template <bool IDX_ONLY>
+__global__ void __launch_bounds__(kBinThreads) k_scan_scatter(uint32_t *hist, uint32_t *cursor, uint32_t bins,
+                                                              unsigned long long *state, uint32_t scan_tiles,
+                                                              const uint32_t *__restrict__ keys, uint32_t n_max,
+                                                              const unsigned int *d_n, const __grid_constant__ VarTable vt,
+                                                              uint32_t *perm, uint32_t *worklist, uint32_t *ctrl) {
+  __shared__ uint32_t s_runs;
+  __shared__ uint32_t s_scan[33];
+  __shared__ uint32_t s_excl;
+  if (blockIdx.x < scan_tiles) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ctrl[0] = 0u;  // big-bin counter of the stable fix-up that may follow
+      ctrl[3] = 0u;  // staged worklist (scatter blocks append only after the scan has finished)
+    }
+    scan_tile_256x16(hist, cursor, bins, state, static_cast<int>(blockIdx.x), s_scan, &s_excl);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(ctrl + 1, 1u);
+    return;
+  }
+  const uint32_t tile = blockIdx.x - scan_tiles, scatter_blocks = gridDim.x - scan_tiles;
+  const uint32_t n = load_count(d_n, n_max);
+  const uint32_t tile0 = tile * kTile;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t w0 = tile0 + warp * (32u * kTileItems);
-  const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+  bool grouped = false;
   uint32_t k[kTileItems], head[kTileItems];  // head: ballot of the lanes that start a run (bit 0 always set)
-  uint32_t runs = 0;
-#pragma unroll
-  for (int r = 0; r < kTileItems; ++r) {
-    const uint32_t i = w0 + r * 32u + lane;
-    k[r] = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
-    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k[r], 1);
-    head[r] = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev != k[r]);
-    runs += __popc(head[r] & __ballot_sync(0xFFFFFFFFu, i < n));
-  }
-  if (lane == 0) atomicAdd(&s_runs, runs);
-  __syncthreads();
-  const bool grouped = s_runs * 2u <= tile_n;
-  if (threadIdx.x == 0) tile_mode[blockIdx.x] = grouped ? 1u : 0u;
-  if (!grouped) return;
-  // claim: the first lane of every run adds the run's length to the bin's cursor (all atomics of a warp in flight)
-  uint32_t dst[kTileItems];
-#pragma unroll
-  for (int r = 0; r < kTileItems; ++r) {
-    const uint32_t i = w0 + r * 32u + lane;
-    const uint32_t below = head[r] & ((2u << lane) - 1u);            // run heads at or below this lane
-    const int first = 31 - __clz(static_cast<int>(below));           // lane that starts this lane's run
-    const uint32_t above = head[r] & ~((2u << lane) - 1u);           // run heads above this lane
-    const int next = above ? __ffs(static_cast<int>(above)) - 1 : 32;  // first lane of the next run
-    uint32_t base = 0;
-    if (static_cast<int>(lane) == first && i < n) {
-      // the run ends at the next head or at the end of the list
-      const uint32_t last_valid = (n - (w0 + r * 32u)) < 32u ? n - (w0 + r * 32u) : 32u;
-      const uint32_t len = (static_cast<uint32_t>(next) < last_valid ? static_cast<uint32_t>(next) : last_valid) - lane;
-      base = atomicAdd(cursor + k[r] + 1, len);
-    }
-    base = __shfl_sync(0xFFFFFFFFu, base, first);
-    dst[r] = base + (lane - static_cast<uint32_t>(first));
-  }
-  if constexpr (IDX_ONLY) {
+  uint32_t cur[kTileItems];
+  bool cur4 = false;
+  if (tile0 < n) {
+    if (threadIdx.x == 0) s_runs = 0u;
+    __syncthreads();
+    const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;
+    uint32_t runs = 0;
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
       const uint32_t i = w0 + r * 32u + lane;
-      if (i < n) perm[dst[r]] = i;
+      k[r] = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
+      const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, k[r], 1);
+      head[r] = __ballot_sync(0xFFFFFFFFu, lane == 0 || prev != k[r]);
+      runs += __popc(head[r] & __ballot_sync(0xFFFFFFFFu, i < n));
     }
-  } else {
-    // software pipeline over the variables: the loads of variable v+1 are in flight while v is stored
-    uint32_t cur[kTileItems];
-    bool cur4 = vt.n > 0 && vt.len[0] == 4;
-    if (cur4) {
-      const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[0]);
-#pragma unroll
-      for (int r = 0; r < kTileItems; ++r) {
-        const uint32_t i = w0 + r * 32u + lane;
-        if (i < n) cur[r] = ld_stream_u32(in + i);
-      }
-    }
-    for (uint32_t v = 0; v < vt.n; ++v) {
-      const bool next4 = v + 1 < vt.n && vt.len[v + 1] == 4;
-      uint32_t nxt[kTileItems];
-      if (next4) {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 1]);
-#pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
-          const uint32_t i = w0 + r * 32u + lane;
-          if (i < n) nxt[r] = ld_stream_u32(in + i);
-        }
-      }
+    if (lane == 0) atomicAdd(&s_runs, runs);
+    __syncthreads();
+    grouped = s_runs * 2u <= tile_n;
+    // the first payload variable does not depend on the cursors: its loads overlap the wait for the scan
+    if (!IDX_ONLY && grouped) {
+      cur4 = vt.n > 0 && vt.len[0] == 4;
       if (cur4) {
-        uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[0]);
 #pragma unroll
         for (int r = 0; r < kTileItems; ++r) {
           const uint32_t i = w0 + r * 32u + lane;
-          if (i < n) o[dst[r]] = cur[r];
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < kTileItems; ++r) {
-          const uint32_t i = w0 + r * 32u + lane;
-          if (i < n) copy_item(vt, v, i, dst[r]);
+          if (i < n) cur[r] = ld_stream_u32(in + i);
         }
       }
-#pragma unroll
-      for (int r = 0; r < kTileItems; ++r) cur[r] = nxt[r];
-      cur4 = next4;
     }
-    if (perm) {  // source slot of every sorted item
+    // wait for the scan
+    if (threadIdx.x == 0)
+      while (ld_acquire_u32(ctrl + 1) < scan_tiles) __nanosleep(40);
+    __syncthreads();
+    if (!grouped && threadIdx.x == 0) worklist[atomicAdd(ctrl + 3, 1u)] = tile;
+  }
+  if (tile0 < n && grouped) {
+    // claim: the first lane of every run adds the run's length to the bin's cursor (all atomics of a warp in flight)
+    uint32_t dst[kTileItems];
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      const uint32_t i = w0 + r * 32u + lane;
+      const uint32_t below = head[r] & ((2u << lane) - 1u);            // run heads at or below this lane
+      const int first = 31 - __clz(static_cast<int>(below));           // lane that starts this lane's run
+      const uint32_t above = head[r] & ~((2u << lane) - 1u);           // run heads above this lane
+      const int next = above ? __ffs(static_cast<int>(above)) - 1 : 32;  // first lane of the next run
+      uint32_t base = 0;
+      if (static_cast<int>(lane) == first && i < n) {
+        // the run ends at the next head or at the end of the list
+        const uint32_t last_valid = (n - (w0 + r * 32u)) < 32u ? n - (w0 + r * 32u) : 32u;
+        const uint32_t len = (static_cast<uint32_t>(next) < last_valid ? static_cast<uint32_t>(next) : last_valid) - lane;
+        base = atomicAdd(cursor + k[r] + 1, len);
+      }
+      base = __shfl_sync(0xFFFFFFFFu, base, first);
+      dst[r] = base + (lane - static_cast<uint32_t>(first));
+    }
+    if constexpr (IDX_ONLY) {
 #pragma unroll
       for (int r = 0; r < kTileItems; ++r) {
         const uint32_t i = w0 + r * 32u + lane;
         if (i < n) perm[dst[r]] = i;
       }
+    } else {
+      // software pipeline over the variables: the loads of variable v+1 are in flight while v is stored
+      for (uint32_t v = 0; v < vt.n; ++v) {
+        const bool next4 = v + 1 < vt.n && vt.len[v + 1] == 4;
+        uint32_t nxt[kTileItems];
+        if (next4) {
+          const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 1]);
+#pragma unroll
+          for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t i = w0 + r * 32u + lane;
+            if (i < n) nxt[r] = ld_stream_u32(in + i);
+          }
+        }
+        if (cur4) {
+          uint32_t *o = reinterpret_cast<uint32_t *>(vt.out[v]);
+#pragma unroll
+          for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t i = w0 + r * 32u + lane;
+            if (i < n) o[dst[r]] = cur[r];
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < kTileItems; ++r) {
+            const uint32_t i = w0 + r * 32u + lane;
+            if (i < n) copy_item(vt, v, i, dst[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) cur[r] = nxt[r];
+        cur4 = next4;
+      }
+      if (perm) {  // source slot of every sorted item
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+          const uint32_t i = w0 + r * 32u + lane;
+          if (i < n) perm[dst[r]] = i;
+        }
+      }
+    }
+  }
+  // the last scatter block to finish cleans up for the next build (it first makes sure the scan has finished: a
+  // list whose device count is 0 lets every scatter block get here without having waited)
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ctrl + 2, 1u) == scatter_blocks - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0)
+      while (ld_acquire_u32(ctrl + 1) < scan_tiles) __nanosleep(40);
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < scan_tiles; t += kBinThreads) state[t] = 0ull;
+    if (threadIdx.x == 0) {
+      ctrl[1] = 0u;
+      ctrl[2] = 0u;
     }
   }
 }
 
-// Ungrouped tiles: shared-memory table + staged, coalesced write-out.
+// Ungrouped tiles: shared-memory table + staged, coalesced write-out.  (1) rank the items per key in the
+// shared-memory table, (2) claim one contiguous output range per distinct key with a single global atomic, (3) lay
+// the tile out in TABLE order in shared memory (the table is indexed by the low key bits, so x-adjacent bins --
+// adjacent in the output -- sit in adjacent slots), (4) write it out with consecutive lanes on consecutive staged
+// items, so stores fill whole 32-byte sectors instead of one sector per 4 bytes.
+// Persistent blocks walk the worklist that k_scan_scatter left (ctrl[3] entries): for a bin-ordered list the list is
+// empty and the launch costs a few hundred threads reading one word.
+template <bool VEC, bool IDX_ONLY>
+__device__ __forceinline__ void staged_tile(uint32_t tile, const uint32_t *__restrict__ keys, uint32_t n, uint32_t *cursor,
+                                            const VarTable &vt, uint32_t *perm, uint32_t *s_key, uint32_t *s_cnt, uint32_t *s_dst,
+                                            uint16_t *s_src, uint32_t *s_scan);
+
 template <bool VEC, bool IDX_ONLY>
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter_staged(const uint32_t *__restrict__ keys, uint32_t n_max,
                                                                     const unsigned int *d_n, uint32_t *cursor,
                                                                     const __grid_constant__ VarTable vt, uint32_t *perm,
-                                                                    const uint32_t *__restrict__ tile_mode) {
+                                                                    const uint32_t *__restrict__ worklist, const uint32_t *ctrl) {
   __shared__ uint32_t s_key[kTabSlots];   // key of the slot, later the slot's offset in the staged tile
   __shared__ uint32_t s_cnt[kTabSlots];   // count of the key in this tile, later its global base
   __shared__ uint32_t s_dst[kTile];       // staged tile: destination index ...
   __shared__ uint16_t s_src[kTile];       // ... and source item (offset inside the tile)
   __shared__ uint32_t s_scan[33];
+  const uint32_t count = ctrl[3];
   const uint32_t n = load_count(d_n, n_max);
-  const uint32_t tile0 = blockIdx.x * kTile;
-  if (tile0 >= n) return;
-  if (tile_mode[blockIdx.x] != 0u) return;  // handled by the direct kernel
+  for (uint32_t w = blockIdx.x; w < count; w += gridDim.x) {
+    staged_tile<VEC, IDX_ONLY>(worklist[w], keys, n, cursor, vt, perm, s_key, s_cnt, s_dst, s_src, s_scan);
+    __syncthreads();
+  }
+}
+
+template <bool VEC, bool IDX_ONLY>
+__device__ __forceinline__ void staged_tile(uint32_t tile, const uint32_t *__restrict__ keys, uint32_t n, uint32_t *cursor,
+                                            const VarTable &vt, uint32_t *perm, uint32_t *s_key, uint32_t *s_cnt, uint32_t *s_dst,
+                                            uint16_t *s_src, uint32_t *s_scan) {
+  const uint32_t tile0 = tile * kTile;
   const uint32_t i0 = tile0 + threadIdx.x * kTileItems;
   const int cnt = i0 < n ? ((n - i0) < static_cast<uint32_t>(kTileItems) ? static_cast<int>(n - i0) : kTileItems) : 0;
   const uint32_t tile_n = (n - tile0) < static_cast<uint32_t>(kTile) ? n - tile0 : kTile;

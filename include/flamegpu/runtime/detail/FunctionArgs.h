@@ -47,6 +47,7 @@ struct SpatialMeta {
   //      and queue their accepted messages in shared memory (MessageSpatial3D.cuh advance_filtered).
   int iter_mode;
   float radius2_eps;   // radius^2 * (1 + 1e-5): conservative in-radius test of the iterator
+  unsigned int pad_index;  // index of the list's padding message (one past its capacity; location far outside any environment)
   const unsigned int *pbm;
 };
 
@@ -140,16 +141,16 @@ FGB_HD LocPtrs make_loc(const FunctionArgs &a) {
   return l;
 }
 
-// Radius-filtered iterator (MessageSpatial2D/3D::In::Filter, ITER_MODE 1).  Each lane walks its strips in chunks
-// of up to 32 consecutive messages and keeps, per chunk with at least one message within the radius, the pair
-// {first message index, accepted bit mask} in dynamic shared memory: word w of thread t at [w * blockDim.x + t]
-// (conflict free).  The scheduler launches with kFilterQueueWords * blockDim.x words.
+// Radius-filtered iterator (MessageSpatial2D/3D::In::Filter, ITER_MODE 1; StripWalk.cuh).  Each lane walks its strips
+// in chunks of up to 32 consecutive messages and keeps, per chunk with at least one message within the radius, the
+// pair {first message index - 1, accepted bit mask} in dynamic shared memory: entry k of thread t is the 8-byte word
+// [k * blockDim.x + t] (conflict free).  The scheduler launches with kFilterQueueWords * blockDim.x words.
 // 8 chunks = 64 B of shared memory per thread.  Shared memory is carved out of the L1: with 16 chunks per lane the
 // L1 hit rate of the message loads fell from 74 % to 9 % and the walk became latency bound (stress model 2x
 // slower than the unfiltered iterator); with 4 the queues fill too often.  Measured: 16 / 8 / 4 chunks ->
 // Circles 16.8 M move 9.2 / 8.0 / 9.9 ms, stress 4 M update 1.90 / 0.96 / 1.09 ms.
 #ifndef FGB_FILTER_CHUNKS
-#define FGB_FILTER_CHUNKS 8
+#define FGB_FILTER_CHUNKS 10
 #endif
 constexpr unsigned int kFilterChunks = FGB_FILTER_CHUNKS;     // queued chunks per lane (each up to 32 accepted messages)
 constexpr unsigned int kFilterQueueWords = 2 * kFilterChunks;
@@ -188,46 +189,6 @@ __device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, un
   unsigned long long r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
-}
-// bit k of the result: message i0+k (k < n <= 32) lies within sqrt(r2) of (ox,oy,oz).  The location arrays are
-// 8-byte aligned at even indices (one cudaMalloc per variable), so pairs of messages are fetched with one 64-bit load.
-template <int DIMS>
-__device__ __forceinline__ uint32_t radius_mask(const float *__restrict__ x, const float *__restrict__ y,
-                                                const float *__restrict__ z, int i0, int n, float ox, float oy, float oz,
-                                                float r2) {
-  auto one = [&](int j) {
-    const float dx = __ldg(x + j) - ox, dy = __ldg(y + j) - oy;
-    float d2 = dx * dx + dy * dy;
-    if (DIMS == 3) {
-      const float dz = __ldg(z + j) - oz;
-      d2 += dz * dz;
-    }
-    return d2 <= r2;
-  };
-  if (n <= 0) return 0u;
-  uint32_t m = 0;  // filled from the top: after c messages they occupy bits [32-c, 32)
-  int i = 0;
-  if (i0 & 1) {
-    m = one(i0) ? 0x80000000u : 0u;
-    i = 1;
-  }
-  const unsigned long long OX = f32x2(ox, ox), OY = f32x2(oy, oy), OZ = f32x2(oz, oz);
-#pragma unroll 2
-  for (; i + 2 <= n; i += 2) {
-    const unsigned long long X = __ldg(reinterpret_cast<const unsigned long long *>(x + i0 + i));
-    const unsigned long long Y = __ldg(reinterpret_cast<const unsigned long long *>(y + i0 + i));
-    const unsigned long long dx = f32x2_sub(X, OX), dy = f32x2_sub(Y, OY);
-    unsigned long long d = f32x2_fma(dy, dy, f32x2_mul(dx, dx));
-    if (DIMS == 3) {
-      const unsigned long long Z = __ldg(reinterpret_cast<const unsigned long long *>(z + i0 + i));
-      const unsigned long long dz = f32x2_sub(Z, OZ);
-      d = f32x2_fma(dz, dz, d);
-    }
-    const float d0 = __uint_as_float(static_cast<uint32_t>(d)), d1 = __uint_as_float(static_cast<uint32_t>(d >> 32));
-    m = (m >> 2) | (d0 <= r2 ? 0x40000000u : 0u) | (d1 <= r2 ? 0x80000000u : 0u);
-  }
-  if (i < n) m = (m >> 1) | (one(i0 + i) ? 0x80000000u : 0u);
-  return m >> (32 - n);
 }
 #endif
 

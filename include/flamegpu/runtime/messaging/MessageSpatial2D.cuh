@@ -8,6 +8,7 @@
 #include <type_traits>
 
 #include "flamegpu/runtime/detail/FunctionArgs.h"
+#include "flamegpu/runtime/detail/StripWalk.cuh"
 #include "flamegpu/runtime/messaging/MessageBruteForce.cuh"
 
 namespace flamegpu {
@@ -46,147 +47,14 @@ class MessageSpatial2D {
    public:
     class Filter {
      public:
-      class Message {
-        const detail::FunctionArgs &a;
-        const detail::LocPtrs loc;
-        float ox, oy;
-        int cx, cy;
-        int strip;  // 0..2, 3 == all strips walked, 4 == end (radius-filtered mode)
-        int idx, idx_end, nxt, nxt_end;
-        int sidx;   // radius-filtered mode, see MessageSpatial3D.cuh
-        int cbase;          // chunk being handed out: first message index, remaining accepted bits
-        unsigned int cmask;
-        unsigned int qpos, qcount, lanes;
-        const int mode;  // compile-time constant after inlining (agent_function_wrapper<..., ITER_MODE>)
-        bool pad;   // this lane is waiting for the others: its current message is a padding message at infinity
-        __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
-          b = 0;
-          e = 0;
-          if (s < 3) {
-            const int y = cy + s - 1;
-            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.win_count;
-            if (y >= 0 && y < gy) {
-              const int row = y * gx;
-              const int x0 = cx > 0 ? cx - 1 : 0;
-              const int x1 = cx + 1 < gx ? cx + 1 : gx - 1;
-              b = static_cast<int>(__ldg(a.in_meta.pbm + row + x0));
-              e = static_cast<int>(__ldg(a.in_meta.pbm + row + x1 + 1));
-            }
-          }
-        }
-        __device__ __forceinline__ void next_strip() {
-          do {
-            ++strip;
-            idx = nxt;
-            idx_end = nxt_end;
-            fetch(strip + 1, nxt, nxt_end);
-          } while (idx >= idx_end && strip < 3);
-        }
-        // lock-step walk + per-lane queue, same scheme as MessageSpatial3D::In::Filter::Message::advance_filtered
-        __device__ __forceinline__ void advance_filtered() {
-          uint32_t *q = detail::filter_queue() + threadIdx.x;
-          const unsigned int stride = blockDim.x;
-          for (;;) {
-            // Every lane takes the same path through this function (all decisions are warp votes), so the warp
-            // stays converged.  While any lane still has accepted messages, every lane returns to the agent
-            // function: lanes that have none left are given a padding message far outside the environment.
-            if (cmask == 0u && qpos < qcount) {
-              cbase = static_cast<int>(q[(2u * qpos) * stride]);
-              cmask = q[(2u * qpos + 1u) * stride];
-              ++qpos;
-            }
-            if (__any_sync(lanes, cmask != 0u)) {
-              pad = cmask == 0u;
-              if (!pad) {
-                idx = cbase + (__ffs(static_cast<int>(cmask)) - 1);
-                cmask &= cmask - 1u;
-              }
-              return;
-            }
-            qpos = 0;
-            qcount = 0;
-            if (__all_sync(lanes, strip >= 3)) {
-              strip = 4;
-              return;
-            }
-            // walk: one chunk of the current strip per round, until a queue is full or every lane has walked all strips
-            for (;;) {
-              const bool walked = strip >= 3;
-              const unsigned int full = __ballot_sync(lanes, !walked && qcount >= detail::kFilterChunks);
-              const unsigned int done = __ballot_sync(lanes, walked);
-              if (full != 0u || done == lanes) break;
-              if (!walked) {
-                const int n = idx_end - sidx < 32 ? idx_end - sidx : 32;
-                const uint32_t m = detail::radius_mask<2>(reinterpret_cast<const float *>(loc.x), reinterpret_cast<const float *>(loc.y),
-                                                          nullptr, sidx, n, ox, oy, 0.f, a.in_meta.radius2_eps);
-                if (m) {
-                  q[(2u * qcount) * stride] = static_cast<uint32_t>(sidx);
-                  q[(2u * qcount + 1u) * stride] = m;
-                  ++qcount;
-                }
-                sidx += n;
-                if (sidx >= idx_end) {
-                  next_strip();
-                  sidx = idx;
-                }
-              }
-            }
-          }
-        }
-        template <typename T>
-        __device__ __forceinline__ T location(const char *base) const {
-          const T v = __ldg(reinterpret_cast<const T *>(base) + static_cast<unsigned int>(idx));
-          return pad ? detail::pad_location<T>() : v;
-        }
-
-       public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, int _cx, int _cy, bool begin, int _mode = 0)
-            : a(args), loc(detail::make_loc(args)), ox(x), oy(y), cx(_cx), cy(_cy), strip(3), idx(0), idx_end(0), nxt(0), nxt_end(0),
-              sidx(0), cbase(0), cmask(0), qpos(0), qcount(0), lanes(0), pad(false), mode(_mode) {
-          if (begin) {
-            strip = -1;
-            fetch(0, nxt, nxt_end);
-            next_strip();
-            if (mode != 0) {
-              lanes = __activemask();
-              sidx = idx;
-              advance_filtered();
-            }
-          }
-        }
-        __device__ __forceinline__ bool operator!=(const Message &) const { return mode != 0 ? strip < 4 : idx < idx_end; }
-        __device__ __forceinline__ bool operator==(const Message &rhs) const { return strip == rhs.strip && idx == rhs.idx; }
-        __device__ __forceinline__ Message &operator++() {
-          if (mode != 0) {
-            advance_filtered();
-          } else if (++idx >= idx_end) {
-            next_strip();
-          }
-          return *this;
-        }
-        template <typename T, unsigned int N>
-        __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
-          if (h == detail::kHashX) return location<T>(loc.x);
-          if (h == detail::kHashY) return location<T>(loc.y);
-          const int s = detail::find_slot(a.msg_in, h);
-          if (s < 0 || pad) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<unsigned int>(idx));
-        }
-        template <typename T, flamegpu::size_type N, unsigned int M>
-        __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
-          if (s < 0 || index >= N || pad) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
-        }
-        __device__ __forceinline__ unsigned int getIndex() const { return static_cast<unsigned int>(idx); }
-      };
+      // strip walk in the reference's order or radius-filtered: flamegpu/runtime/detail/StripWalk.cuh
+      typedef detail::SpatialFilterMessage<2> Message;
       class iterator {
         Message m;
 
        public:
         __device__ __forceinline__ iterator(const detail::FunctionArgs &args, float x, float y, int cx, int cy, bool begin, int mode)
-            : m(args, x, y, cx, cy, begin, mode) {}
+            : m(args, x, y, 0.f, cx, cy, 0, begin, mode) {}
         __device__ __forceinline__ iterator &operator++() {
           ++m;
           return *this;

@@ -17,6 +17,7 @@
 #define FGB_INCLUDE_FLAMEGPU_RUNTIME_MESSAGING_MESSAGESPATIAL3D_CUH_
 
 #include "flamegpu/runtime/detail/FunctionArgs.h"
+#include "flamegpu/runtime/detail/StripWalk.cuh"
 #include "flamegpu/runtime/messaging/MessageSpatial2D.cuh"
 
 namespace flamegpu {
@@ -47,156 +48,8 @@ class MessageSpatial3D {
    public:
     class Filter {
      public:
-      class Message {
-        const detail::FunctionArgs &a;
-        const detail::LocPtrs loc;
-        float ox, oy, oz;   // search origin (radius-filtered mode only)
-        int cx, cy, cz;
-        int strip;          // 0..8 current strip, 9 == all strips walked, 10 == end (radius-filtered mode)
-        int idx, idx_end;   // message presented to the agent function, one past the last message of the strip
-        int nxt, nxt_end;   // prefetched bounds of strip+1
-        // radius-filtered mode: scan cursor, this lane's queue of accepted messages, lanes that walk together
-        int sidx;
-        int cbase;          // chunk being handed out: first message index, remaining accepted bits
-        unsigned int cmask;
-        unsigned int qpos, qcount, lanes;
-        const int mode;  // compile-time constant after inlining (agent_function_wrapper<..., ITER_MODE>)
-        bool pad;   // this lane is waiting for the others: its current message is a padding message at infinity
-
-        // [PBM[hash(cx-1,y,z)], PBM[hash(cx+1,y,z)+1]) of strip s; empty if outside the grid
-        __device__ __forceinline__ void fetch(int s, int &b, int &e) const {
-          b = 0;
-          e = 0;
-          if (s < 9) {
-            const int y = cy + (s / 3) - 1, z = cz + (s % 3) - 1;
-            const int gx = a.in_meta.grid_dim[0], gy = a.in_meta.grid_dim[1], gz = a.in_meta.win_count;
-            if (y >= 0 && z >= 0 && y < gy && z < gz) {
-              const int row = (z * gy + y) * gx;
-              const int x0 = cx > 0 ? cx - 1 : 0;                 // getHash3D clamps x (reference :660-672)
-              const int x1 = cx + 1 < gx ? cx + 1 : gx - 1;
-              b = static_cast<int>(__ldg(a.in_meta.pbm + row + x0));
-              e = static_cast<int>(__ldg(a.in_meta.pbm + row + x1 + 1));
-            }
-          }
-        }
-        __device__ __forceinline__ void next_strip() {
-          do {
-            ++strip;
-            idx = nxt;
-            idx_end = nxt_end;
-            fetch(strip + 1, nxt, nxt_end);
-          } while (idx >= idx_end && strip < 9);
-        }
-        // Radius-filtered mode: the lanes of a warp walk their strips TOGETHER, each testing
-        // its own messages against the radius and queueing the accepted ones in shared memory; only when a
-        // queue is full (or every lane has walked all strips) do the lanes return to the agent function, once
-        // per queued message.  The expensive in-radius branch of the user code then runs max-over-lanes(#accepted)
-        // times per warp instead of once per message of the neighbourhood.
-        __device__ __forceinline__ void advance_filtered() {
-          uint32_t *q = detail::filter_queue() + threadIdx.x;
-          const unsigned int stride = blockDim.x;
-          for (;;) {
-            // Every lane takes the same path through this function (all decisions are warp votes), so the warp
-            // stays converged.  While any lane still has accepted messages, every lane returns to the agent
-            // function: lanes that have none left are given a padding message far outside the environment.
-            if (cmask == 0u && qpos < qcount) {
-              cbase = static_cast<int>(q[(2u * qpos) * stride]);
-              cmask = q[(2u * qpos + 1u) * stride];
-              ++qpos;
-            }
-            if (__any_sync(lanes, cmask != 0u)) {
-              pad = cmask == 0u;
-              if (!pad) {
-                idx = cbase + (__ffs(static_cast<int>(cmask)) - 1);
-                cmask &= cmask - 1u;
-              }
-              return;
-            }
-            qpos = 0;
-            qcount = 0;
-            if (__all_sync(lanes, strip >= 9)) {
-              strip = 10;
-              return;
-            }
-            // walk: one chunk of the current strip per round, until a queue is full or every lane has walked all strips
-            for (;;) {
-              const bool walked = strip >= 9;
-              const unsigned int full = __ballot_sync(lanes, !walked && qcount >= detail::kFilterChunks);
-              const unsigned int done = __ballot_sync(lanes, walked);
-              if (full != 0u || done == lanes) break;
-              if (!walked) {
-                const int n = idx_end - sidx < 32 ? idx_end - sidx : 32;
-                const uint32_t m = detail::radius_mask<3>(reinterpret_cast<const float *>(loc.x), reinterpret_cast<const float *>(loc.y),
-                                                          reinterpret_cast<const float *>(loc.z), sidx, n, ox, oy, oz, a.in_meta.radius2_eps);
-                if (m) {
-                  q[(2u * qcount) * stride] = static_cast<uint32_t>(sidx);
-                  q[(2u * qcount + 1u) * stride] = m;
-                  ++qcount;
-                }
-                sidx += n;
-                if (sidx >= idx_end) {
-                  next_strip();
-                  sidx = idx;
-                }
-              }
-            }
-          }
-        }
-        template <typename T>
-        __device__ __forceinline__ T location(const char *base) const {
-          const T v = __ldg(reinterpret_cast<const T *>(base) + static_cast<unsigned int>(idx));
-          return pad ? detail::pad_location<T>() : v;
-        }
-
-       public:
-        __device__ __forceinline__ Message(const detail::FunctionArgs &args, float x, float y, float z, int _cx, int _cy, int _cz, bool begin, int _mode = 0)
-            : a(args), loc(detail::make_loc(args)), ox(x), oy(y), oz(z), cx(_cx), cy(_cy), cz(_cz), strip(9), idx(0), idx_end(0),
-              nxt(0), nxt_end(0), sidx(0), cbase(0), cmask(0), qpos(0), qcount(0), lanes(0), pad(false), mode(_mode) {
-          if (begin) {
-            strip = -1;
-            fetch(0, nxt, nxt_end);
-            next_strip();
-            if (mode != 0) {
-              lanes = __activemask();
-              sidx = idx;
-              advance_filtered();
-            }
-          }
-        }
-        __device__ __forceinline__ bool operator!=(const Message &) const {
-          // reference order: after the last strip next_strip() leaves an empty range, so one compare serves both
-          // "advance within the strip" and "end of iteration"
-          return mode != 0 ? strip < 10 : idx < idx_end;
-        }
-        __device__ __forceinline__ bool operator==(const Message &rhs) const {
-          return strip == rhs.strip && idx == rhs.idx;
-        }
-        __device__ __forceinline__ Message &operator++() {
-          if (mode != 0) {
-            advance_filtered();
-          } else if (++idx >= idx_end) {
-            next_strip();
-          }
-          return *this;
-        }
-        template <typename T, unsigned int N>
-        __device__ __forceinline__ T getVariable(const char (&name)[N]) const {
-          const uint32_t h = detail::name_hash(name);  // folds to a constant after inlining
-          if (h == detail::kHashX) return location<T>(loc.x);
-          if (h == detail::kHashY) return location<T>(loc.y);
-          if (h == detail::kHashZ) return location<T>(loc.z);
-          const int s = detail::find_slot(a.msg_in, h);
-          if (s < 0 || pad) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<unsigned int>(idx));
-        }
-        template <typename T, flamegpu::size_type N, unsigned int M>
-        __device__ __forceinline__ T getVariable(const char (&name)[M], unsigned int index) const {
-          const int s = detail::find_slot(a.msg_in, detail::name_hash(name));
-          if (s < 0 || index >= N || pad) return T{};
-          return __ldg(reinterpret_cast<const T *>(a.msg_in.ptr[s]) + static_cast<size_t>(idx) * N + index);
-        }
-        __device__ __forceinline__ unsigned int getIndex() const { return static_cast<unsigned int>(idx); }
-      };
+      // strip walk in the reference's order or radius-filtered: flamegpu/runtime/detail/StripWalk.cuh
+      typedef detail::SpatialFilterMessage<3> Message;
       class iterator {
         Message m;
 

@@ -151,6 +151,10 @@ struct DevList {
   unsigned int count_slot = 0;  // control-block slot of the device count
   unsigned int appended_this_step = 0;  // upper bound of what listAppend added since the last endStep
   bool double_buffered = true;
+  // Spatial message lists keep a PADDING item at index `capacity` of every buffer (floating-point variables 1e18, others
+  // zero): the radius-filtered iterator shows it to lanes that wait for the other lanes of their warp (StripWalk.cuh).
+  // Nothing ever writes at or beyond `capacity`, so the item is written once per allocation.
+  bool pad_slot = false;
   // the owning simulation's allocation generation, bumped whenever a buffer of this list moves: launches captured
   // into a CUDA graph hold raw pointers, CUDASimulation::step() drops its cached graphs when the generation moved
   unsigned long long *gen = nullptr;
@@ -183,16 +187,26 @@ struct DevList {
     unsigned int cap = std::max(capacity, 256u);
     while (cap < need) cap = static_cast<unsigned int>(std::min<unsigned long long>(0xFFFFFFF0ull, static_cast<unsigned long long>(cap) * 5 / 4 + 64));
     cap = (cap + 63u) & ~63u;
+    const size_t items = static_cast<size_t>(cap) + (pad_slot ? 8u : 0u);
     for (size_t v = 0; v < names.size(); ++v) {
       const size_t b = meta[v].bytes();
       char *nd = nullptr;
-      FGB_CUDA_THROW(cudaMalloc(&nd, static_cast<size_t>(cap) * b));
+      FGB_CUDA_THROW(cudaMalloc(&nd, items * b));
       if (data[v] && keep) FGB_CUDA_THROW(cudaMemcpy(nd, data[v], static_cast<size_t>(std::min(keep, capacity)) * b, cudaMemcpyDeviceToDevice));
       if (data[v]) cudaFree(data[v]);
       data[v] = nd;
       if (double_buffered) {
         if (swap[v]) cudaFree(swap[v]);
-        FGB_CUDA_THROW(cudaMalloc(&swap[v], static_cast<size_t>(cap) * b));
+        FGB_CUDA_THROW(cudaMalloc(&swap[v], items * b));
+      }
+      if (pad_slot) {
+        std::vector<char> pad(b, 0);
+        if (meta[v].type == std::type_index(typeid(float)))
+          for (unsigned int e = 0; e < meta[v].elements; ++e) reinterpret_cast<float *>(pad.data())[e] = detail::pad_location<float>();
+        else if (meta[v].type == std::type_index(typeid(double)))
+          for (unsigned int e = 0; e < meta[v].elements; ++e) reinterpret_cast<double *>(pad.data())[e] = detail::pad_location<double>();
+        FGB_CUDA_THROW(cudaMemcpy(data[v] + static_cast<size_t>(cap) * b, pad.data(), b, cudaMemcpyHostToDevice));
+        if (double_buffered) FGB_CUDA_THROW(cudaMemcpy(swap[v] + static_cast<size_t>(cap) * b, pad.data(), b, cudaMemcpyHostToDevice));
       }
     }
     capacity = cap;

@@ -59,6 +59,7 @@ inline void CUDASimulation::initialise() {
     m.keyed_slot = alloc_slot();
     if (!mp.second->persistent) zero_slots.push_back(m.list.count_slot);
     if (mp.second->dims() > 0) {
+      m.list.pad_slot = true;  // padding message of the radius-filtered iterator
       if (!(mp.second->radius > 0.f)) throw exception::InvalidMessageType("spatial message '" + mp.first + "' has no radius");
       auto w = windows.find(mp.first);
       if (w != windows.end()) {
@@ -780,6 +781,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       a.in_meta.radius = M.md.radius;
       a.in_meta.iter_mode = filtered_iteration(f) ? 1 : 0;
       a.in_meta.radius2_eps = M.md.radius * M.md.radius * 1.00001f;
+      a.in_meta.pad_index = M.list.capacity;
       a.in_meta.wrap_compatible = M.md.wrap_compatible ? 1 : 0;
       a.in_meta.pbm = M.md.PBM;
     }
@@ -1002,6 +1004,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
 // which iterator variant a function runs with (CUDAConfig().spatialIterationMode)
 inline bool CUDASimulation::filtered_iteration(const detail::FunctionRT &f) const {
   if (!(f.msg_in && f.msg_in->spatial && !f.msg_in->bucket && f.fn->func_filtered)) return false;
+  if (f.msg_in->list.capacity >= (1u << 30)) return false;  // the filtered walk addresses locations with 32-bit byte offsets
   const int mode = cuda_config.spatialIterationMode;
   return mode > 0 || (mode < 0 && f.fn->radius_filtered_input);
 }
