@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflamegpu2_b200.so")
+LIB_PATH = os.environ.get("FGB_KERNELS_LIB") or os.path.join(_HERE, "lib", "libflamegpu2_b200.so")  # override: A/B builds
 
 FGB_MAX_VARS = 32
 FGB_BUILD_DEFAULT = 0
@@ -73,6 +73,7 @@ SIGNATURES = {
     "fgb_slab_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong,
                                      C.c_void_p, C.c_uint, C.c_void_p]),
     "fgb_spatial_destroy": (C.c_int, [C.c_void_p]),
+    "fgb_spatial_use_pbm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fgb_spatial_get_metadata": (C.c_int, [C.c_void_p, C.POINTER(fgb_spatial_metadata), C.POINTER(C.c_uint)]),
     "fgb_spatial_metadata_device_ptr": (C.c_void_p, [C.c_void_p]),
     "fgb_spatial_bin_count": (C.c_uint, [C.c_void_p]),

@@ -2,6 +2,7 @@
 // Host launchers only: every entry point enqueues kernels on the caller's stream and returns.
 // There is no CPU fallback; without a CUDA device every call fails with FGB_ERR_NO_DEVICE.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -17,6 +18,10 @@
 #include "fgb_slab.cuh"
 
 using namespace fgb;
+
+#ifndef FGB_COMPACT_BULK_DEFAULT
+#define FGB_COMPACT_BULK_DEFAULT 0
+#endif
 
 namespace {
 
@@ -112,7 +117,7 @@ void launch_scan_scatter(fgb_spatial *sp, unsigned int n, const unsigned int *d_
   uint32_t *wl = static_cast<uint32_t *>(sp->tile_mode.p);
   k_scan_scatter<IDX_ONLY><<<scan_tiles + tiles, kBinThreads, 0, st>>>(sp->d_hist, sp->md.PBM, sp->bin_count, sp->d_state, scan_tiles, keys, n,
                                                                        d_n, vt, perm, wl, sp->d_ctrl);
-  const unsigned int sgrid = std::min<unsigned int>(tiles, 2u * kNumSMs);
+  const unsigned int sgrid = std::min<unsigned int>(tiles, 4u * kNumSMs);  // 46 KB of shared memory per block: 4 per SM
   if (vec)
     k_bin_scatter_staged<true, IDX_ONLY><<<sgrid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, wl, sp->d_ctrl);
   else
@@ -456,7 +461,7 @@ fgb_status fgb_bucket_get_bounds(const fgb_spatial *sp, int *min_key, int *max_k
 fgb_status fgb_spatial_destroy(fgb_spatial *sp) {
   if (!sp) return FGB_OK;
   if (sp->d_hist) cudaFree(sp->d_hist);
-  if (sp->md.PBM) cudaFree(sp->md.PBM);
+  if (sp->md.PBM && !sp->pbm_external) cudaFree(sp->md.PBM);
   if (sp->d_state) cudaFree(sp->d_state);
   if (sp->d_md) cudaFree(sp->d_md);
   if (sp->d_ctrl) cudaFree(sp->d_ctrl);
@@ -476,6 +481,16 @@ fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata 
 }
 
 unsigned int fgb_spatial_bin_count(const fgb_spatial *sp) { return sp ? sp->bin_count : 0u; }
+
+fgb_status fgb_spatial_use_pbm(fgb_spatial *sp, unsigned int *pbm) {
+  if (!sp || !pbm) return FGB_ERR_INVALID_ARG;
+  FGB_CHECK(cudaDeviceSynchronize());
+  if (sp->md.PBM && !sp->pbm_external) cudaFree(sp->md.PBM);
+  sp->md.PBM = pbm;
+  sp->pbm_external = true;
+  FGB_CHECK(cudaMemcpy(sp->d_md, &sp->md, sizeof(sp->md), cudaMemcpyHostToDevice));
+  return FGB_OK;
+}
 
 const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp) { return sp ? sp->d_md : nullptr; }
 
@@ -750,8 +765,17 @@ fgb_status fgb_compact_limited(fgb_ctx *ctx, unsigned int stream_id, const unsig
   if (r) return r;
   unsigned long long *state = static_cast<unsigned long long *>(s.tile_state.p);
   uint32_t *done = static_cast<uint32_t *>(s.ctrl.p) + 1;
-  k_compact<<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state, done,
-                                           d_out_count, d_out_total);
+  // bulk-copy write-out (fgb_compact.cuh) needs 16-byte aligned output arrays; FGB_COMPACT_BULK=0/1 overrides for A/B runs
+  static const int bulk_env = [] {
+    const char *e = std::getenv("FGB_COMPACT_BULK");
+    return e ? std::atoi(e) : FGB_COMPACT_BULK_DEFAULT;
+  }();
+  if (bulk_env && vars_out_aligned(vars, nvars))
+    k_compact<true><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state, done,
+                                                   d_out_count, d_out_total);
+  else
+    k_compact<false><<<tiles, kCmpThreads, 0, st>>>(flags, invert, n, d_n, keep_front, out_offset, d_out_offset, out_limit, vt, state, done,
+                                                    d_out_count, d_out_total);
   ctx->launches += 1;
   return launch_ok();
 }

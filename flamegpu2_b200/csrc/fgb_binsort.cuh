@@ -282,8 +282,11 @@ __device__ __forceinline__ void scan_tile_256x16(uint32_t *hist, uint32_t *out, 
   if (tile == 0 && threadIdx.x == 0) out[0] = 0u;
 }
 
+#ifndef FGB_SCATTER_MIN_BLOCKS
+#define FGB_SCATTER_MIN_BLOCKS 5  // 48 registers instead of 64, no spills
+#endif
 template <bool IDX_ONLY>
-__global__ void __launch_bounds__(kBinThreads) k_scan_scatter(uint32_t *hist, uint32_t *cursor, uint32_t bins,
+__global__ void __launch_bounds__(kBinThreads, FGB_SCATTER_MIN_BLOCKS) k_scan_scatter(uint32_t *hist, uint32_t *cursor, uint32_t bins,
                                                               unsigned long long *state, uint32_t scan_tiles,
                                                               const uint32_t *__restrict__ keys, uint32_t n_max,
                                                               const unsigned int *d_n, const __grid_constant__ VarTable vt,
@@ -346,7 +349,9 @@ __global__ void __launch_bounds__(kBinThreads) k_scan_scatter(uint32_t *hist, ui
     if (!grouped && threadIdx.x == 0) worklist[atomicAdd(ctrl + 3, 1u)] = tile;
   }
   if (tile0 < n && grouped) {
-    // claim: the first lane of every run adds the run's length to the bin's cursor (all atomics of a warp in flight)
+    // claim: the first lane of every run adds the run's length to the bin's cursor.  All eight rounds' atomics are
+    // issued before the first result is consumed (interleaved with the shuffles below, each round waited a full L2
+    // round trip for its atomic before the next one was issued: 8 serial round trips per tile)
     uint32_t dst[kTileItems];
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
@@ -355,15 +360,19 @@ __global__ void __launch_bounds__(kBinThreads) k_scan_scatter(uint32_t *hist, ui
       const int first = 31 - __clz(static_cast<int>(below));           // lane that starts this lane's run
       const uint32_t above = head[r] & ~((2u << lane) - 1u);           // run heads above this lane
       const int next = above ? __ffs(static_cast<int>(above)) - 1 : 32;  // first lane of the next run
-      uint32_t base = 0;
+      dst[r] = 0;
       if (static_cast<int>(lane) == first && i < n) {
         // the run ends at the next head or at the end of the list
         const uint32_t last_valid = (n - (w0 + r * 32u)) < 32u ? n - (w0 + r * 32u) : 32u;
         const uint32_t len = (static_cast<uint32_t>(next) < last_valid ? static_cast<uint32_t>(next) : last_valid) - lane;
-        base = atomicAdd(cursor + k[r] + 1, len);
+        dst[r] = atomicAdd(cursor + k[r] + 1, len);
       }
-      base = __shfl_sync(0xFFFFFFFFu, base, first);
-      dst[r] = base + (lane - static_cast<uint32_t>(first));
+    }
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+      const uint32_t below = head[r] & ((2u << lane) - 1u);
+      const int first = 31 - __clz(static_cast<int>(below));
+      dst[r] = __shfl_sync(0xFFFFFFFFu, dst[r], first) + (lane - static_cast<uint32_t>(first));
     }
     if constexpr (IDX_ONLY) {
 #pragma unroll

@@ -274,8 +274,9 @@ struct fgb_spatial {
   fgb_spatial_metadata *d_md = nullptr;
   fgb::DevBuf perm;      // stable mode: permutation
   fgb::DevBuf worklist;  // stable mode: big bins
-  unsigned int *d_ctrl = nullptr;  // [0] = big-bin count
-  fgb::DevBuf tile_mode;           // per 2048-item tile: 1 = grouped (direct scatter), 0 = ungrouped (staged scatter)
+  unsigned int *d_ctrl = nullptr;  // [0] big-bin count, [1..3] k_scan_scatter (fgb_binsort.cuh)
+  bool pbm_external = false;       // md.PBM belongs to the caller (fgb_spatial_use_pbm)
+  fgb::DevBuf tile_mode;           // worklist of the ungrouped 2048-item tiles of the build in flight (staged scatter)
   fgb::DevBuf keys;                // bin of every item of the list being indexed (written once, by k_bin_keys or by the
                                    // list's writer: fgb_spatial_writer_args)
 };

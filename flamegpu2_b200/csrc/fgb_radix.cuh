@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(kRsThreads) k_sort_keys_hist(const float *__re
 
 // One digit pass.  keys_in/idx_in -> keys_out/idx_out, stable.  idx_in == NULL: index = position.
 // state: [tiles][digits] look-back words (2 flag bits | 30 value bits), all-zero on entry.
-__global__ void __launch_bounds__(kRsThreads) k_radix_onesweep(const uint32_t *__restrict__ keys_in,
+#ifndef FGB_ONESWEEP_MIN_BLOCKS
+#define FGB_ONESWEEP_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kRsThreads, FGB_ONESWEEP_MIN_BLOCKS) k_radix_onesweep(const uint32_t *__restrict__ keys_in,
                                                                const uint32_t *__restrict__ idx_in, uint32_t *keys_out,
                                                                uint32_t *idx_out, uint32_t n_max, const unsigned int *d_n,
                                                                int shift, int bits, uint32_t key_mask,

@@ -116,6 +116,11 @@ fgb_status fgb_spatial_get_metadata(const fgb_spatial *sp, fgb_spatial_metadata 
  * (include/flamegpu/runtime/messaging/MessageSpecialisationHandler.h:44) */
 const void *fgb_spatial_metadata_device_ptr(const fgb_spatial *sp);
 unsigned int fgb_spatial_bin_count(const fgb_spatial *sp);  /* bins of the (windowed) PBM */
+/* Drop-in use inside the reference: build into a PBM the CALLER owns -- the hd_data.PBM that
+ * MessageSpatial3D::CUDAModelHandler::allocateMetaDataDevicePtr allocated (MessageSpatial3D.cu:81-90, binCount + 1
+ * words) and that the reference's device MetaData already points at -- instead of the handler's own array, which
+ * is freed.  fgb_spatial_destroy then leaves `pbm` alone.  Synchronous. */
+fgb_status fgb_spatial_use_pbm(fgb_spatial *sp, unsigned int *pbm);
 
 /* Inspection helper (no reference counterpart: "The PBM is never stored on the host",
  * MessageSpatial3D.h:55-58): copies the bin_count+1 PBM entries to host memory after

@@ -10,6 +10,8 @@ import numpy as np
 MAGIC = 0x53424746
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SIM = os.path.join(ROOT, "oracle", "_ref", "ref_sim")
+# the reference with four method bodies replaced by integration/fgb_reference_shims.cu (oracle/ref_build/build_dropin.sh)
+REF_SIM_FGB = os.path.join(ROOT, "oracle", "_ref", "ref_sim_fgb")
 
 
 def write_state(path, columns):
@@ -46,12 +48,16 @@ def have_ref():
     return os.path.exists(REF_SIM) and os.access(REF_SIM, os.X_OK)
 
 
+def have_dropin():
+    return have_ref() and os.path.exists(REF_SIM_FGB) and os.access(REF_SIM_FGB, os.X_OK)
+
+
 def run_ref(model, params, in_state, out_prefix, steps=1, warmup=0, dump_messages=None, timeout=600, pops=None, dumps=None,
-            dump_steps=False):
+            dump_steps=False, binary=None):
     """Runs the reference's CUDA build; returns the parsed JSON line it prints.
     in_state: state file of the model's main agent (or None); pops: [(agent, state, path)] further populations;
     dumps: [(agent, state)] -> <out_prefix>.<agent>.<state>.bin; dump_steps: <out_prefix>.s<k>.<agent>.bin after each step."""
-    cmd = [REF_SIM, "--model", model, "--params", ",".join(f"{k}={v}" for k, v in params.items()), "--out",
+    cmd = [binary or REF_SIM, "--model", model, "--params", ",".join(f"{k}={v}" for k, v in params.items()), "--out",
            out_prefix, "--steps", str(steps), "--warmup", str(warmup), "--quiet"]
     if in_state:
         cmd += ["--in", in_state]

@@ -13,11 +13,20 @@ ap.add_argument("--iter-mode", type=int, default=0)
 ap.add_argument("--graphs", type=int, default=0)
 ap.add_argument("--times", action="store_true")
 ap.add_argument("--extra", default="")
+ap.add_argument("--cross", type=float, default=0.0, help="> 0: box [0,cross)^2 x [0,depth) at density 1 instead of the cube of --n agents")
+ap.add_argument("--depth", type=float, default=64.0)
 a = ap.parse_args()
-L = float(np.floor(np.cbrt(float(a.n)) + 1e-6))
 rng = np.random.default_rng(0)
-x, y, z = [rng.uniform(0.0, L, a.n).astype(np.float32) for _ in range(3)]
 kw = dict(kv.split("=") for kv in a.extra.split(",") if kv)
+if a.cross > 0:
+    L = a.cross
+    a.n = int(round(a.cross * a.cross * a.depth))
+    x, y = [rng.uniform(0.0, L, a.n).astype(np.float32) for _ in range(2)]
+    z = rng.uniform(0.0, a.depth, a.n).astype(np.float32)
+    kw["env_max_z"] = a.depth
+else:
+    L = float(np.floor(np.cbrt(float(a.n)) + 1e-6))
+    x, y, z = [rng.uniform(0.0, L, a.n).astype(np.float32) for _ in range(3)]
 s = fsim.Simulation("circles", env_max=L, radius=2.0, repulse=0.05, graphs=a.graphs, iter_mode=a.iter_mode, timing=1 if a.times else 0, **kw)
 s.set_population("Circle", {"x": x, "y": y, "z": z})
 s.step(a.steps)
