@@ -82,19 +82,13 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
   uint32_t keptbits = 0;  // bit r: this lane's item of round r is kept
 #pragma unroll
   for (int r = 0; r < kCmpItems; ++r) keptbits |= ((bal[r] >> lane) & 1u) << r;
-  const bool first4 = vt.n > 0 && vt.len[0] == 4, second4 = vt.n > 1 && vt.len[1] == 4;
-  uint32_t val0[kCmpItems], val1[kCmpItems];
+  const bool first4 = vt.n > 0 && vt.len[0] == 4;
+  uint32_t val0[kCmpItems];
   if (first4) {
     const uint32_t *in0 = reinterpret_cast<const uint32_t *>(vt.in[0]);
 #pragma unroll
     for (int r = 0; r < kCmpItems; ++r)
       if (keptbits & (1u << r)) val0[r] = ld_stream_u32(in0 + w0 + r * 32u + lane);
-  }
-  if (second4) {  // two variables in flight while the block waits for its prefix (ncu: 24 % of the stall samples sat there)
-    const uint32_t *in1 = reinterpret_cast<const uint32_t *>(vt.in[1]);
-#pragma unroll
-    for (int r = 0; r < kCmpItems; ++r)
-      if (keptbits & (1u << r)) val1[r] = ld_stream_u32(in1 + w0 + r * 32u + lane);
   }
   if (lane == 0) s_warp[warp] = wcount;
   __syncthreads();
@@ -121,16 +115,17 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
   }
   __syncthreads();
   const uint32_t tile_excl = s_excl;
-  // ---- self-clean the look-back words.  This block will not read another block's word again, so thread 0 takes the
-  // block's arrival ticket now and looks at the result only at the very end: the atomic's round trip hides behind the
-  // payload move and no other warp waits for it.  Release/acquire around the counter: this block's st_state() words
-  // must be visible before its arrival is, and the block that sees the last arrival must observe every such word before
-  // it overwrites them (otherwise a zero could land first and a stale {inclusive|value} word would survive into the
-  // next launch).
-  uint32_t ticket = 0;
+  // ---- self-clean the look-back words.  This block will not read another block's word again, so thread 0 counts the
+  // block as arrived now, with a fire-and-forget RED (no result, no register, nobody waits), and only looks at the
+  // counter at the very end of the kernel: a block that then sees every block arrived knows that every look-back has
+  // finished and re-zeroes the words with its first warp.  The block whose RED came last is guaranteed to see the full
+  // count (unless an earlier finisher already cleaned up and reset it); several late finishers may all clean, which is
+  // idempotent.  Release/acquire around the counter: this block's st_state() words must be visible before its arrival
+  // is, and a cleaning block must observe every such word before it overwrites them (otherwise a zero could land first
+  // and a stale {inclusive|value} word would survive into the next launch).
   if (threadIdx.x == 0) {
     __threadfence();
-    ticket = atomicAdd(done, 1u);
+    atomicAdd(done, 1u);
   }
   if (last_tile && threadIdx.x == 0) {
     if (d_out_count) *d_out_count = tile_excl + agg;
@@ -151,14 +146,12 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
       if (((bal[r] >> lane) & 1u) && rank[r] < out_limit) mine |= 1u << r;
       run += __popc(bal[r]);
     }
-    // software pipeline over the variables, two deep: the loads of variables v+1 and v+2 are in flight while v is stored
-    uint32_t cur[kCmpItems], nxt[kCmpItems];
+    // software pipeline over the variables: the loads of variable v+1 are in flight while v is stored.  (Two variables
+    // ahead needs 64 registers, i.e. 4 blocks per SM instead of 5: measured 281 us against 269 us at 16.8 M agents.)
+    uint32_t cur[kCmpItems];
 #pragma unroll
-    for (int r = 0; r < kCmpItems; ++r) {
-      cur[r] = val0[r];
-      nxt[r] = val1[r];
-    }
-    bool cur4 = first4, next4 = second4;
+    for (int r = 0; r < kCmpItems; ++r) cur[r] = val0[r];
+    bool cur4 = first4;
     // BULK: slot a + j of the staging buffer holds the tile's j-th kept item, a = destination index modulo 4, so the
     // 16-byte aligned middle [s_lo, s_hi) of the buffer and of the destination range coincide
     const uint32_t dst0 = out_offset + tile_excl;
@@ -167,13 +160,13 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
     const uint32_t s_lo = (a + 3u) & ~3u, s_hi = (a + nw) & ~3u;
     const bool bulk = BULK && s_hi > s_lo;
     for (uint32_t v = 0; v < vt.n; ++v) {
-      const bool after4 = v + 2 < vt.n && vt.len[v + 2] == 4;
-      uint32_t aft[kCmpItems];
-      if (after4) {
-        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 2]);
+      const bool next4 = v + 1 < vt.n && vt.len[v + 1] == 4;
+      uint32_t nxt[kCmpItems];
+      if (next4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[v + 1]);
 #pragma unroll
         for (int r = 0; r < kCmpItems; ++r)
-          if (mine & (1u << r)) aft[r] = ld_stream_u32(in + w0 + r * 32u + lane);
+          if (mine & (1u << r)) nxt[r] = ld_stream_u32(in + w0 + r * 32u + lane);
       }
       if (BULK && cur4) {
         uint32_t *stage = s_stage[v & 1u];
@@ -209,20 +202,19 @@ k_compact(const uint32_t *__restrict__ flags, int invert, uint32_t n_max, const 
           if (mine & (1u << r)) copy_item(vt, v, w0 + r * 32u + lane, static_cast<size_t>(out_offset) + rank[r]);
       }
 #pragma unroll
-      for (int r = 0; r < kCmpItems; ++r) {
-        cur[r] = nxt[r];
-        nxt[r] = aft[r];
-      }
+      for (int r = 0; r < kCmpItems; ++r) cur[r] = nxt[r];
       cur4 = next4;
-      next4 = after4;
     }
   }
   if (BULK && threadIdx.x == 0) bulk_wait_all();  // the staging buffers must outlive the copies
   if (threadIdx.x < 32) {
-    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-    if (ticket == gridDim.x - 1) {  // every block is past its look-back: the first warp of the last one re-zeroes the words
+    uint32_t arrived = 0;
+    if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(arrived) : "l"(done) : "memory");
+    arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+    if (arrived == gridDim.x) {
       __threadfence();
       for (uint32_t t = threadIdx.x; t < gridDim.x; t += 32u) state[t] = 0ull;
+      __syncwarp();
       if (threadIdx.x == 0) *done = 0u;
     }
   }

@@ -771,6 +771,9 @@ class CUDASimulation {
     FGB_CUDA_THROW(cudaEventRecord(prof.back().e1, st));
   }
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> step_events;
+  std::vector<cudaEvent_t> event_pool;  // recycled timing events (take_event / harvest_step_events)
+  cudaEvent_t take_event();
+  void harvest_step_events(bool only_finished);
   std::vector<double> step_seconds;
   double elapsed_simulation = 0.0;
 

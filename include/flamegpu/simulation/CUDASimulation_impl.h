@@ -209,6 +209,9 @@ inline void CUDASimulation::destroy() {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
+  step_events.clear();
+  for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+  event_pool.clear();
   for (auto &l : layers)
     for (auto &f : l) {
       f.scratch_new.release();
@@ -1506,8 +1509,11 @@ inline bool CUDASimulation::step() {
   plan_step();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (config.timing) {
-    FGB_CUDA_THROW(cudaEventCreate(&e0));
-    FGB_CUDA_THROW(cudaEventCreate(&e1));
+    // events come from a pool and go back to it when their times are harvested (every 256 steps at the latest), so a
+    // long run neither creates two events per step nor keeps one pair per step alive
+    if (step_events.size() >= 256) harvest_step_events(/*only_finished=*/true);
+    e0 = take_event();
+    e1 = take_event();
     FGB_CUDA_THROW(cudaEventRecord(e0, main_stream));
   }
   if (cuda_config.useCUDAGraphs && !model_has_host_layers && !cuda_config.profile && !streamed.armed) {
@@ -1565,8 +1571,9 @@ inline bool CUDASimulation::step() {
   ++step_count;
   if (!model->step_functions.empty()) {
     // step functions see the finished step (reference CUDASimulation.cu:603-617 runs them inside step(), inside its
-    // per-step timer); their reductions are launched on the step's stream
-    FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+    // per-step timer).  Everything HostAPI reads from the device goes through main_stream (reductions, counts, agent
+    // data) and synchronises that stream itself when the value is handed to the host, so the step is NOT drained
+    // first: a reduction's kernel is queued right behind the step's graph and the GPU never idles for a launch latency
     for (auto sf : model->step_functions) sf(&host_api);
     flush_host_agents();
   }
@@ -1640,16 +1647,36 @@ inline void CUDASimulation::simulate() {
   if (config.timing) std::printf("Total Processing time: %.3f ms\n", elapsed_simulation * 1e3);
 }
 
-inline std::vector<double> CUDASimulation::getElapsedTimeSteps() {
-  if (initialised) FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+inline cudaEvent_t CUDASimulation::take_event() {
+  if (!event_pool.empty()) {
+    cudaEvent_t e = event_pool.back();
+    event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  FGB_CUDA_THROW(cudaEventCreate(&e));
+  return e;
+}
+
+// convert recorded (start, end) pairs into seconds, oldest first, and recycle the events; only_finished stops at the
+// first pair whose end event has not completed yet (never blocks)
+inline void CUDASimulation::harvest_step_events(bool only_finished) {
+  size_t done = 0;
   for (auto &e : step_events) {
+    if (only_finished && cudaEventQuery(e.second) != cudaSuccess) break;
     float ms = 0.f;
     FGB_CUDA_THROW(cudaEventElapsedTime(&ms, e.first, e.second));
     step_seconds.push_back(ms * 1e-3);
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
+    event_pool.push_back(e.first);
+    event_pool.push_back(e.second);
+    ++done;
   }
-  step_events.clear();
+  step_events.erase(step_events.begin(), step_events.begin() + static_cast<std::ptrdiff_t>(done));
+}
+
+inline std::vector<double> CUDASimulation::getElapsedTimeSteps() {
+  if (initialised) FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+  harvest_step_events(/*only_finished=*/false);
   return step_seconds;
 }
 
