@@ -69,6 +69,8 @@ SIGNATURES = {
     "fgb_slab_migrate_out": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                        C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "fgb_slab_pack_planes": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_slab_check_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
     "fgb_slab_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong,
                                      C.c_void_p, C.c_uint, C.c_void_p]),

@@ -569,7 +569,7 @@ fgb_status fgb_slab_migrate_out(fgb_ctx *ctx, unsigned int stream_id, const floa
   }
   if (n) k_slab_select<<<(n + 255) / 256, 256, 0, st>>>(pos, n, d_n, env_min, radius, grid_dim, lo_plane, hi_plane, capacity, sel, idx_lo, idx_hi);
   const unsigned int pgrid = std::max(1u, std::min((capacity + 255u) / 256u, 4u * kNumSMs));
-  k_slab_pack<<<dim3(pgrid, 2), 256, 0, st>>>(sel, idx_lo, idx_hi, capacity, vt_lo, vt_hi, peer_count_lo, peer_count_hi);
+  k_slab_pack<<<dim3(pgrid, 2), 256, 0, st>>>(sel, idx_lo, idx_hi, capacity, vt_lo, vt_hi, peer_count_lo, peer_count_hi, nullptr);
   k_slab_holes<<<1, 1024, 0, st>>>(sel, idx_lo, idx_hi, capacity, n, d_n, to, from, d_err);
   // in == out == the list's own columns: tail agents move into the holes
   VarTable vt_move = vt_list;
@@ -577,6 +577,40 @@ fgb_status fgb_slab_migrate_out(fgb_ctx *ctx, unsigned int stream_id, const floa
   const unsigned int fgrid = std::max(1u, std::min((2u * capacity + 255u) / 256u, 2u * kNumSMs));
   k_slab_fill<<<fgrid, 256, 0, st>>>(sel, to, from, vt_move, d_n_inout, done);
   ctx->launches += n ? 4 : 3;
+  return launch_ok();
+}
+
+fgb_status fgb_slab_pack_planes(fgb_ctx *ctx, unsigned int stream_id, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                                float radius, int grid_dim, int lo_plane, int hi_plane, unsigned int capacity, const fgb_var *list_vars,
+                                unsigned int nvars, void *const *peer_lo, void *const *peer_hi, unsigned int *peer_count_lo,
+                                unsigned int *peer_count_hi, void *stream) {
+  if (!ctx || stream_id >= FGB_MAX_STREAMS || (n && !pos) || capacity == 0 || (peer_lo && !peer_count_lo) || (peer_hi && !peer_count_hi))
+    return FGB_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fgb_stream_scratch &s = ctx->slot[stream_id];
+  const size_t head = 256;
+  int r = reserve_zeroed(s.slab, head + static_cast<size_t>(capacity) * 4 * 6);
+  if (r) return r;
+  char *base = static_cast<char *>(s.slab.p);
+  SlabSel *sel = reinterpret_cast<SlabSel *>(base);
+  unsigned int *done = reinterpret_cast<unsigned int *>(base + 64);
+  uint32_t *idx_lo = reinterpret_cast<uint32_t *>(base + head);
+  uint32_t *idx_hi = idx_lo + capacity;
+  VarTable vt_list, vt_lo{}, vt_hi{};
+  r = make_var_table(list_vars, nvars, &vt_list);
+  if (r) return r;
+  vt_lo.n = vt_hi.n = 0;
+  for (int side = 0; side < 2; ++side) {
+    void *const *peer = side == 0 ? peer_lo : peer_hi;
+    if (!peer) continue;
+    VarTable &vt = side == 0 ? vt_lo : vt_hi;
+    vt = vt_list;
+    for (unsigned int v = 0; v < nvars; ++v) vt.out[v] = static_cast<char *>(peer[v]);
+  }
+  if (n) k_slab_select<<<(n + 255) / 256, 256, 0, st>>>(pos, n, d_n, env_min, radius, grid_dim, lo_plane, hi_plane, capacity, sel, idx_lo, idx_hi);
+  const unsigned int pgrid = std::max(1u, std::min((capacity + 255u) / 256u, 4u * kNumSMs));
+  k_slab_pack<<<dim3(pgrid, 2), 256, 0, st>>>(sel, idx_lo, idx_hi, capacity, vt_lo, vt_hi, peer_count_lo, peer_count_hi, done);
+  ctx->launches += n ? 2 : 1;
   return launch_ok();
 }
 

@@ -180,20 +180,34 @@ __global__ void __launch_bounds__(256) k_slab_select(const float *__restrict__ p
 // blockIdx.y = side.  vt_lo / vt_hi: in = the list's columns, out = the neighbour's staging columns (NULL table n == 0:
 // no neighbour on that side; its leavers are still removed -- they left the global domain's decomposition range never
 // happens with clamped planes, so the lists are empty there).
-__global__ void __launch_bounds__(256) k_slab_pack(const SlabSel *sel, const uint32_t *__restrict__ idx_lo, const uint32_t *__restrict__ idx_hi,
+// reset_done != NULL (halo pack: nothing is removed, so no k_slab_fill follows): the last block to finish clears the
+// control block for the next exchange.
+__global__ void __launch_bounds__(256) k_slab_pack(SlabSel *sel, const uint32_t *__restrict__ idx_lo, const uint32_t *__restrict__ idx_hi,
                                                    uint32_t cap, const __grid_constant__ VarTable vt_lo, const __grid_constant__ VarTable vt_hi,
-                                                   unsigned int *peer_count_lo, unsigned int *peer_count_hi) {
+                                                   unsigned int *peer_count_lo, unsigned int *peer_count_hi, unsigned int *reset_done) {
   const int s = blockIdx.y;
   const VarTable &vt = s == 0 ? vt_lo : vt_hi;
   const uint32_t *idx = s == 0 ? idx_lo : idx_hi;
   unsigned int *peer_count = s == 0 ? peer_count_lo : peer_count_hi;
   const unsigned int total = sel->cnt[s];
   if (blockIdx.x == 0 && threadIdx.x == 0 && peer_count) *peer_count = total;  // the receiver flags total > cap as an overflow
-  if (vt.n == 0) return;
-  const unsigned int m = total < cap ? total : cap;
+  const unsigned int m = vt.n == 0 ? 0u : (total < cap ? total : cap);
   for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < m; j += gridDim.x * 256) {
     const uint32_t src = idx[j];
     for (uint32_t v = 0; v < vt.n; ++v) copy_item(vt, v, src, j);
+  }
+  if (reset_done) {
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(reset_done, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      sel->cnt[0] = sel->cnt[1] = 0u;
+      *reset_done = 0u;
+    }
   }
 }
 

@@ -48,7 +48,8 @@ __global__ void agent_function_wrapper(const __grid_constant__ detail::FunctionA
   // Run agents in the bin order of the input list when the scheduler provides it: lanes of a warp then
   // walk the same message strips (coalesced / broadcast loads).  Every per-agent slot (variables, scan
   // flags, message and new-agent slots) is addressed by the AGENT index, so results do not change.
-  const unsigned int agent = args.exec_perm ? __ldg(args.exec_perm + index) : offset + index;
+  const bool permuted = args.exec_perm && (!args.d_perm_limit || index < __ldg(args.d_perm_limit));
+  const unsigned int agent = permuted ? __ldg(args.exec_perm + index) : offset + index;
   if (agent >= n) return;  // a stale permutation must never address outside the list (the scheduler versions it)
   // message / new-agent slot: index among the executing agents, or -- for a mandatory output that the scheduler runs in
   // bin order -- the thread index, so that the list is WRITTEN bin-grouped (any bijection agent <-> slot is a legal

@@ -62,6 +62,7 @@ struct DevEnv {
 struct FunctionArgs {
   const unsigned int *d_count;  // device-resident agent count (<= bound)
   const unsigned int *exec_perm; // thread t runs agent exec_perm[t] (bin order); NULL: agent t
+  const unsigned int *d_perm_limit;  // non-NULL: exec_perm is valid for threads below this device word only, the rest run agent t
   const unsigned int *d_agent_offset;  // function condition: agents [0, *d_agent_offset) are disabled (NULL: 0)
   unsigned int bound;           // launch bound
   unsigned int first_thread;    // this launch covers threads [first_thread, last_thread) of the function (a function may be

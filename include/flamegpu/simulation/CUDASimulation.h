@@ -122,6 +122,14 @@ __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const 
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
+// limit of a partially valid tile-local permutation (DevList::perm_partial): mode 0 before the list changes
+// (limit = count, or min(limit, count) if it was partial already), mode 1 afterwards (min with the new count, rounded
+// down to whole 2048-item tiles)
+__global__ void k_perm_limit(unsigned int *limit, const unsigned int *count, int was_partial, int after) {
+  unsigned int l = (was_partial || after) ? (*limit < *count ? *limit : *count) : *count;
+  if (after) l &= ~2047u;
+  *limit = l;
+}
 // function condition helpers: words[active] = words[count] - words[failed]; death flags of the
 // disabled front are forced to "alive"; move flags select the executing survivors for a state change
 __global__ void k_sub_word(unsigned int *dst, const unsigned int *a, const unsigned int *b) { *dst = *a - *b; }
@@ -165,6 +173,11 @@ struct DevList {
   const unsigned int *cached_perm = nullptr;
   void touch() { ++order_version; }
   bool perm_valid() const { return cached_perm != nullptr && cached_perm_version == order_version; }
+  // Slab migration changes a few items of the list in place (holes filled from the tail, arrivals appended): the
+  // tile-local permutation stays a bijection on every 2048-item tile below min(count before, count after), so it is
+  // kept, valid up to the device word at control slot perm_limit_slot (threads beyond it run the identity).
+  bool perm_partial = false;
+  unsigned int perm_limit_slot = 0;
 
   void init(const VariableMap &vars, bool dbl) {
     double_buffered = dbl;

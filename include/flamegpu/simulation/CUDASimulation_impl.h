@@ -93,6 +93,7 @@ inline void CUDASimulation::initialise() {
       l.init(ap.second->variables, true);
       l.gen = &alloc_gen;
       l.count_slot = alloc_slot();
+      l.perm_limit_slot = alloc_slot();
     }
   }
   n_zero_slots = static_cast<unsigned int>(zero_slots.size());
@@ -499,7 +500,7 @@ inline std::vector<unsigned long long> CUDASimulation::snapshot_host_state() con
       s.push_back(reinterpret_cast<unsigned long long>(l.data[v]));
       s.push_back(reinterpret_cast<unsigned long long>(l.swap[v]));
     }
-    s.push_back(l.perm_valid() ? reinterpret_cast<unsigned long long>(l.cached_perm) : 0ull);
+    s.push_back(l.perm_valid() ? (reinterpret_cast<unsigned long long>(l.cached_perm) | (l.perm_partial ? 1ull : 0ull)) : 0ull);
   };
   for (const auto &a : agents) {
     s.push_back(a.second.pop_bound);
@@ -521,7 +522,8 @@ inline void CUDASimulation::restore_host_state(const std::vector<unsigned long l
       l.data[v] = reinterpret_cast<char *>(s[k++]);
       l.swap[v] = reinterpret_cast<char *>(s[k++]);
     }
-    l.cached_perm = reinterpret_cast<const unsigned int *>(s[k++]);
+    l.cached_perm = reinterpret_cast<const unsigned int *>(s[k] & ~1ull);
+    l.perm_partial = (s[k++] & 1ull) != 0;
     l.cached_perm_version = l.cached_perm ? l.order_version : 0ull;
   };
   for (auto &a : agents) {
@@ -657,7 +659,7 @@ inline void CUDASimulation::plan_step() {
     }
     for (auto &f : slab_flags) f.reserve(most);
     FGB_ABI_THROW(fgb_ctx_reserve(ctx, kSlabScratchSlot, most, 0));
-    FGB_ABI_THROW(fgb_slab_reserve(ctx, kSlabScratchSlot, std::max(slab.mig_cap, 1u)));
+    FGB_ABI_THROW(fgb_slab_reserve(ctx, kSlabScratchSlot, std::max(std::max(slab.mig_cap, slab.halo_cap), 1u)));
   }
   // reserving may have raised list bounds' capacity only; bounds themselves are untouched
 }
@@ -750,6 +752,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
                                       sorted_now ? FGB_BUILD_TILE_LOCAL : FGB_BUILD_DEFAULT, st));
     L.cached_perm = f.exec_perm.p;  // an output function of this list may reuse it while the list is unchanged
     L.cached_perm_version = L.order_version;
+    L.perm_partial = false;
     prof_end(st);
   }
 
@@ -808,6 +811,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       // build orders a bin by message slot.)
       if (cuda_config.binOrderedOutput && !cuda_config.stableMessageOrder && !bin_order && !conditional && !f.out_agent && L.perm_valid()) {
         a.exec_perm = L.cached_perm;
+        a.d_perm_limit = L.perm_partial ? slot_ptr(L.perm_limit_slot) : nullptr;
         a.slot_by_thread = 1u;
       }
       if (cuda_config.fusedIndexBuild) {
@@ -1385,12 +1389,21 @@ inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plan
   unsigned int *d_err = slot_ptr(slab.err_slot);
   const bool has[2] = {slab.rank > 0, slab.rank < slab.world - 1};
   const unsigned int nv = static_cast<unsigned int>(l.names.size());
-  if (n > 0 && !remove) {
+  // halo: a slab of >= 2 planes sends every boundary message to ONE side, so the messages are selected with one read of the
+  // position column and gathered by index (fgb_slab_pack_planes); a one-plane slab keeps the flag + compaction form
+  const bool gather_halo = !remove && slab.z1 - slab.z0 >= 2;
+  if (n > 0 && !remove && !gather_halo) {
     for (auto &f : slab_flags) f.reserve(n);
     FGB_ABI_THROW(fgb_plane_flags(ctx, reinterpret_cast<const float *>(l.data[S.pos_var]), n, d_n, G.md.min[slow], G.md.radius,
                                   static_cast<int>(G.md.grid_dim[slow]), lo_plane, hi_plane, slab_flags[0].p, nullptr, slab_flags[2].p, st));
   }
   unsigned long long *peer_flag[2] = {nullptr, nullptr};
+  // migration edits the agent list in place: a valid tile-local execution order survives below min(count before, after)
+  const bool keep_perm = remove && cuda_config.binOrderedOutput && l.perm_valid() && l.perm_limit_slot != 0;
+  if (keep_perm) {
+    detail::k_perm_limit<<<1, 1, 0, st>>>(slot_ptr(l.perm_limit_slot), d_n, l.perm_partial ? 1 : 0, 0);
+    ++own_launches;
+  }
   if (remove) {
     // migration: only a few agents leave per step, so the list is not rewritten: the leavers are gathered by index into the
     // neighbours' staging buffers and their holes are filled from the tail (fgb_slab_migrate_out)
@@ -1415,7 +1428,31 @@ inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plan
                                        has[0] ? peer_cols[0].data() : nullptr, has[1] ? peer_cols[1].data() : nullptr, peer_count[0], peer_count[1],
                                        d_n, d_err, st));
   }
-  for (int side = 0; side < 2 && !remove; ++side) {
+  if (gather_halo) {
+    std::vector<void *> peer_cols[2];
+    unsigned int *peer_count[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side) {
+      if (!has[side]) continue;
+      // I am the neighbour's OTHER side: what I send down arrives in rank-1's "from rank+1" buffer and vice versa
+      char *base = slab.peer[slab.rank + (side == 0 ? -1 : 1)];
+      const SlabStaging &g = S.st[side == 0 ? 1 : 0];
+      for (unsigned int v = 0; v < nv; ++v) peer_cols[side].push_back(base + g.var_off[v]);
+      peer_count[side] = reinterpret_cast<unsigned int *>(base + g.count_off);
+      peer_flag[side] = reinterpret_cast<unsigned long long *>(base + g.flag_off);
+    }
+    std::vector<fgb_var> cols(nv);
+    for (unsigned int v = 0; v < nv; ++v) {
+      cols[v].type_len = l.meta[v].bytes();
+      cols[v].in = l.data[v];
+      cols[v].out = l.data[v];
+    }
+    // without a neighbour on a side nothing is selected for it: the plane range is opened up (planes are clamped to the grid)
+    FGB_ABI_THROW(fgb_slab_pack_planes(ctx, kSlabScratchSlot, reinterpret_cast<const float *>(l.data[S.pos_var]), n, d_n, G.md.min[slow], G.md.radius,
+                                       static_cast<int>(G.md.grid_dim[slow]), has[0] ? lo_plane : 0, has[1] ? hi_plane : static_cast<int>(G.md.grid_dim[slow]),
+                                       S.capacity, cols.data(), nv, has[0] ? peer_cols[0].data() : nullptr, has[1] ? peer_cols[1].data() : nullptr,
+                                       peer_count[0], peer_count[1], st));
+  }
+  for (int side = 0; side < 2 && !remove && !gather_halo; ++side) {
     if (!has[side]) continue;
     // I am the neighbour's OTHER side: what I send down arrives in rank-1's "from rank+1" buffer and vice versa
     char *base = slab.peer[slab.rank + (side == 0 ? -1 : 1)];
@@ -1458,6 +1495,12 @@ inline void CUDASimulation::slab_exchange(SlabList &S, int lo_plane, int hi_plan
   // agent lists keep their (sticky) launch bound: fgb_slab_check_bound raises the error word if the population outgrows
   // it before the next slab_refresh_bounds()
   l.touch();
+  if (keep_perm) {
+    detail::k_perm_limit<<<1, 1, 0, st>>>(slot_ptr(l.perm_limit_slot), d_n, 1, 1);
+    ++own_launches;
+    l.cached_perm_version = l.order_version;
+    l.perm_partial = true;
+  }
 }
 
 // Re-read the list counts (one small copy + sync every slabRefreshPeriod steps) and re-centre the sticky launch bounds

@@ -338,6 +338,14 @@ fgb_status fgb_slab_migrate_out(fgb_ctx *ctx, unsigned int stream_id, const floa
                                 float radius, int grid_dim, int lo_plane, int hi_plane, unsigned int capacity, const fgb_var *list_vars,
                                 unsigned int nvars, void *const *peer_lo, void *const *peer_hi, unsigned int *peer_count_lo,
                                 unsigned int *peer_count_hi, unsigned int *d_n_inout, unsigned int *d_err, void *stream);
+/* The halo form of fgb_slab_migrate_out: the items in planes < lo_plane / >= hi_plane are COPIED to the neighbours' staging
+ * columns (and their counts to *peer_count_*); the list itself is left alone.  One read of the position column + a gather
+ * of the few selected items, instead of scan flags and two compactions over the whole list.  The receiver validates the
+ * count against its capacity (fgb_slab_wait).  An item can be sent to one side only: the slab must own >= 2 planes. */
+fgb_status fgb_slab_pack_planes(fgb_ctx *ctx, unsigned int stream_id, const float *pos, unsigned int n, const unsigned int *d_n, float env_min,
+                                float radius, int grid_dim, int lo_plane, int hi_plane, unsigned int capacity, const fgb_var *list_vars,
+                                unsigned int nvars, void *const *peer_lo, void *const *peer_hi, unsigned int *peer_count_lo,
+                                unsigned int *peer_count_hi, void *stream);
 fgb_status fgb_slab_signal(fgb_ctx *ctx, unsigned long long *peer_flag_lo, unsigned long long *peer_flag_hi, const unsigned int *d_epoch,
                            void *stream);
 fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const unsigned long long *flag_hi, const unsigned int *count_lo,

@@ -139,6 +139,16 @@ def run_check(rank, world, local, n_per_rank=100_000, planes_per_rank=23, radius
             # (the agents that stay keep their relative order except for the few tail agents that fill the holes of the
             #  leavers -- fgb_slab_migrate_out -- so `stayers_keep_list_order` is reported, not required)
         elif not fails:
+            # the last step's message lists (written through the execution order that survived the migrations of the
+            # earlier steps): over the planes each rank owns, every agent id exactly once
+            own_msgs = []
+            for g in gathered:
+                wl = g["pbm"].astype(np.int64)
+                a, b = int(wl[(g["z0"] - g["w0"]) * gxy]), int(wl[(g["z1"] - g["w0"]) * gxy])
+                own_msgs.append(g["mids"][a:b])
+            own_msgs = np.sort(np.concatenate(own_msgs))
+            if len(own_msgs) != n or not np.array_equal(own_msgs, ids):
+                fails.append(f"messages of the last step: {len(own_msgs)} in owned planes for {n} agents (lost or duplicated)")
             # free-running: summation-order differences are amplified by the dynamics; almost all agents must agree
             pos_in_ref = np.empty(n + 1, np.int64)
             pos_in_ref[rid] = np.arange(n)
