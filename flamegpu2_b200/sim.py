@@ -215,27 +215,3 @@ class Simulation:
         _check(lib().fgbm_circles_step_host(self.h, n, x.ctypes.data, y.ctypes.data, z.ctypes.data, drift.ctypes.data, steps,
                                             out["x"].ctypes.data, out["y"].ctypes.data, out["z"].ctypes.data,
                                             out["drift"].ctypes.data, out["id"].ctypes.data), "fgbm_circles_step_host")
-
-
-def smoke_check():
-    """One tiny Circles step on cuda:0 through the C++ API layer, checked against the CPU oracle."""
-    import sys
-
-    sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "tests"))
-    import oracle_py as orc
-
-    n, L = 4096, 16.0
-    rng = np.random.default_rng(1)
-    pos = [rng.uniform(0, L, n).astype(np.float32) for _ in range(3)]
-    sim = Simulation("circles", env_max=L, radius=2.0)
-    sim.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
-    sim.step(1)
-    ids = sim.get("Circle", "_id", np.uint32)
-    x = sim.get("Circle", "x", np.float32)
-    g = orc.Grid(3, (0, 0, 0), (L, L, L), 2.0)
-    i2, x2, y2, z2, d2, pbm = g.circles_step(np.arange(1, n + 1, dtype=np.uint32), pos[0], pos[1], pos[2],
-                                             np.zeros(n, np.float32), want_pbm=True)
-    assert np.array_equal(ids, i2), "agent order after the auto-sort must match the oracle bit-exactly"
-    assert np.array_equal(sim.message_pbm("location"), pbm), "PBM must match the oracle bit-exactly"
-    assert np.allclose(x, x2, rtol=1e-5, atol=1e-6), "agent positions differ from the oracle beyond tolerance"
-    sim.close()
