@@ -251,6 +251,15 @@ int fgbm_agent_reduce(void *h, const char *agent, const char *var, int op, char 
   });
 }
 
+// what the Circles example's Validation step function saw last (a sum<float>("drift") per step, examples/circles_model.cuh)
+int fgbm_circles_validation(double *last_total_drift, unsigned int *dropped, unsigned int *increased) {
+  const fgb_examples::CirclesValidationState &v = fgb_examples::circles_validation_state();
+  if (last_total_drift) *last_total_drift = static_cast<double>(v.prev_total_drift);
+  if (dropped) *dropped = v.dropped;
+  if (increased) *increased = v.increased;
+  return 0;
+}
+
 // HostAgentAPI::histogramEven (kind 'f' float, 'i' int, 'u' unsigned) into out[bins]
 int fgbm_agent_histogram(void *h, const char *agent, const char *var, char kind, unsigned int bins, double lower, double upper, unsigned int *out) {
   return guarded([&] {

@@ -122,6 +122,11 @@ __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const 
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
+// epoch of the prefetched reductions: the step counter AFTER the step, written to mapped host memory behind the results
+__global__ void k_publish_epoch(unsigned long long *mapped, const unsigned int *ctrl, unsigned int step_slot) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(mapped) = ctrl[step_slot];
+}
 // limit of a partially valid tile-local permutation (DevList::perm_partial): mode 0 before the list changes
 // (limit = count, or min(limit, count) if it was partial already), mode 1 afterwards (min with the new count, rounded
 // down to whole 2048-item tiles)
@@ -178,6 +183,7 @@ struct DevList {
   // kept, valid up to the device word at control slot perm_limit_slot (threads beyond it run the identity).
   bool perm_partial = false;
   unsigned int perm_limit_slot = 0;
+  bool cached_perm_global = false;  // the cached permutation orders the WHOLE list by bin (not inside 2048-item tiles)
 
   void init(const VariableMap &vars, bool dbl) {
     double_buffered = dbl;
@@ -501,6 +507,7 @@ class CUDASimulation {
   unsigned int getStepCounter() const { return step_count; }
   void resetStepCounter() {
     step_count = 0;
+    last_step_prefetched = 0;
     if (initialised) FGB_CUDA_THROW(cudaMemset(d_ctrl + kStepSlot, 0, 4));
   }
   // seconds per step (reference CUDASimulation.h:362); measured with CUDA events on the step stream
@@ -723,6 +730,21 @@ class CUDASimulation {
   std::vector<cudaEvent_t> join_events;
   cudaEvent_t fork_event = nullptr;
   void *d_reduce_out = nullptr;          // 8-byte result word of HostAgentAPI reductions
+  // Reductions a step function asked for are LEARNED and from the next step on recorded behind the step itself (inside
+  // its CUDA graph): their results and the step's epoch land in mapped pinned host memory, so the step function finds the
+  // value with a spin on one host word -- no kernel launch behind a drained stream, no D2H copy, no stream synchronise.
+  struct PrefetchedReduction {
+    std::string agent, state, variable;
+    int op = 0, dtype = 0;
+  };
+  std::vector<PrefetchedReduction> prefetch;
+  static constexpr unsigned int kMaxPrefetch = 32;
+  unsigned long long *h_prefetch = nullptr;  // [0] epoch = step counter after the step, [1 + k] result of prefetch[k]
+  unsigned long long *d_prefetch = nullptr;  // device alias of h_prefetch
+  unsigned int last_step_prefetched = 0;     // how many reductions the step that just ran has recorded
+  bool in_step_function = false;             // a prefetched value describes the lists as the step left them: step functions only
+  void record_prefetched_reductions(cudaStream_t st);
+  bool prefetched_result(const std::string &agent, const std::string &state, const std::string &variable, int op, int dtype, void *out, size_t bytes);
   void *d_user_reduce = nullptr;         // block partials + arrival counter of the user-functor reductions
   unsigned int *d_hist_out = nullptr;    // histogramEven counts
   unsigned int hist_cap = 0;
@@ -758,6 +780,7 @@ class CUDASimulation {
     std::vector<unsigned long long> key;
     cudaGraphExec_t exec = nullptr;
     unsigned long long launches = 0;
+    unsigned int prefetched = 0;  // reductions recorded behind the step (prefetch[0 .. prefetched))
     // host-side state after the step (pointer parity, bounds, flags) to restore on replay
     std::vector<unsigned long long> post_state;
   };

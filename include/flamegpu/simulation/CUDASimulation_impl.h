@@ -263,6 +263,9 @@ inline void CUDASimulation::destroy() {
   if (index_stream) cudaStreamDestroy(index_stream);
   if (d_reduce_out) cudaFree(d_reduce_out);
   d_reduce_out = nullptr;
+  if (h_prefetch) cudaFreeHost(h_prefetch);
+  h_prefetch = nullptr;
+  d_prefetch = nullptr;
   if (d_user_reduce) cudaFree(d_user_reduce);
   d_user_reduce = nullptr;
   if (d_hist_out) cudaFree(d_hist_out);
@@ -500,7 +503,7 @@ inline std::vector<unsigned long long> CUDASimulation::snapshot_host_state() con
       s.push_back(reinterpret_cast<unsigned long long>(l.data[v]));
       s.push_back(reinterpret_cast<unsigned long long>(l.swap[v]));
     }
-    s.push_back(l.perm_valid() ? (reinterpret_cast<unsigned long long>(l.cached_perm) | (l.perm_partial ? 1ull : 0ull)) : 0ull);
+    s.push_back(l.perm_valid() ? (reinterpret_cast<unsigned long long>(l.cached_perm) | (l.perm_partial ? 1ull : 0ull) | (l.cached_perm_global ? 2ull : 0ull)) : 0ull);
   };
   for (const auto &a : agents) {
     s.push_back(a.second.pop_bound);
@@ -522,8 +525,9 @@ inline void CUDASimulation::restore_host_state(const std::vector<unsigned long l
       l.data[v] = reinterpret_cast<char *>(s[k++]);
       l.swap[v] = reinterpret_cast<char *>(s[k++]);
     }
-    l.cached_perm = reinterpret_cast<const unsigned int *>(s[k] & ~1ull);
-    l.perm_partial = (s[k++] & 1ull) != 0;
+    l.cached_perm = reinterpret_cast<const unsigned int *>(s[k] & ~3ull);
+    l.perm_partial = (s[k] & 1ull) != 0;
+    l.cached_perm_global = (s[k++] & 2ull) != 0;
     l.cached_perm_version = l.cached_perm ? l.order_version : 0ull;
   };
   for (auto &a : agents) {
@@ -551,6 +555,7 @@ inline std::vector<unsigned long long> CUDASimulation::graph_key() const {
       ++bit;
     }
   k.push_back(sort_bits);
+  k.push_back(prefetch.size());  // reductions recorded behind the step (record_prefetched_reductions)
   k.push_back((cuda_config.stableMessageOrder ? 1ull : 0ull) | (cuda_config.trueSpatialSortKey ? 2ull : 0ull) |
               (cuda_config.binOrderExecution ? 4ull : 0ull) | (cuda_config.overlapIndexBuild ? 8ull : 0ull) |
               (cuda_config.tileLocalExecOrder ? 16ull : 0ull) | (cuda_config.fusedIndexBuild ? 32ull : 0ull) |
@@ -608,6 +613,8 @@ inline void CUDASimulation::plan_step() {
         f.exec_perm.reserve(n);
         FGB_ABI_THROW(fgb_spatial_reserve(f.exec_binner, n));
       }
+      // a spatial writer may need its own tile-local order (run_function step 3: the reader's order was a global one)
+      if (f.msg_out && f.msg_out->spatial && !f.msg_out->bucket && !f.exec_binner && cuda_config.binOrderedOutput) f.exec_perm.reserve(n);
       if (f.msg_out) {
         detail::DevList &O = f.msg_out->list;
         unsigned int &ob = bound_of(O);
@@ -753,6 +760,7 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
     L.cached_perm = f.exec_perm.p;  // an output function of this list may reuse it while the list is unchanged
     L.cached_perm_version = L.order_version;
     L.perm_partial = false;
+    L.cached_perm_global = !sorted_now;
     prof_end(st);
   }
 
@@ -810,9 +818,24 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
       // (Not with stableMessageOrder: the permutation's order inside a bin is atomic-arrival order, and the stable
       // build orders a bin by message slot.)
       if (cuda_config.binOrderedOutput && !cuda_config.stableMessageOrder && !bin_order && !conditional && !f.out_agent && L.perm_valid()) {
-        a.exec_perm = L.cached_perm;
-        a.d_perm_limit = L.perm_partial ? slot_ptr(L.perm_limit_slot) : nullptr;
-        a.slot_by_thread = 1u;
+        const int ix = L.index_of("x"), iy = L.index_of("y"), iz = MO.desc->dims() == 3 ? L.index_of("z") : -1;
+        if (!L.cached_perm_global) {
+          a.exec_perm = L.cached_perm;
+          a.d_perm_limit = L.perm_partial ? slot_ptr(L.perm_limit_slot) : nullptr;
+          a.slot_by_thread = 1u;
+        } else if (n > 0 && ix >= 0 && iy >= 0 && (MO.desc->dims() == 2 || iz >= 0)) {
+          // the reader ran in GLOBAL bin order (deep grids, or a step without the auto sort): reading the agents through
+          // that permutation is a random gather over the whole list (16.8 M agents: 983 us against 221 us).  Grouping inside
+          // 2048-agent tiles is all the scatter needs to find runs, so the writer gets its own tile-local order
+          // (one k_group_tile pass over the positions; the heuristic assumes the model's location variables are x, y, z).
+          f.exec_perm.reserve(n);
+          FGB_ABI_THROW(fgb_bin_permutation(MO.spatial, n, d_n, reinterpret_cast<const float *>(L.data[ix]),
+                                            reinterpret_cast<const float *>(L.data[iy]),
+                                            iz >= 0 ? reinterpret_cast<const float *>(L.data[iz]) : nullptr, f.exec_perm.p,
+                                            FGB_BUILD_TILE_LOCAL, st));
+          a.exec_perm = f.exec_perm.p;
+          a.slot_by_thread = 1u;
+        }
       }
       if (cuda_config.fusedIndexBuild) {
         if (MO.hist_dirty)  // keyed by an earlier writer but never built: start from a clean histogram
@@ -1130,6 +1153,59 @@ inline void CUDASimulation::record_step(cudaStream_t main) {
   for (auto &m : messages) m.second.truncate = true;  // reference CUDASimulation.cu:599-601
   record_layers(main, 0, layers.size());
   record_end_of_step(main);
+  record_prefetched_reductions(main);
+}
+
+// The reductions the model's step functions are known to ask for, recorded behind the step (so inside its graph); their
+// 8-byte results go straight to mapped pinned host memory, followed by the step's epoch.
+inline void CUDASimulation::record_prefetched_reductions(cudaStream_t st) {
+  last_step_prefetched = 0;
+  if (prefetch.empty() || slab.enabled || model->step_functions.empty()) return;
+  if (!h_prefetch) return;  // allocated when the first reduction is learned (never during capture)
+  for (const PrefetchedReduction &r : prefetch) {
+    detail::DevList &l = state_list(r.agent, r.state);
+    const int i = l.index_of(r.variable);
+    FGB_ABI_THROW(fgb_reduce(ctx, 0, r.op, r.dtype, l.data[i], l.bound, slot_ptr(l.count_slot), d_prefetch + 1 + last_step_prefetched, st));
+    ++last_step_prefetched;
+  }
+  detail::k_publish_epoch<<<1, 1, 0, st>>>(d_prefetch, d_ctrl, kStepSlot);
+  ++own_launches;
+}
+
+// true: *out holds the result that the step which just ran has left for (agent, state, variable, op, dtype).  false: not
+// recorded with that step; the request is remembered so that the following steps record it.
+inline bool CUDASimulation::prefetched_result(const std::string &agent, const std::string &state, const std::string &variable, int op, int dtype,
+                                              void *out, size_t bytes) {
+  if (slab.enabled) return false;
+  size_t k = 0;
+  for (; k < prefetch.size(); ++k) {
+    const PrefetchedReduction &r = prefetch[k];
+    if (r.op == op && r.dtype == dtype && r.variable == variable && r.agent == agent && r.state == state) break;
+  }
+  if (k == prefetch.size()) {
+    if (prefetch.size() < kMaxPrefetch) {
+      if (!h_prefetch) {
+        FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+        FGB_CUDA_THROW(cudaHostAlloc(&h_prefetch, (1 + kMaxPrefetch) * sizeof(unsigned long long), cudaHostAllocMapped));
+        std::memset(h_prefetch, 0xFF, (1 + kMaxPrefetch) * sizeof(unsigned long long));
+        FGB_CUDA_THROW(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_prefetch), h_prefetch, 0));
+      }
+      prefetch.push_back(PrefetchedReduction{agent, state, variable, op, dtype});
+    }
+    return false;
+  }
+  if (k >= last_step_prefetched) return false;
+  // the step (graph) that just ran publishes its epoch behind the results: spin on the host word; should the epoch not
+  // show up (it always does unless the step failed), drain the stream and report the error through the normal path
+  volatile unsigned long long *epoch = h_prefetch;
+  for (unsigned long long spins = 0; *epoch != step_count; ++spins) {
+    if ((spins & 0xFFFFFull) == 0xFFFFFull) {
+      FGB_CUDA_THROW(cudaStreamSynchronize(main_stream));
+      if (*epoch != step_count) return false;
+    }
+  }
+  std::memcpy(out, const_cast<const unsigned long long *>(h_prefetch) + 1 + k, bytes);
+  return true;
 }
 
 // ---- phase-wise execution for the multi-GPU slab driver (eager; exchanges happen between phases) ----
@@ -1595,6 +1671,7 @@ inline bool CUDASimulation::step() {
       FGB_CUDA_THROW(cudaGraphInstantiate(&g.exec, graph, 0));
       cudaGraphDestroy(graph);
       g.launches = getLaunchCount() - l0;
+      g.prefetched = last_step_prefetched;
       g.post_state = snapshot_host_state();
       if (graphs.size() >= 64) {  // bounded cache
         cudaGraphExecDestroy(graphs.front().exec);
@@ -1605,6 +1682,7 @@ inline bool CUDASimulation::step() {
     } else {
       restore_host_state(hit->post_state);
       own_launches += hit->launches;
+      last_step_prefetched = hit->prefetched;
     }
     FGB_CUDA_THROW(cudaGraphLaunch(hit->exec, main_stream));
   } else {
@@ -1617,7 +1695,14 @@ inline bool CUDASimulation::step() {
     // per-step timer).  Everything HostAPI reads from the device goes through main_stream (reductions, counts, agent
     // data) and synchronises that stream itself when the value is handed to the host, so the step is NOT drained
     // first: a reduction's kernel is queued right behind the step's graph and the GPU never idles for a launch latency
-    for (auto sf : model->step_functions) sf(&host_api);
+    in_step_function = true;
+    try {
+      for (auto sf : model->step_functions) sf(&host_api);
+    } catch (...) {
+      in_step_function = false;
+      throw;
+    }
+    in_step_function = false;
     flush_host_agents();
   }
   if (config.timing) {
@@ -1843,10 +1928,14 @@ inline R HostAgentAPI::reduce(const std::string &variable, int op) {
   const int i = l.index_of(variable);
   if (i < 0) throw exception::InvalidAgentVar("agent '" + agent + "' has no variable '" + variable + "'");
   if (l.meta[i].type != std::type_index(typeid(T)) || l.meta[i].elements != 1) throw exception::InvalidVarType("wrong type for '" + variable + "'");
+  R r{};
+  static_assert(sizeof(R) <= 8, "reduction results travel in an 8-byte slot");
+  // recorded behind the step that just ran (learned from an earlier step's step function)?  then the value is already in
+  // mapped host memory; the request is valid only for the list as the step left it
+  if (sim->in_step_function && sim->prefetched_result(agent, state, variable, op, detail::reduce_dtype<T>::value, &r, sizeof(R))) return r;
   FGB_ABI_THROW(fgb_reduce(sim->ctx, 0, op, detail::reduce_dtype<T>::value, l.data[i], l.bound, sim->slot_ptr(l.count_slot),
                            sim->d_reduce_out, sim->main_stream));
   FGB_SLAB_FOLD(R, op);
-  R r{};
   FGB_CUDA_THROW(cudaMemcpyAsync(&r, sim->d_reduce_out, sizeof(R), cudaMemcpyDeviceToHost, sim->main_stream));
   FGB_CUDA_THROW(cudaStreamSynchronize(sim->main_stream));
   return r;

@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-ref", action="store_true")
-    ap.add_argument("--iter-mode", type=int, default=0, help="1: opt-in radius-filtered iterator")
+    ap.add_argument("--iter-mode", type=int, default=-1, help="-1 per function as the model declares (default), 0 reference order everywhere, 1 radius-filtered everywhere")
     args = ap.parse_args()
     for name, cfg in CONFIGS.items():
         if (args.only and name != args.only) or (not args.only and name == "stress_4m"):

@@ -399,6 +399,35 @@ def test_host_agent_reductions():
     s.close()
 
 
+@pytest.mark.parametrize("graphs", [1, 0])
+def test_step_function_reduction_recorded_behind_the_step(graphs):
+    # The Circles example's Validation step function sums "drift" every step.  From the second step on that reduction is
+    # recorded behind the step itself (inside its CUDA graph) and its result reaches the step function through mapped
+    # host memory: the value must be the sum over the list exactly as that step left it, every step.
+    import ctypes as C
+
+    from flamegpu2_b200 import sim as fsim
+
+    L = fsim.lib()
+    L.fgbm_circles_validation.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    n, Lx = 60000, 39.0
+    pos = _circles_pop(n, Lx, seed=5)
+    s = _sim("circles", env_max=Lx, radius=2.0, graphs=graphs, validation=1)
+    s.set_population("Circle", {"x": pos[0], "y": pos[1], "z": pos[2]})
+    tot, d0, i0 = C.c_double(), C.c_uint(), C.c_uint()
+    L.fgbm_circles_validation(C.byref(tot), C.byref(d0), C.byref(i0))
+    seen = d0.value + i0.value
+    for k in range(7):
+        s.step(1)
+        d, i = C.c_uint(), C.c_uint()
+        L.fgbm_circles_validation(C.byref(tot), C.byref(d), C.byref(i))
+        assert d.value + i.value == seen + k + 1, "the step function ran once per step"
+        drift = s.get("Circle", "drift", np.float32)
+        ref = float(drift.astype(np.float64).sum())
+        assert abs(tot.value - ref) <= 2e-6 * ref, (k, tot.value, ref)  # the step function keeps the sum as float
+    s.close()
+
+
 def test_true3d_sort_key_extension():
     # b200 extension: the intended x,y,z sort key (the reference's key collapses z, CUDASimulation.cu:487)
     n, L = 30000, 31.0
