@@ -255,7 +255,13 @@ inline void define_boids(flamegpu::ModelDescription &model, const BoidsParams &p
     agent.newVariable<float>("z");
     agent.newVariable<float>("fz");
     agent.newFunction("outputdata", boids3d_output).setMessageOutput("location");
-    agent.newFunction("inputdata", boids3d_input).setMessageInput("location");
+    flamegpu::AgentFunctionDescription in3 = agent.newFunction("inputdata", boids3d_input);
+    in3.setMessageInput("location");
+#ifdef FLAMEGPU2_B200
+    // b200 extension (no reference counterpart): `inputdata` tests `separation < INTERACTION_RADIUS` (== the message radius)
+    // itself, so it may be shown only the messages within the radius of its search origin
+    in3.setMessageInputRadiusFiltered(true);
+#endif
     model.newLayer().addAgentFunction(boids3d_output);
     model.newLayer().addAgentFunction(boids3d_input);
   } else {
@@ -267,7 +273,11 @@ inline void define_boids(flamegpu::ModelDescription &model, const BoidsParams &p
     message.newVariable<float>("fx");
     message.newVariable<float>("fy");
     agent.newFunction("outputdata", boids2d_output).setMessageOutput("location");
-    agent.newFunction("inputdata", boids2d_input).setMessageInput("location");
+    flamegpu::AgentFunctionDescription in2 = agent.newFunction("inputdata", boids2d_input);
+    in2.setMessageInput("location");
+#ifdef FLAMEGPU2_B200
+    in2.setMessageInputRadiusFiltered(true);
+#endif
     model.newLayer().addAgentFunction(boids2d_output);
     model.newLayer().addAgentFunction(boids2d_input);
   }

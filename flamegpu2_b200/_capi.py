@@ -72,7 +72,7 @@ SIGNATURES = {
     "fgb_slab_pack_planes": (C.c_int, [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                        C.c_uint, C.POINTER(fgb_var), C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fgb_slab_check_bound": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
-    "fgb_slab_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong,
+    "fgb_slab_allreduce": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_uint, C.c_void_p]),
     "fgb_spatial_destroy": (C.c_int, [C.c_void_p]),
     "fgb_spatial_use_pbm": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -622,8 +622,8 @@ fgb_status fgb_slab_check_bound(fgb_ctx *ctx, const unsigned int *d_count, unsig
 }
 
 fgb_status fgb_slab_allreduce(fgb_ctx *ctx, int op, int dtype, void *d_value_inout, void *const *mailboxes, int rank, int world,
-                              unsigned long long epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream) {
-  if (!ctx || !d_value_inout || !mailboxes || !d_err || world < 1 || world > kSlabMaxWorld || rank < 0 || rank >= world ||
+                              unsigned long long *d_epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream) {
+  if (!ctx || !d_value_inout || !mailboxes || !d_err || !d_epoch || world < 1 || world > kSlabMaxWorld || rank < 0 || rank >= world ||
       op < FGB_REDUCE_SUM || op > FGB_REDUCE_MAX || dtype < FGB_F32 || dtype > FGB_U64)
     return FGB_ERR_INVALID_ARG;
   SlabMailboxes mb{};
@@ -634,12 +634,12 @@ fgb_status fgb_slab_allreduce(fgb_ctx *ctx, int op, int dtype, void *d_value_ino
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned long long to = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
   switch (dtype) {
-    case FGB_F32: k_slab_allreduce<float><<<1, 32, 0, st>>>(static_cast<float *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
-    case FGB_F64: k_slab_allreduce<double><<<1, 32, 0, st>>>(static_cast<double *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
-    case FGB_I32: k_slab_allreduce<int><<<1, 32, 0, st>>>(static_cast<int *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
-    case FGB_U32: k_slab_allreduce<unsigned int><<<1, 32, 0, st>>>(static_cast<unsigned int *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
-    case FGB_I64: k_slab_allreduce<long long><<<1, 32, 0, st>>>(static_cast<long long *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
-    default: k_slab_allreduce<unsigned long long><<<1, 32, 0, st>>>(static_cast<unsigned long long *>(d_value_inout), mb, rank, world, op, epoch, d_err, to); break;
+    case FGB_F32: k_slab_allreduce<float><<<1, 32, 0, st>>>(static_cast<float *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
+    case FGB_F64: k_slab_allreduce<double><<<1, 32, 0, st>>>(static_cast<double *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
+    case FGB_I32: k_slab_allreduce<int><<<1, 32, 0, st>>>(static_cast<int *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
+    case FGB_U32: k_slab_allreduce<unsigned int><<<1, 32, 0, st>>>(static_cast<unsigned int *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
+    case FGB_I64: k_slab_allreduce<long long><<<1, 32, 0, st>>>(static_cast<long long *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
+    default: k_slab_allreduce<unsigned long long><<<1, 32, 0, st>>>(static_cast<unsigned long long *>(d_value_inout), mb, rank, world, op, d_epoch, d_err, to); break;
   }
   ctx->launches += 1;
   return launch_ok();

@@ -70,6 +70,8 @@ __global__ void k_slab_check_bound(const unsigned int *d_count, unsigned int bou
 // 2 (epoch parity) x world slots of {value bits, epoch}.  Lane r < world writes this rank's value into rank r's
 // slot [parity][rank], then waits for rank r's value in the local slot [parity][r]; lane 0 folds the world values
 // in RANK ORDER (every rank computes the identical result).  op: 0 sum, 1 min, 2 max; dtype as fgb_dtype.
+// Consecutive calls alternate the parity slot, so a rank can never overwrite a value its neighbour has not consumed
+// (it needs that neighbour's next contribution before it can get two calls ahead).
 struct SlabMailSlot {
   unsigned long long value;
   unsigned long long epoch;
@@ -86,10 +88,13 @@ __device__ __forceinline__ A slab_combine(A a, A b, int op) {
 
 template <typename A>
 __global__ void k_slab_allreduce(A *value_inout, const __grid_constant__ SlabMailboxes mb, int rank, int world, int op,
-                                 unsigned long long epoch, unsigned int *d_err, unsigned long long timeout_ns) {
+                                 unsigned long long *d_epoch, unsigned int *d_err, unsigned long long timeout_ns) {
   __shared__ A s_val[kSlabMaxWorld];
   __shared__ int s_ok;
   const int r = threadIdx.x;
+  // the epoch lives in a device word that every call advances by one (identically on every rank): the launch carries no
+  // host-side counter and can be replayed from a CUDA graph
+  const unsigned long long epoch = *d_epoch + 1ull;
   const int par = static_cast<int>(epoch & 1ull);
   if (r == 0) s_ok = 1;
   __syncwarp();
@@ -121,6 +126,7 @@ __global__ void k_slab_allreduce(A *value_inout, const __grid_constant__ SlabMai
     s_val[r] = v;
   }
   __syncwarp();
+  if (r == 0) *d_epoch = epoch;
   if (r == 0 && s_ok) {
     A acc = s_val[0];
     for (int i = 1; i < world; ++i) acc = slab_combine(acc, s_val[i], op);

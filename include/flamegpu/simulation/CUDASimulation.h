@@ -122,10 +122,14 @@ __global__ void k_end_of_step(unsigned int *ctrl, unsigned int step_slot, const 
   for (unsigned int i = threadIdx.x; i < n_zero; i += blockDim.x) ctrl[zero_slots[i]] = 0u;
 }
 __global__ void k_copy_word(unsigned int *dst, const unsigned int *src) { *dst = *src; }
-// epoch of the prefetched reductions: the step counter AFTER the step, written to mapped host memory behind the results
-__global__ void k_publish_epoch(unsigned long long *mapped, const unsigned int *ctrl, unsigned int step_slot) {
+// results of the reductions recorded behind a step, then (system fence) the step's epoch = the step counter AFTER the
+// step, to mapped host memory: mapped[0] epoch, mapped[1 + k] result k
+__global__ void k_publish_reductions(unsigned long long *mapped, const unsigned long long *vals, unsigned int count, const unsigned int *ctrl,
+                                     unsigned int step_slot) {
+  if (threadIdx.x < count) *reinterpret_cast<volatile unsigned long long *>(mapped + 1 + threadIdx.x) = vals[threadIdx.x];
   __threadfence_system();
-  *reinterpret_cast<volatile unsigned long long *>(mapped) = ctrl[step_slot];
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(mapped) = ctrl[step_slot];
 }
 // limit of a partially valid tile-local permutation (DevList::perm_partial): mode 0 before the list changes
 // (limit = count, or min(limit, count) if it was partial already), mode 1 afterwards (min with the new count, rounded
@@ -674,7 +678,6 @@ class CUDASimulation {
     std::vector<char *> peer;  // arena of every rank as mapped here (peer[rank] == arena)
     std::vector<SlabList> lists;  // [0] = the halo message list, then every agent state list that carries the position
     unsigned int epoch_slot = 0, err_slot = 0;
-    unsigned long long reduce_epoch = 0;
   } slab;
   struct Streamed {
     bool armed = false, chunked = false;
@@ -741,6 +744,8 @@ class CUDASimulation {
   static constexpr unsigned int kMaxPrefetch = 32;
   unsigned long long *h_prefetch = nullptr;  // [0] epoch = step counter after the step, [1 + k] result of prefetch[k]
   unsigned long long *d_prefetch = nullptr;  // device alias of h_prefetch
+  unsigned long long *d_prefetch_vals = nullptr;  // device-resident results (all-reduced in place under slabs) before they are published
+  unsigned long long *d_reduce_epoch = nullptr;   // device word: epoch of the slab all-reduce mailboxes (fgb_slab_allreduce)
   unsigned int last_step_prefetched = 0;     // how many reductions the step that just ran has recorded
   bool in_step_function = false;             // a prefetched value describes the lists as the step left them: step functions only
   void record_prefetched_reductions(cudaStream_t st);

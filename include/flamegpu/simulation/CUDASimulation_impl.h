@@ -30,6 +30,8 @@ inline void CUDASimulation::initialise() {
   FGB_CUDA_THROW(cudaEventCreateWithFlags(&index_done, cudaEventDisableTiming));
   FGB_CUDA_THROW(cudaStreamCreateWithFlags(&index_stream, cudaStreamNonBlocking));
   FGB_CUDA_THROW(cudaMalloc(&d_reduce_out, 8));
+  FGB_CUDA_THROW(cudaMalloc(&d_reduce_epoch, 8));
+  FGB_CUDA_THROW(cudaMemset(d_reduce_epoch, 0, 8));
   FGB_CUDA_THROW(cudaMalloc(&d_ctrl, kCtrlWords * 4));
   FGB_CUDA_THROW(cudaMemset(d_ctrl, 0, kCtrlWords * 4));
   next_slot = 1;
@@ -266,6 +268,10 @@ inline void CUDASimulation::destroy() {
   if (h_prefetch) cudaFreeHost(h_prefetch);
   h_prefetch = nullptr;
   d_prefetch = nullptr;
+  if (d_prefetch_vals) cudaFree(d_prefetch_vals);
+  d_prefetch_vals = nullptr;
+  if (d_reduce_epoch) cudaFree(d_reduce_epoch);
+  d_reduce_epoch = nullptr;
   if (d_user_reduce) cudaFree(d_user_reduce);
   d_user_reduce = nullptr;
   if (d_hist_out) cudaFree(d_hist_out);
@@ -1160,15 +1166,25 @@ inline void CUDASimulation::record_step(cudaStream_t main) {
 // 8-byte results go straight to mapped pinned host memory, followed by the step's epoch.
 inline void CUDASimulation::record_prefetched_reductions(cudaStream_t st) {
   last_step_prefetched = 0;
-  if (prefetch.empty() || slab.enabled || model->step_functions.empty()) return;
+  if (prefetch.empty() || model->step_functions.empty()) return;
   if (!h_prefetch) return;  // allocated when the first reduction is learned (never during capture)
   for (const PrefetchedReduction &r : prefetch) {
     detail::DevList &l = state_list(r.agent, r.state);
     const int i = l.index_of(r.variable);
-    FGB_ABI_THROW(fgb_reduce(ctx, 0, r.op, r.dtype, l.data[i], l.bound, slot_ptr(l.count_slot), d_prefetch + 1 + last_step_prefetched, st));
+    unsigned long long *d_val = d_prefetch_vals + last_step_prefetched;
+    FGB_ABI_THROW(fgb_reduce(ctx, 0, r.op, r.dtype, l.data[i], l.bound, slot_ptr(l.count_slot), d_val, st));
+    if (slab.enabled) {  // every rank holds a part of the population: fold the per-rank results (same sequence on every rank)
+      // sum<T> accumulates in the 8-byte type of T's kind, min / max keep T (fgb_reduce)
+      const int rdtype = r.op == FGB_REDUCE_SUM ? (r.dtype == FGB_F32 || r.dtype == FGB_F64 ? FGB_F64 : (r.dtype == FGB_I32 || r.dtype == FGB_I64 ? FGB_I64 : FGB_U64))
+                                                : r.dtype;
+      std::vector<void *> boxes(slab.world);
+      for (int k = 0; k < slab.world; ++k) boxes[k] = slab.peer[k] + slab.mail_off;
+      FGB_ABI_THROW(fgb_slab_allreduce(ctx, r.op, rdtype, d_val, boxes.data(), slab.rank, slab.world, d_reduce_epoch, slot_ptr(slab.err_slot),
+                                       cuda_config.slabTimeoutMs, st));
+    }
     ++last_step_prefetched;
   }
-  detail::k_publish_epoch<<<1, 1, 0, st>>>(d_prefetch, d_ctrl, kStepSlot);
+  detail::k_publish_reductions<<<1, 32, 0, st>>>(d_prefetch, d_prefetch_vals, last_step_prefetched, d_ctrl, kStepSlot);
   ++own_launches;
 }
 
@@ -1176,7 +1192,6 @@ inline void CUDASimulation::record_prefetched_reductions(cudaStream_t st) {
 // recorded with that step; the request is remembered so that the following steps record it.
 inline bool CUDASimulation::prefetched_result(const std::string &agent, const std::string &state, const std::string &variable, int op, int dtype,
                                               void *out, size_t bytes) {
-  if (slab.enabled) return false;
   size_t k = 0;
   for (; k < prefetch.size(); ++k) {
     const PrefetchedReduction &r = prefetch[k];
@@ -1189,6 +1204,7 @@ inline bool CUDASimulation::prefetched_result(const std::string &agent, const st
         FGB_CUDA_THROW(cudaHostAlloc(&h_prefetch, (1 + kMaxPrefetch) * sizeof(unsigned long long), cudaHostAllocMapped));
         std::memset(h_prefetch, 0xFF, (1 + kMaxPrefetch) * sizeof(unsigned long long));
         FGB_CUDA_THROW(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_prefetch), h_prefetch, 0));
+        FGB_CUDA_THROW(cudaMalloc(&d_prefetch_vals, kMaxPrefetch * sizeof(unsigned long long)));
       }
       prefetch.push_back(PrefetchedReduction{agent, state, variable, op, dtype});
     }
@@ -1603,7 +1619,7 @@ inline void CUDASimulation::slab_refresh_bounds() {
 inline void CUDASimulation::slab_allreduce(void *d_value, int dtype, int op) {
   std::vector<void *> boxes(slab.world);
   for (int r = 0; r < slab.world; ++r) boxes[r] = slab.peer[r] + slab.mail_off;
-  FGB_ABI_THROW(fgb_slab_allreduce(ctx, op, dtype, d_value, boxes.data(), slab.rank, slab.world, ++slab.reduce_epoch, slot_ptr(slab.err_slot),
+  FGB_ABI_THROW(fgb_slab_allreduce(ctx, op, dtype, d_value, boxes.data(), slab.rank, slab.world, d_reduce_epoch, slot_ptr(slab.err_slot),
                                    cuda_config.slabTimeoutMs, main_stream));
 }
 

@@ -322,8 +322,9 @@ fgb_status fgb_histogram_even(fgb_ctx *ctx, int dtype, const void *in, unsigned 
  *   fgb_slab_check_bound : *d_count > bound raises FGB_SLAB_ERR_BOUND (agents beyond a launch bound would not execute)
  *   fgb_slab_allreduce   : all-reduce (op: fgb_reduce_op, dtype: fgb_dtype of the 4/8-byte value) over per-rank
  *                     mailboxes (mailboxes[r] = rank r's array of 2 * world 16-byte slots, peer memory for r != rank);
- *                     folded in rank order, so every rank obtains the identical value; `epoch` must increase by one
- *                     per call on every rank
+ *                     folded in rank order, so every rank obtains the identical value; *d_epoch is a device word (zero
+ *                     before the first call) that every call advances by one, identically on every rank, so the launch is
+ *                     CUDA-graph replayable
  *   fgb_slab_migrate_out : removes the items of a list whose position `pos` lies in planes < lo_plane / >= hi_plane
  *                     (plane arithmetic of fgb_plane_flags) and writes them -- and their counts -- into the neighbours'
  *                     staging columns peer_lo[v] / peer_hi[v] (peer memory; NULL = no neighbour on that side).  Only the
@@ -353,7 +354,7 @@ fgb_status fgb_slab_wait(fgb_ctx *ctx, const unsigned long long *flag_lo, const 
                          unsigned int timeout_ms, void *stream);
 fgb_status fgb_slab_check_bound(fgb_ctx *ctx, const unsigned int *d_count, unsigned int bound, unsigned int *d_err, void *stream);
 fgb_status fgb_slab_allreduce(fgb_ctx *ctx, int op, int dtype, void *d_value_inout, void *const *mailboxes, int rank, int world,
-                              unsigned long long epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream);
+                              unsigned long long *d_epoch, unsigned int *d_err, unsigned int timeout_ms, void *stream);
 
 /* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
 unsigned long long fgb_launch_count(const fgb_ctx *ctx);

@@ -65,7 +65,15 @@ def run_check(rank, world, local, n_per_rank=100_000, planes_per_rank=23, radius
     mids = s.sim.message_variable("location", "id", np.uint32, int(pbm[-1]))
     pl = np.clip(np.floor(got["z"] / np.float32(radius)), 0, planes - 1).astype(np.int64)
     on_owner = bool(np.all((pl >= z0) & (pl < z1)))
-    mine_out = {"ids": got_id, "key": got_key, "pbm": pbm, "mids": mids, "on_owner": on_owner, "err": err, "z0": z0, "z1": z1, "w0": w0, "wc": wc}
+    # what the example's Validation step function saw in the last step: the GLOBAL sum of "drift" (all-reduced over the slabs)
+    import ctypes as C
+
+    lib = fsim.lib()
+    lib.fgbm_circles_validation.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    seen_total = C.c_double()
+    lib.fgbm_circles_validation(C.byref(seen_total), None, None)
+    mine_out = {"ids": got_id, "key": got_key, "pbm": pbm, "mids": mids, "on_owner": on_owner, "err": err, "z0": z0, "z1": z1, "w0": w0, "wc": wc,
+                "validation_total": float(seen_total.value)}
     mine_out.update(got)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine_out)
@@ -86,6 +94,10 @@ def run_check(rank, world, local, n_per_rank=100_000, planes_per_rank=23, radius
             fails.append(f"device error bits {[g['err'] for g in gathered]}")
         if not all(g["on_owner"] for g in gathered):
             fails.append("agents outside their rank's slab after migration")
+        global_drift = float(sum(np.asarray(g["drift"], np.float64).sum() for g in gathered))
+        for r, g in enumerate(gathered):
+            if abs(g["validation_total"] - global_drift) > 1e-5 * max(global_drift, 1e-30):
+                fails.append(f"rank {r}: the Validation step function saw total drift {g['validation_total']}, the slabs hold {global_drift}")
         all_ids = np.concatenate([g["ids"] for g in gathered])
         if len(all_ids) != n or not np.array_equal(np.sort(all_ids), ids):
             fails.append(f"ids lost or duplicated ({len(all_ids)} of {n})")
