@@ -47,6 +47,7 @@ RADIUS = 2.0
 REPULSE = 0.05
 S_AGENT = 24  # _auto_sort_bin_index,_id,drift,x,y,z  
 S_MSG = 16    # id,x,y,z
+PY_LOOP = False                  # --py-loop: N > 1 timed steps driven from Python (A/B against the single C++ call)
 NORTH_STAR_PER_GPU = 1 << 24     # 16.8 M agents per GPU
 NORTH_STAR_CROSS = 512.0         # 512 x 512 cross-section, 64 deep per GPU: 8 GPUs make the 512^3 box of configs[4]
 
@@ -179,6 +180,8 @@ def timed_run(box, rank, world, local, steps, warmup, flush, dist, **cfg):
     """Runs warmup + steps steps of `box`; returns (seconds of the timed steps: max over ranks, wall, sim facts)."""
     import torch
 
+    cfg_py_loop = PY_LOOP
+
     s, sl = make_sim(box, rank, world, local, timing=1, **cfg)
     s.set_population("Circle", box.population(rank))
     stream = torch.cuda.ExternalStream(s.stream, device=f"cuda:{local}")
@@ -198,12 +201,19 @@ def timed_run(box, rank, world, local, steps, warmup, flush, dist, **cfg):
         dist.barrier()
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:  # NVML queries take driver locks: one sampling rank is enough, the others would only add jitter to a coupled step
+        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(stream)
-    for _ in range(steps):
-        one_step()
+    if flush is None and not cfg_py_loop:
+        # one call: the K-step loop runs in C++ (CUDASimulation::step() K times).  The ranks of a slab run are coupled every
+        # step, so the slowest host of every step gates all of them; a Python loop adds its jitter (GIL hand-overs with the
+        # clock sampler thread) to every step of every rank
+        s.step(steps)
+    else:
+        for _ in range(steps):
+            one_step()
     ev1.record(stream)
     s.sync()
     torch.cuda.synchronize()
@@ -425,6 +435,7 @@ def main():
     ap.add_argument("--bin-order", type=int, default=1, help="run message-reading functions in bin order (b200 extension)")
     ap.add_argument("--fused-index", type=int, default=1)
     ap.add_argument("--ordered-output", type=int, default=1)
+    ap.add_argument("--py-loop", type=int, default=0, help="N > 1: drive the timed steps from a Python loop instead of one C++ call (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -446,6 +457,8 @@ def main():
 
     cfg = dict(stable=args.stable, true3d_sort=args.true3d_sort, bin_order=args.bin_order, iter_mode=args.iter_mode, overlap=args.overlap,
                tile_order=args.tile_order, block=args.block, fused_index=args.fused_index, ordered_output=args.ordered_output)
+    global PY_LOOP
+    PY_LOOP = bool(args.py_loop)
     n = args.agents_per_gpu
     box = Box.cube(n, world)
     flush = torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.int32, device=f"cuda:{local}") if world == 1 else None

@@ -705,6 +705,7 @@ class CUDASimulation {
   void slab_allreduce(void *d_value, int dtype, int op);
   void upload_environment();
   void plan_step();                         // reserve capacities for the coming step (may allocate)
+  std::vector<unsigned int> last_plan_sig;  // list bounds the last plan was made for (plan_step is skipped while they hold)
   void record_step(cudaStream_t main);      // enqueue one whole step
   void record_layers(cudaStream_t main, size_t first, size_t last);
   void record_end_of_step(cudaStream_t main);

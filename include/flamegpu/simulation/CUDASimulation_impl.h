@@ -595,6 +595,21 @@ inline int CUDASimulation::sort_geometry(const detail::FunctionRT &f, float mn[3
 // Reserve capacities for everything the coming step can produce (same bound arithmetic as
 // run_function, no launches).  Allocation is illegal during stream capture, so it happens here.
 inline void CUDASimulation::plan_step() {
+  // Reservations only grow and depend on nothing but the lists' bounds (and the model): when the bounds are what they were
+  // when the last plan was made, every buffer is still large enough and the walk below is skipped (host time between two
+  // steps is GPU idle time whenever a step function makes the host wait for the step).
+  {
+    std::vector<unsigned int> sig;
+    sig.reserve(16);
+    for (const auto &a : agents) {
+      sig.push_back(a.second.pop_bound);
+      for (const auto &st : a.second.states) sig.push_back(st.second.bound);
+    }
+    for (const auto &m : messages) sig.push_back(m.second.list.bound);
+    sig.push_back(cuda_config.binOrderedOutput ? 1u : 0u);
+    if (sig == last_plan_sig) return;
+    last_plan_sig.swap(sig);
+  }
   std::map<const detail::DevList *, unsigned int> b;  // running bounds
   auto bound_of = [&](const detail::DevList &l) -> unsigned int & {
     auto it = b.find(&l);
@@ -1639,7 +1654,9 @@ inline bool CUDASimulation::step() {
   if (env_dirty) upload_environment();
   if (slab.enabled) {
     if (!slab.connected) throw exception::InvalidArgument("slab decomposition: slabConnect() must be called before the first step");
-    if (step_count % std::max(1u, cuda_config.slabRefreshPeriod) == 0) slab_refresh_bounds();
+    // the launch bounds are re-centred from the device counts every slabRefreshPeriod steps -- and after each of the first
+    // steps, when the initial transient (the first migrations) settles, so that the one re-capture it causes happens early
+    if (step_count < 4 || step_count % std::max(1u, cuda_config.slabRefreshPeriod) == 0) slab_refresh_bounds();
   }
   plan_step();
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -30,7 +30,7 @@ for i in range(4 + a.steps):
         s.step_times()
 s.sync()
 t = s.step_times() * 1e3
-out = {"rank": rank, "agents": box.n_per_rank, "ms_per_step": float(t.mean())}
+out = {"rank": rank, "agents": box.n_per_rank, "ms_per_step": float(t.mean()), "series_us": [int(round(v * 1e3)) for v in t[:48]]}
 if a.profile:
     prof = s.profile()
     out["phases_us"] = {k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items() if v[1]}
