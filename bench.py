@@ -222,18 +222,23 @@ def timed_run(box, rank, world, local, steps, warmup, flush, dist, **cfg):
     if dist is not None:
         dist.barrier()
     per_step = s.step_times()
-    if world == 1:
-        dev_total = float(per_step.sum())  # per-step events: the L2 flush between steps is excluded
-    else:
-        dev_total = ev0.elapsed_time(ev1) * 1e-3  # the whole K-step region on the simulation stream (waits for neighbours included)
+    # The same clock at every N: the sum of this rank's per-step CUDA-event times (CUDASimulation::step() records an event
+    # pair around every step on the simulation stream, like the reference's getElapsedTimeSteps()), max over ranks.  Waits for
+    # neighbours (halo, migration, all-reduce) happen inside a step and are included; what lies BETWEEN two steps -- at N=1 the
+    # L2 flush, at every N the host's turn-around after a step function made it wait for the step -- is not.  The bracketed
+    # K-step region (everything between the first and the last event) is reported next to it as `region`.
+    dev_total = float(per_step.sum())
+    region = ev0.elapsed_time(ev1) * 1e-3
+    if world > 1:
         sl.check_overflow()
     facts = {"launches": s.launches - launches0, "graphs": s.graphs, "clocks": clk, "per_step": per_step,
              "agents_end": s.count("Circle")}
     if dist is not None:
-        t = torch.tensor([dev_total, wall], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([dev_total, wall, region], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_total, wall = float(t[0]), float(t[1])
+        dev_total, wall, region = float(t[0]), float(t[1]), float(t[2])
         dist.barrier()
+    facts["region"] = region
     s.close()
     return dev_total, wall, facts
 
@@ -493,8 +498,11 @@ def main():
             "fused_index_build": bool(args.fused_index), "bin_ordered_output": bool(args.ordered_output),
             "l2": "flushed between steps (256 MiB write outside the timed events)" if world == 1 else
                   "not flushed (the steps of neighbouring ranks are coupled by the exchange; per-GPU working set ~80 MB)",
-            "timing": "sum of per-step CUDA-event times on the simulation stream" if world == 1 else
-                      "CUDA events around the K-step region on the simulation stream (waits for neighbours included), max over ranks",
+            "timing": "sum of per-step CUDA-event times on the simulation stream (waits for neighbours happen inside a step and are included), "
+                      "max over ranks; the same clock at every N",
+            "region_ms_per_step": (facts["region"] / args.steps * 1e3) if world > 1 else None,
+            "region": "CUDA events around the whole K-step loop incl. the host's turn-around between steps, max over ranks (N=1: the loop also "
+                      "contains the L2 flushes, see wall_ms_per_step)",
             "wall_ms_per_step": wall / args.steps * 1e3,
             "ms_first_30_steps": float(ps[:30].mean() * 1e3) if len(ps) else None,
             "ms_last_30_steps": float(ps[-30:].mean() * 1e3) if len(ps) else None,
