@@ -24,9 +24,13 @@ Besides the contract's keys the line carries
   strong_scaling  the fixed 128 M-agent box on N GPUs
   parity_check  (N>1) one teacher-forced step of a 100 k-agents-per-GPU domain, slabs vs one GPU, before the timed region
 
-Timing: the agent state is resident in HBM; every step is timed with CUDA events recorded on the simulation's own
-stream (where its graph is launched); at 1 M agents the working set fits the 126 MB L2, so a 256 MiB buffer is written
-between steps, outside the events, to flush it.
+Timing: the agent state is resident in HBM; every step is timed with the CUDA event pair that CUDASimulation::step()
+records around it on the simulation's own stream (where its graph is launched; the analogue of the reference's
+getElapsedTimeSteps()).  `value` is K steps / (sum of a rank's per-step times, max over ranks) at every N: waits for
+neighbours (halo, migration, all-reduce) happen inside a step and count; what lies between two steps does not -- at N=1 the
+256 MiB write that flushes the 126 MB L2 (the 1 M-agent working set would otherwise stay cache resident), at every N the
+host's turn-around after the step function made it wait for the step.  The bracketed K-step region is printed next to it
+(config.region_ms_per_step, config.wall_ms_per_step).
 """
 from __future__ import annotations
 
