@@ -17,6 +17,7 @@ FGB_BUILD_DEFAULT = 0
 FGB_BUILD_STABLE = 1
 FGB_BUILD_TILE_LOCAL = 2
 FGB_BUILD_KEYS_READY = 4
+FGB_BUILD_EXPECT_GROUPED = 8
 FGB_REDUCE_SUM, FGB_REDUCE_MIN, FGB_REDUCE_MAX = 0, 1, 2
 FGB_F32, FGB_F64, FGB_I32, FGB_U32, FGB_I64, FGB_U64 = range(6)
 FGB_ERR_NO_DEVICE = -3

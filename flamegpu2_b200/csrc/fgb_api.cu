@@ -111,12 +111,16 @@ int launch_bin_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, co
 static_assert(kFsTile == kScanTile, "k_scan_scatter and scan_num_tiles() must agree on the scan tile size");
 template <bool IDX_ONLY>
 void launch_scan_scatter(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, const VarTable &vt, unsigned int *perm, bool vec,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool expect_grouped = false) {
   const unsigned int tiles = tile_grid(n), scan_tiles = scan_num_tiles(sp->bin_count);
   const uint32_t *keys = static_cast<const uint32_t *>(sp->keys.p);
   uint32_t *wl = static_cast<uint32_t *>(sp->tile_mode.p);
   k_scan_scatter<IDX_ONLY><<<scan_tiles + tiles, kBinThreads, 0, st>>>(sp->d_hist, sp->md.PBM, sp->bin_count, sp->d_state, scan_tiles, keys, n,
-                                                                       d_n, vt, perm, wl, sp->d_ctrl);
+                                                                       d_n, vt, perm, wl, sp->d_ctrl, expect_grouped ? 1u : 0u);
+  if (expect_grouped) {  // ungrouped tiles were scattered inside that launch: nothing is queued
+    sp->ctx->launches += 1;
+    return;
+  }
   const unsigned int sgrid = std::min<unsigned int>(tiles, 4u * kNumSMs);  // 46 KB of shared memory per block: 4 per SM
   if (vec)
     k_bin_scatter_staged<true, IDX_ONLY><<<sgrid, kBinThreads, 0, st>>>(keys, n, d_n, sp->md.PBM, vt, perm, wl, sp->d_ctrl);
@@ -137,7 +141,7 @@ int scatter_from_keys(fgb_spatial *sp, unsigned int n, const unsigned int *d_n, 
   const bool stable = (flags & FGB_BUILD_STABLE) != 0;
   uint32_t *perm = static_cast<uint32_t *>(sp->perm.p);
   if (!stable) {
-    launch_scan_scatter<false>(sp, n, d_n, vt, src_slot_out, vec, st);
+    launch_scan_scatter<false>(sp, n, d_n, vt, src_slot_out, vec, st, (flags & FGB_BUILD_EXPECT_GROUPED) != 0);
     return launch_ok();
   }
   launch_scan_scatter<true>(sp, n, d_n, vt, perm, true, st);

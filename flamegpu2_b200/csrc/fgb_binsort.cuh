@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kBinThreads, FGB_SCATTER_MIN_BLOCKS) k_scan_sc
                                                               unsigned long long *state, uint32_t scan_tiles,
                                                               const uint32_t *__restrict__ keys, uint32_t n_max,
                                                               const unsigned int *d_n, const __grid_constant__ VarTable vt,
-                                                              uint32_t *perm, uint32_t *worklist, uint32_t *ctrl) {
+                                                              uint32_t *perm, uint32_t *worklist, uint32_t *ctrl, uint32_t inline_ungrouped) {
   __shared__ uint32_t s_runs;
   __shared__ uint32_t s_scan[33];
   __shared__ uint32_t s_excl;
@@ -346,13 +346,26 @@ __global__ void __launch_bounds__(kBinThreads, FGB_SCATTER_MIN_BLOCKS) k_scan_sc
     if (threadIdx.x == 0)
       while (ld_acquire_u32(ctrl + 1) < scan_tiles) __nanosleep(40);
     __syncthreads();
-    if (!grouped && threadIdx.x == 0) worklist[atomicAdd(ctrl + 3, 1u)] = tile;
+    if (!grouped && !inline_ungrouped && threadIdx.x == 0) worklist[atomicAdd(ctrl + 3, 1u)] = tile;
   }
-  if (tile0 < n && grouped) {
+  if (tile0 < n && (grouped || inline_ungrouped)) {
     // claim: the first lane of every run adds the run's length to the bin's cursor.  All eight rounds' atomics are
     // issued before the first result is consumed (interleaved with the shuffles below, each round waited a full L2
     // round trip for its atomic before the next one was issued: 8 serial round trips per tile)
+    // (An ungrouped tile handled inline -- FGB_BUILD_EXPECT_GROUPED -- takes the same code: with almost every lane a run
+    // head it degenerates to one atomic and one scattered store per message, correct for any input.)
     uint32_t dst[kTileItems];
+    if (!IDX_ONLY && !grouped) {  // nothing was prefetched for this tile
+      cur4 = vt.n > 0 && vt.len[0] == 4;
+      if (cur4) {
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(vt.in[0]);
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) {
+          const uint32_t i = w0 + r * 32u + lane;
+          if (i < n) cur[r] = ld_stream_u32(in + i);
+        }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
       const uint32_t i = w0 + r * 32u + lane;

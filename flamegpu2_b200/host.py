@@ -231,9 +231,11 @@ class Spatial:
         _check(lib().fgb_bin_permutation(self.h, n, _ptr(d_n), _ptr(x), _ptr(y), _ptr(z), _ptr(perm_out), flags, _stream_ptr()),
                "fgb_bin_permutation")
 
-    def build_index(self, x, y, z, ins, outs, n: int, *, stable=False, d_n=None):
+    def build_index(self, x, y, z, ins, outs, n: int, *, stable=False, d_n=None, expect_grouped=False):
         arr, nv = make_vars(ins, outs)
         flags = _capi.FGB_BUILD_STABLE if stable else _capi.FGB_BUILD_DEFAULT
+        if expect_grouped:
+            flags |= _capi.FGB_BUILD_EXPECT_GROUPED
         _check(lib().fgb_build_index(self.h, n, _ptr(d_n), _ptr(x), _ptr(y), _ptr(z), arr, nv, flags, _stream_ptr()),
                "fgb_build_index")
 

@@ -304,6 +304,7 @@ struct CUDAMessage {
   bool keyed_by_writer = false;      // keys + histogram exist for the first *keyed_slot items
   bool appended_after_keyed = false; // ... and more items were appended since (they are keyed by the build)
   bool hist_dirty = false;           // the histogram holds counts that no build has consumed yet
+  bool written_bin_ordered = false;  // the writer ran in bin order (slot == thread): the build may expect grouped tiles
   unsigned int keyed_slot = 0;       // control word: number of items keyed by the writer
   int win_begin = 0, win_count = -1;  // slab window (planes of the slowest axis held by this process)
 };

@@ -518,7 +518,8 @@ inline std::vector<unsigned long long> CUDASimulation::snapshot_host_state() con
   for (const auto &m : messages) {
     put_list(m.second.list);
     s.push_back((m.second.pbm_dirty ? 1ull : 0ull) | (m.second.truncate ? 2ull : 0ull) | (m.second.keyed_by_writer ? 4ull : 0ull) |
-                (m.second.appended_after_keyed ? 8ull : 0ull) | (m.second.hist_dirty ? 16ull : 0ull));
+                (m.second.appended_after_keyed ? 8ull : 0ull) | (m.second.hist_dirty ? 16ull : 0ull) |
+                (m.second.written_bin_ordered ? 32ull : 0ull));
   }
   return s;
 }
@@ -547,6 +548,7 @@ inline void CUDASimulation::restore_host_state(const std::vector<unsigned long l
     m.second.truncate = (f & 2ull) != 0;
     m.second.keyed_by_writer = (f & 4ull) != 0;
     m.second.appended_after_keyed = (f & 8ull) != 0;
+    m.second.written_bin_ordered = (f & 32ull) != 0;
     m.second.hist_dirty = (f & 16ull) != 0;
   }
 }
@@ -953,12 +955,14 @@ inline void CUDASimulation::run_function(detail::FunctionRT &f, cudaStream_t st,
         O.appended_after_keyed = false;
         O.hist_dirty = true;
       }
+      O.written_bin_ordered = a.slot_by_thread != 0;
     } else {
       std::vector<fgb_var> vars = O.list.vars(false);
       FGB_ABI_THROW(fgb_compact(ctx, sid, nullptr, 0, n, d_exec, n, 0, d_mc, vars.data(), static_cast<unsigned int>(vars.size()), nullptr,
                                 d_mc, st));
       O.list.bound += n;
     }
+    if (fn.message_output_optional || !O.truncate) O.written_bin_ordered = false;
     if (!a.out_keys) {
       if (O.truncate) O.keyed_by_writer = false;      // a plain (unfused) rewrite of the list
       else if (O.keyed_by_writer) O.appended_after_keyed = true;  // the appended items are keyed by the build
@@ -1087,6 +1091,9 @@ inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream
     const int ix = M.list.index_of("x"), iy = M.list.index_of("y"), iz = M.desc->dims() == 3 ? M.list.index_of("z") : -1;
     unsigned int flags = cuda_config.stableMessageOrder ? FGB_BUILD_STABLE : FGB_BUILD_DEFAULT;
     if (M.keyed_by_writer) flags |= FGB_BUILD_KEYS_READY;
+    // written in bin order: the few tiles that are not grouped (fast movers, appended ghosts) are scattered inside the scan +
+    // scatter launch and the worklist launch is saved
+    if (M.keyed_by_writer && M.written_bin_ordered && !cuda_config.stableMessageOrder) flags |= FGB_BUILD_EXPECT_GROUPED;
     FGB_ABI_THROW(fgb_build_index_ex(M.spatial, M.list.bound, slot_ptr(M.list.count_slot), reinterpret_cast<const float *>(M.list.data[ix]),
                                      reinterpret_cast<const float *>(M.list.data[iy]),
                                      iz >= 0 ? reinterpret_cast<const float *>(M.list.data[iz]) : nullptr, vars.data(),
@@ -1096,6 +1103,7 @@ inline void CUDASimulation::build_input_index(detail::CUDAMessage &M, cudaStream
     prof_end(st);
   }
   M.keyed_by_writer = false;  // the sorted list has new slots; the histogram was consumed (and re-zeroed) by the scan
+  M.written_bin_ordered = false;
   M.appended_after_keyed = false;
   M.hist_dirty = false;
   M.pbm_dirty = false;

@@ -137,7 +137,12 @@ enum fgb_build_flags {
   FGB_BUILD_TILE_LOCAL = 2,
   /* fgb_build_index_ex only: the bin key of the leading items and their histogram contribution were already written
    * by the list's writer (fgb_spatial_writer_args); see fgb_build_index_ex */
-  FGB_BUILD_KEYS_READY = 4
+  FGB_BUILD_KEYS_READY = 4,
+  /* The caller expects the list to arrive (nearly) bin-grouped -- its writer ran in bin order.  The build then handles
+   * the few tiles that are not grouped inside the scan + scatter launch itself (one atomic and one scattered store per
+   * message: correct for any input, cheap only when such tiles are rare) and the launch that walks the worklist of
+   * unordered tiles is not issued.  Ignored with FGB_BUILD_STABLE. */
+  FGB_BUILD_EXPECT_GROUPED = 8
 };
 
 /* MessageSpatial3D::CUDAModelHandler::buildIndex (MessageSpatial3D.cu:113-146) and

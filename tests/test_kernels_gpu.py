@@ -33,7 +33,7 @@ def _positions(n, lo, hi, seed, sorted_like=False, dims=3):
     return p
 
 
-def _check_build(ctx, dims, mn, mx, radius, pos, stable, extra_len=0):
+def _check_build(ctx, dims, mn, mx, radius, pos, stable, extra_len=0, expect_grouped=False):
     from flamegpu2_b200 import host
 
     n = len(pos[0])
@@ -52,7 +52,7 @@ def _check_build(ctx, dims, mn, mx, radius, pos, stable, extra_len=0):
     ins = [t(host_vars[k]) for k in names]
     outs = [torch.zeros_like(a) for a in ins]
     zt = ins[names.index("z")] if dims == 3 else None
-    sp.build_index(ins[names.index("x")], ins[names.index("y")], zt, ins, outs, n, stable=stable)
+    sp.build_index(ins[names.index("x")], ins[names.index("y")], zt, ins, outs, n, stable=stable, expect_grouped=expect_grouped)
     torch.cuda.synchronize()
     pbm = sp.pbm()
     pbm_ref, perm_ref = g.build_index(pos[0], pos[1], pos[2] if dims == 3 else None)
@@ -71,6 +71,37 @@ def _check_build(ctx, dims, mn, mx, radius, pos, stable, extra_len=0):
     for k, o in zip(names, outs):
         hv = host_vars[k]
         assert np.array_equal(o.cpu().numpy().view(hv.dtype).reshape(hv.shape), hv[got_id]), k
+    sp.close()
+
+
+@pytest.mark.parametrize("dims", [3, 2])
+@pytest.mark.parametrize("order", ["random", "bin_sorted", "mixed"])
+@pytest.mark.parametrize("n", [1, 2049, 300007])
+def test_build_index_expect_grouped_is_correct_for_any_order(ctx, n, order, dims):
+    # FGB_BUILD_EXPECT_GROUPED is a performance hint: tiles that are NOT grouped are scattered inside the scan + scatter
+    # launch (one atomic per message) instead of by the worklist launch; the result must be the same for any input order
+    mn, mx, radius = [0.0] * dims, [30.0, 22.0, 17.0][:dims], 1.5
+    pos = _positions(n, mn, mx, seed=7 * n + dims, dims=dims)
+    if order != "random":
+        g = orc.Grid(dims, mn, mx, radius)
+        keys = g.bin_keys(pos[0], pos[1], pos[2] if dims == 3 else None)
+        o = np.argsort(keys, kind="stable")
+        if order == "mixed":  # half of the list bin-ordered, the rest behind it in random order (like ghosts appended by a halo)
+            rest = np.arange(n)[np.isin(np.arange(n), o[: n // 2], invert=True)]
+            o = np.concatenate([o[: n // 2], rest])
+        pos = [p[o].copy() for p in pos]
+    _check_build(ctx, dims, mn, mx, radius, pos, False, expect_grouped=True)
+    # and repeated on one handler: the look-back words, counters and histogram come back clean without the worklist launch
+    from flamegpu2_b200 import host
+
+    g = orc.Grid(dims, mn, mx, radius)
+    sp = host.Spatial(ctx, dims, mn, mx, radius)
+    ins = [t(p) for p in pos]
+    outs = [torch.zeros_like(a) for a in ins]
+    pbm_ref, _ = g.build_index(pos[0], pos[1], pos[2] if dims == 3 else None)
+    for k in range(3):
+        sp.build_index(ins[0], ins[1], ins[2] if dims == 3 else None, ins, outs, n, expect_grouped=(k != 1))
+        assert np.array_equal(sp.pbm(), pbm_ref)
     sp.close()
 
 
