@@ -549,8 +549,8 @@ def main():
         traffic = committed_json("ncu_traffic.json")
         bi_us = phases.get("build_index")
         if bi_us:
-            line["roofline"] = roofline_entry("buildIndex in-step: k_scan_scatter (scan + scatter in one launch) + k_bin_scatter_staged over the worklist of "
-                                              "unordered tiles (empty for a bin-ordered list); bin keys and histogram are published by the output function", alg, bi_us, peak, peak_src,
+            line["roofline"] = roofline_entry("buildIndex in-step: k_scan_scatter (scan + scatter of every tile in ONE launch); bin keys and histogram are "
+                                              "published by the output function", alg, bi_us, peak, peak_src,
                                               traffic=traffic.get("build_index", {}).get(str(n)))
         line["phases_us"] = phases
         rl = {}

@@ -131,10 +131,10 @@ def main():
             ins = [ids, pos[0].contiguous(), pos[1].contiguous(), pos[2].contiguous()]
             outs = [torch.empty_like(a) for a in ins]
             alg = n * 2 * 16 + 4 * (sp.bin_count + 1)
-            for stable in (False, True):
-                med, best = timed(lambda: sp.build_index(ins[1], ins[2], ins[3], ins, outs, n, stable=stable),
+            for stable, expect in ((False, False), (False, True), (True, False)):
+                med, best = timed(lambda: sp.build_index(ins[1], ins[2], ins[3], ins, outs, n, stable=stable, expect_grouped=expect),
                                   reps=args.reps, flush=flush)
-                print(json.dumps({"op": "build_index", "n": n, "bins": sp.bin_count, "stable": stable,
+                print(json.dumps({"op": "build_index", "n": n, "bins": sp.bin_count, "stable": stable, "expect_grouped": expect,
                                   "input": "bin-sorted+jitter" if sorted_like else "random", "us_median": med,
                                   "us_best": best, "alg_bytes": alg, "GBps": alg / med / 1e3,
                                   "frac_of_measured_peak": alg / med / 1e3 / peak}), flush=True)
