@@ -2,13 +2,14 @@
 // agent sort (fgb_sort_by_key): key histogram, cursor scatter, per-bin order fix-up, gather.
 //
 // Pipeline (every arrow is one kernel launch; nothing returns to the host):
-//   keys -> k_*_hist (RLE-aggregated RED atomics into a clean histogram)
-//        -> k_exclusive_scan (shift=1: cursor[k+1] = start of bin k; histogram re-zeroed)
-//        -> k_*_scatter (dst = atomicAdd(&cursor[k+1], run) ; afterwards cursor[] IS the prefix
-//                        array, i.e. the PBM -- no separate cursor array, no second memset)
-//   default order : the scatter moves the payload directly (arrival order inside a bin)
-//   stable order  : the scatter writes source indices, k_fix_* sorts each bin's indices
-//                   ascending (== source order), k_gather applies the permutation.
+//   keys -> k_bin_keys (bin key of every item stored once, RLE-aggregated RED atomics into a clean histogram; inside a
+//           simulation step the list's writer publishes both and this launch does not exist)
+//        -> k_scan_scatter: blocks [0,S) scan the histogram (shift=1: cursor[k+1] = start of bin k; histogram re-zeroed),
+//           blocks [S,S+T) scatter one 2048-item tile each (dst = atomicAdd(&cursor[k+1], run); afterwards cursor[] IS
+//           the prefix array, i.e. the PBM -- no separate cursor array, no second memset)
+//   default order : the scatter moves the payload directly (arrival order inside a bin), any input order
+//   stable order  : the scatter writes source indices (unordered tiles through k_bin_scatter_staged), k_fix_* sorts
+//                   each bin's indices ascending (== source order), k_gather applies the permutation.
 #pragma once
 #include "fgb_common.cuh"
 
